@@ -1,0 +1,133 @@
+/* rs_retriever.h - C ABI of the B200-native similarity + top-k backend.
+ *
+ * This is the drop-in boundary for the one hot path of ngray0/RAG-Serving-System: the work that
+ * rag_service/core/retriever.py does through CuPy.  Each entry point names the reference
+ * interface it replaces (file:line relative to the reference checkout).  The reference is pure
+ * Python, so the binding a maintainer adds is a ctypes stub; the signatures use
+ * plain pointers and sizes only - no torch, no Python.h, no C++ types.
+ *
+ * Conventions: every function returns 0 on success and a negative RS_E_* code on failure; the
+ * message is available from rs_last_error() (thread-local).  No function ever falls back to a
+ * CPU computation: without a usable sm_100a device rs_create fails.
+ * Result ordering everywhere: score descending, ties broken by the LOWER index.
+ */
+#ifndef RS_RETRIEVER_H_
+#define RS_RETRIEVER_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RS_API __attribute__((visibility("default")))
+#else
+#define RS_API
+#endif
+
+/* storage dtype of the corpus on device (the reference stores fp32 only, retriever.py:576-578) */
+#define RS_DTYPE_BF16 0
+#define RS_DTYPE_FP16 1
+#define RS_DTYPE_FP32 2 /* kept as two fp16 planes (hi + lo*2^-11): 4 B/element, ~2^-22 relative */
+
+/* similarity: RS_METRIC_DOT = SimpleRetriever (retriever.py:112);
+ * RS_METRIC_COSINE = CupyRetriever.distance_cosine (retriever.py:594-611): dot/(|q||d|+1e-8), clipped */
+#define RS_METRIC_DOT 0
+#define RS_METRIC_COSINE 1
+
+#define RS_OK 0
+#define RS_E_INVALID (-1)   /* bad argument */
+#define RS_E_CUDA (-2)      /* CUDA runtime error (message has the cudaError string) */
+#define RS_E_STATE (-3)     /* call out of order (e.g. search before finalize) */
+#define RS_E_UNSUPPORTED (-4) /* device is not sm_100 / shape outside kernel limits */
+
+typedef struct rs_index rs_index;
+
+typedef struct rs_config {
+  int32_t struct_size; /* = sizeof(rs_config) */
+  int32_t device;      /* CUDA device ordinal that owns this shard */
+  int64_t n_rows;      /* documents in THIS shard (N_A of retriever.py:590 for one GPU) */
+  int64_t row_offset;  /* global index of local row 0; added to every returned index */
+  int32_t dim;         /* embedding dimension D (retriever.py:591), multiple of 64, <= 4096 */
+  int32_t dtype;       /* RS_DTYPE_* storage type */
+  int32_t scale_exp;   /* RS_DTYPE_FP32 only: rows are multiplied by 2^scale_exp before the fp16 split */
+  int32_t max_batch;   /* largest B a search call may pass */
+  int32_t max_k;       /* largest k a search call may pass */
+  int32_t reserved;
+} rs_config;
+
+typedef struct rs_stats {
+  int32_t struct_size;
+  int32_t sm_count;         /* SMs on the device */
+  int32_t grid;             /* CTAs of the last fused kernel */
+  int32_t stages;           /* depth of its bulk-copy ring */
+  int32_t smem_bytes;       /* its dynamic shared memory */
+  int32_t passes;           /* query sub-batches the last search needed */
+  int32_t launches;         /* kernels launched by the last search (prep + fused + merge per pass) */
+  int32_t query_terms;      /* 1 or 2 */
+  int64_t bytes_streamed;   /* corpus bytes read by the last search (passes * shard bytes) */
+  int64_t corpus_bytes;     /* device bytes of the tiled corpus image */
+  int64_t total_launches;   /* kernels launched since rs_create */
+} rs_stats;
+
+RS_API int rs_version(void);
+RS_API const char* rs_last_error(void);
+
+/* Replaces CupyRetriever.__init__'s device allocation (retriever.py:580-586). Allocates the
+ * tiled corpus image, norms and all per-call workspaces. */
+RS_API int rs_create(const rs_config* cfg, rs_index** out);
+RS_API int rs_destroy(rs_index* ix);
+
+/* Replaces cp.asarray(doc_embeddings) (retriever.py:582): chunked ingest of host rows
+ * [row0, row0+nrows) (local numbering), row-major, src_dtype = RS_DTYPE_FP32 (float) or
+ * RS_DTYPE_BF16 / RS_DTYPE_FP16 (uint16 bit patterns).  Converts to the storage dtype, writes
+ * the tiled image and the document norms (computed ONCE here; the reference recomputes them on
+ * every call, retriever.py:603). */
+RS_API int rs_load_rows(rs_index* ix, const void* host_rows, int32_t src_dtype, int64_t row0, int64_t nrows);
+
+/* Fill the shard with the synthetic unit-normalised corpus (oracle: retrieval_oracle.synth_rows);
+ * local row i is global row global_row0 + i, so any sharding reproduces the same corpus. */
+RS_API int rs_fill_synthetic(rs_index* ix, uint64_t seed, int64_t global_row0);
+
+/* Must be called after the last load/fill and before the first search. */
+RS_API int rs_finalize(rs_index* ix);
+
+/* Replaces the body of CupyRetriever.batch_retrieve between the H2D copy and the D2H copy
+ * (retriever.py:736-773): scores + per-row top-k for B queries.  HOST buffers; blocking.
+ *   q_host      float[B*dim], row-major (batch_processor.py:92 hands exactly this)
+ *   metric      RS_METRIC_*
+ *   query_terms 1 = queries rounded to the storage dtype; 2 = exact hi+lo split (fp32 storage
+ *               always uses 2)
+ *   out_idx     int64[B*k]  global indices, -1 padding when the shard has < k rows (:767-769)
+ *   out_score   float[B*k]  matching scores, -inf padding */
+RS_API int rs_search(rs_index* ix, const float* q_host, int32_t B, int32_t k, int32_t metric, int32_t query_terms,
+              int64_t* out_idx, float* out_score);
+
+/* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t passed as void*; NULL =
+ * the legacy default stream).  This is the per-GPU step of the sharded search; the outputs are
+ * the B x k candidates that the NCCL all-gather exchanges. */
+RS_API int rs_search_device(rs_index* ix, const float* q_dev, int32_t B, int32_t k, int32_t metric, int32_t query_terms,
+                     int64_t* out_idx_dev, float* out_score_dev, void* stream);
+
+/* Final merge of n_lists sorted candidate lists per query (the multi-GPU step):
+ * scores_dev/idx_dev are [n_lists][B][kc] device arrays as produced by an all-gather of
+ * rs_search_device outputs; writes the global top-k [B][k]. */
+RS_API int rs_merge_device(int32_t device, const float* scores_dev, const int64_t* idx_dev, int32_t n_lists, int32_t B,
+                    int32_t kc, int32_t k, int64_t* out_idx_dev, float* out_score_dev, void* stream);
+
+/* Read back the represented values of rows [row0,row0+nrows) as float (inverse of the tiling);
+ * used by the tests (ingest round trip) and by the CPU-baseline sampler. */
+RS_API int rs_get_rows(rs_index* ix, int64_t row0, int64_t nrows, float* out_host);
+RS_API int rs_get_norms(rs_index* ix, int64_t row0, int64_t nrows, float* out_host);
+/* Raw tiled image bytes [off, off+nbytes) - layout tests compare them bit-exactly with the oracle. */
+RS_API int rs_get_image(rs_index* ix, int64_t off, int64_t nbytes, void* out_host);
+
+RS_API int rs_get_stats(rs_index* ix, rs_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RS_RETRIEVER_H_ */

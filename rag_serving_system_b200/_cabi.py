@@ -1,0 +1,180 @@
+"""ctypes binding of include/rs_retriever.h (the C-ABI drop-in boundary).
+
+There is no fallback: if the shared library is missing or a call fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+DTYPE_BF16, DTYPE_FP16, DTYPE_FP32 = 0, 1, 2
+METRIC_DOT, METRIC_COSINE = 0, 1
+DTYPES = {"bf16": DTYPE_BF16, "fp16": DTYPE_FP16, "fp32": DTYPE_FP32}
+METRICS = {"dot": METRIC_DOT, "cosine": METRIC_COSINE}
+
+EXPORTS = (
+    "rs_version", "rs_last_error", "rs_create", "rs_destroy", "rs_load_rows", "rs_fill_synthetic",
+    "rs_finalize", "rs_search", "rs_search_device", "rs_merge_device", "rs_get_rows",
+    "rs_get_norms", "rs_get_image", "rs_get_stats",
+)
+
+
+class RsError(RuntimeError):
+    pass
+
+
+class rs_config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("device", C.c_int32), ("n_rows", C.c_int64),
+        ("row_offset", C.c_int64), ("dim", C.c_int32), ("dtype", C.c_int32),
+        ("scale_exp", C.c_int32), ("max_batch", C.c_int32), ("max_k", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class rs_stats(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("sm_count", C.c_int32), ("grid", C.c_int32),
+        ("stages", C.c_int32), ("smem_bytes", C.c_int32), ("passes", C.c_int32),
+        ("launches", C.c_int32), ("query_terms", C.c_int32), ("bytes_streamed", C.c_int64),
+        ("corpus_bytes", C.c_int64), ("total_launches", C.c_int64),
+    ]
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load librs_retriever.so (building it in-tree first if nvcc is present and it is stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        path = _build.build()
+    if not os.path.exists(path):
+        raise RsError(f"{path} is missing: run `python -m rag_serving_system_b200.build`; "
+                      "there is no CPU fallback")
+    lib = C.CDLL(path)
+    vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+    lib.rs_version.restype = C.c_int
+    lib.rs_last_error.restype = C.c_char_p
+    sigs = {
+        "rs_create": [C.POINTER(rs_config), C.POINTER(vp)],
+        "rs_destroy": [vp],
+        "rs_load_rows": [vp, vp, i32, i64, i64],
+        "rs_fill_synthetic": [vp, u64, i64],
+        "rs_finalize": [vp],
+        "rs_search": [vp, vp, i32, i32, i32, i32, vp, vp],
+        "rs_search_device": [vp, vp, i32, i32, i32, i32, vp, vp, vp],
+        "rs_merge_device": [i32, vp, vp, i32, i32, i32, i32, vp, vp, vp],
+        "rs_get_rows": [vp, i64, i64, vp],
+        "rs_get_norms": [vp, i64, i64, vp],
+        "rs_get_image": [vp, i64, i64, vp],
+        "rs_get_stats": [vp, C.POINTER(rs_stats)],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().rs_last_error().decode("utf-8", "replace")
+        raise RsError(f"{what} failed (code {rc}): {msg}")
+
+
+class Index:
+    """Owner of one device shard (thin, explicit wrapper over the C ABI)."""
+
+    def __init__(self, n_rows: int, dim: int, dtype: str = "bf16", device: int = 0, row_offset: int = 0,
+                 max_batch: int = 256, max_k: int = 128, scale_exp: int = 0):
+        self.lib = load()
+        self.n_rows, self.dim, self.dtype, self.device = int(n_rows), int(dim), dtype, int(device)
+        self.row_offset, self.max_batch, self.max_k = int(row_offset), int(max_batch), int(max_k)
+        cfg = rs_config(C.sizeof(rs_config), device, n_rows, row_offset, dim, DTYPES[dtype], scale_exp,
+                        max_batch, max_k, 0)
+        h = C.c_void_p()
+        check(self.lib.rs_create(C.byref(cfg), C.byref(h)), "rs_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rs_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # ---- ingest
+    def load_rows(self, rows: np.ndarray, row0: int = 0, src_dtype: str | None = None):
+        rows = np.ascontiguousarray(rows)
+        if src_dtype is None:
+            if rows.dtype == np.float32:
+                src_dtype = "fp32"
+            elif rows.dtype == np.float16:
+                src_dtype = "fp16"
+            else:
+                raise RsError(f"load_rows: pass float32/float16 rows or uint16 bits with src_dtype (got {rows.dtype})")
+        assert rows.ndim == 2 and rows.shape[1] == self.dim
+        check(self.lib.rs_load_rows(self.h, rows.ctypes.data, DTYPES[src_dtype], row0, rows.shape[0]), "rs_load_rows")
+
+    def fill_synthetic(self, seed: int, global_row0: int | None = None):
+        g0 = self.row_offset if global_row0 is None else global_row0
+        check(self.lib.rs_fill_synthetic(self.h, seed, g0), "rs_fill_synthetic")
+
+    def finalize(self):
+        check(self.lib.rs_finalize(self.h), "rs_finalize")
+
+    # ---- search
+    def search(self, q: np.ndarray, k: int, metric: str = "dot", query_terms: int = 1):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        B = q.shape[0]
+        idx = np.empty((B, k), dtype=np.int64)
+        sc = np.empty((B, k), dtype=np.float32)
+        check(self.lib.rs_search(self.h, q.ctypes.data, B, k, METRICS[metric], query_terms, idx.ctypes.data,
+                                 sc.ctypes.data), "rs_search")
+        return idx, sc
+
+    def search_device(self, q_ptr: int, B: int, k: int, out_idx_ptr: int, out_score_ptr: int, metric: str = "dot",
+                      query_terms: int = 1, stream: int = 0):
+        check(self.lib.rs_search_device(self.h, q_ptr, B, k, METRICS[metric], query_terms, out_idx_ptr,
+                                        out_score_ptr, stream), "rs_search_device")
+
+    # ---- introspection
+    def get_rows(self, row0: int, nrows: int) -> np.ndarray:
+        out = np.empty((nrows, self.dim), dtype=np.float32)
+        check(self.lib.rs_get_rows(self.h, row0, nrows, out.ctypes.data), "rs_get_rows")
+        return out
+
+    def get_norms(self, row0: int, nrows: int) -> np.ndarray:
+        out = np.empty(nrows, dtype=np.float32)
+        check(self.lib.rs_get_norms(self.h, row0, nrows, out.ctypes.data), "rs_get_norms")
+        return out
+
+    def get_image(self, off: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        check(self.lib.rs_get_image(self.h, off, nbytes, out.ctypes.data), "rs_get_image")
+        return out
+
+    def stats(self) -> dict:
+        st = rs_stats()
+        st.struct_size = C.sizeof(rs_stats)
+        check(self.lib.rs_get_stats(self.h, C.byref(st)), "rs_get_stats")
+        return {f: getattr(st, f) for f, _ in rs_stats._fields_}
+
+
+def merge_device(device: int, scores_ptr: int, idx_ptr: int, n_lists: int, B: int, kc: int, k: int,
+                 out_idx_ptr: int, out_score_ptr: int, stream: int = 0):
+    check(load().rs_merge_device(device, scores_ptr, idx_ptr, n_lists, B, kc, k, out_idx_ptr, out_score_ptr, stream),
+          "rs_merge_device")

@@ -1,0 +1,413 @@
+// C-ABI host side of the retriever backend (include/rs_retriever.h).  Owns all device memory,
+// plans the per-call launch sequence (query prep -> fused score+select -> candidate merge) and
+// never computes a result on the CPU.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+
+#include "../../include/rs_retriever.h"
+#include "rs_kernels.h"
+#include "rs_layout.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define RS_CUDA(expr)                                                                             \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(RS_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+constexpr int kMaxSmem = 232448;  // 227 KiB opt-in dynamic shared memory per CTA on sm_100
+constexpr int kMinStages = 4;
+constexpr int kMaxStages = 24;
+constexpr int64_t kIngestChunkBytes = 64ll << 20;
+
+struct Plan {
+  int per_pass;  // queries per fused launch
+  int passes;
+  int bpad;
+  int stages;
+};
+
+}  // namespace
+
+struct rs_index {
+  rs_config cfg;
+  int sm_count = 0;
+  int kc = 0, planes = 1, n_tiles = 0;
+  int plane_dtype = RS_DTYPE_BF16;
+  size_t tile_bytes = 0, corpus_bytes = 0;
+  uint8_t* corpus = nullptr;
+  float* dnorm = nullptr;
+  float2* minmax = nullptr;
+  bool finalized = false;
+  // workspaces
+  uint8_t* qimg = nullptr;
+  float* qnorm = nullptr;
+  float* qscale = nullptr;
+  float* cand_score = nullptr;
+  int* cand_idx = nullptr;
+  float* q_dev = nullptr;           // staging for host queries
+  long long* out_idx_dev = nullptr;  // staging for host outputs
+  float* out_score_dev = nullptr;
+  void* ingest_dev = nullptr;
+  void* pinned = nullptr;  // pinned host staging (queries in, results out, ingest chunks)
+  size_t pinned_bytes = 0;
+  cudaStream_t stream = nullptr;
+  rs_stats stats;
+  std::mutex mu;
+};
+
+namespace {
+
+int max_cap_rows(int kc, int terms, int k) {
+  // largest bpad (multiple of 8, <= 128) that leaves at least kMinStages ring slots
+  int best = 0;
+  for (int bpad = 8; bpad <= 128; bpad += 8) {
+    if (rs::fused_smem_bytes(bpad, kc, terms, kMinStages, k) <= kMaxSmem) best = bpad;
+  }
+  return best;
+}
+
+int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
+  const int cap = max_cap_rows(ix->kc, terms, k);
+  if (cap <= 0) return fail(RS_E_UNSUPPORTED, "k=%d with dim=%d does not fit in shared memory", k, ix->cfg.dim);
+  pl->passes = (B + cap - 1) / cap;
+  pl->per_pass = (B + pl->passes - 1) / pl->passes;
+  pl->bpad = (pl->per_pass + 7) / 8 * 8;
+  int stages = kMinStages;
+  while (stages < kMaxStages && rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages + 1, k) <= kMaxSmem) ++stages;
+  pl->stages = stages;
+  return RS_OK;
+}
+
+void free_all(rs_index* ix) {
+  cudaSetDevice(ix->cfg.device);
+  cudaFree(ix->corpus);
+  cudaFree(ix->dnorm);
+  cudaFree(ix->minmax);
+  cudaFree(ix->qimg);
+  cudaFree(ix->qnorm);
+  cudaFree(ix->qscale);
+  cudaFree(ix->cand_score);
+  cudaFree(ix->cand_idx);
+  cudaFree(ix->q_dev);
+  cudaFree(ix->out_idx_dev);
+  cudaFree(ix->out_score_dev);
+  cudaFree(ix->ingest_dev);
+  if (ix->pinned) cudaFreeHost(ix->pinned);
+  if (ix->stream) cudaStreamDestroy(ix->stream);
+}
+
+// one search on device buffers; all launches go to `stream`
+int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int metric, int terms, long long* out_idx,
+                         float* out_score, cudaStream_t stream) {
+  if (!ix->finalized) return fail(RS_E_STATE, "rs_finalize has not been called");
+  if (B <= 0 || B > ix->cfg.max_batch) return fail(RS_E_INVALID, "B=%d outside [1,%d]", B, ix->cfg.max_batch);
+  if (k <= 0 || k > ix->cfg.max_k) return fail(RS_E_INVALID, "k=%d outside [1,%d]", k, ix->cfg.max_k);
+  if (metric != RS_METRIC_DOT && metric != RS_METRIC_COSINE) return fail(RS_E_INVALID, "bad metric %d", metric);
+  if (ix->planes == 2) terms = 2;
+  if (terms != 1 && terms != 2) return fail(RS_E_INVALID, "query_terms must be 1 or 2");
+  Plan pl;
+  int rc = make_plan(ix, B, k, terms, &pl);
+  if (rc != RS_OK) return rc;
+  const int grid = std::min(ix->sm_count, ix->n_tiles);
+  ix->stats.grid = grid;
+  ix->stats.stages = pl.stages;
+  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, k);
+  ix->stats.passes = pl.passes;
+  ix->stats.query_terms = terms;
+  ix->stats.launches = 0;
+  ix->stats.bytes_streamed = 0;
+  for (int pass = 0; pass < pl.passes; ++pass) {
+    const int b0 = pass * pl.per_pass;
+    const int nb = std::min(pl.per_pass, B - b0);
+    RS_CUDA(rs::launch_query_prep(q_dev + (size_t)b0 * ix->cfg.dim, nb, ix->cfg.dim, pl.bpad, ix->plane_dtype, terms,
+                                  ix->planes == 2 ? ix->cfg.scale_exp : 0, ix->qimg, ix->qnorm, ix->qscale, stream));
+    rs::SearchParams p;
+    p.corpus = ix->corpus;
+    p.qimg = ix->qimg;
+    p.qnorm = ix->qnorm;
+    p.qscale = ix->qscale;
+    p.dnorm = ix->dnorm;
+    p.tile_norm_minmax = ix->minmax;
+    p.cand_score = ix->cand_score;
+    p.cand_idx = ix->cand_idx;
+    p.n_rows = (int)ix->cfg.n_rows;
+    p.n_tiles = ix->n_tiles;
+    p.n_queries = nb;
+    p.kc = ix->kc;
+    p.planes = ix->planes;
+    p.terms = terms;
+    p.bpad = pl.bpad;
+    p.k = k;
+    p.metric = metric;
+    p.dtype = ix->plane_dtype;
+    p.stages = pl.stages;
+    p.lo_coef = ix->plane_dtype == RS_DTYPE_FP16 ? ldexpf(1.0f, -RS_FP16_SPLIT_SHIFT) : 1.0f;
+    RS_CUDA(rs::launch_fused_search(p, grid, stream));
+    RS_CUDA(rs::launch_merge_i32(ix->cand_score, ix->cand_idx, grid, nb, k, k, ix->cfg.row_offset,
+                                 out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, stream));
+    ix->stats.launches += 3;
+    ix->stats.bytes_streamed += (int64_t)ix->corpus_bytes;
+  }
+  ix->stats.total_launches += ix->stats.launches;
+  return RS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+RS_API int rs_version(void) { return RS_ABI_VERSION; }
+RS_API const char* rs_last_error(void) { return g_err; }
+
+RS_API int rs_create(const rs_config* cfg, rs_index** out) {
+  if (!cfg || !out) return fail(RS_E_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->struct_size != (int32_t)sizeof(rs_config)) return fail(RS_E_INVALID, "rs_config.struct_size mismatch");
+  if (cfg->n_rows <= 0 || cfg->n_rows > 0x7fffff00ll) return fail(RS_E_INVALID, "n_rows=%lld out of range", (long long)cfg->n_rows);
+  if (cfg->dim <= 0 || cfg->dim % 64 != 0 || cfg->dim > 4096) return fail(RS_E_INVALID, "dim=%d must be a multiple of 64 in [64,4096]", cfg->dim);
+  if (cfg->dtype < RS_DTYPE_BF16 || cfg->dtype > RS_DTYPE_FP32) return fail(RS_E_INVALID, "bad dtype %d", cfg->dtype);
+  if (cfg->max_batch <= 0 || cfg->max_batch > 65536) return fail(RS_E_INVALID, "bad max_batch %d", cfg->max_batch);
+  if (cfg->max_k <= 0 || cfg->max_k > 1024) return fail(RS_E_INVALID, "max_k=%d outside [1,1024]", cfg->max_k);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(RS_E_CUDA, "no CUDA device available (%s); this backend has no CPU fallback", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(RS_E_INVALID, "device %d of %d", cfg->device, ndev);
+  RS_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  RS_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(RS_E_UNSUPPORTED, "device %d is sm_%d%d; the kernels are sm_100a only", cfg->device, prop.major, prop.minor);
+
+  rs_index* ix = new (std::nothrow) rs_index();
+  if (!ix) return fail(RS_E_INVALID, "out of host memory");
+  ix->cfg = *cfg;
+  ix->sm_count = prop.multiProcessorCount;
+  ix->kc = cfg->dim / RS_KCHUNK_ELEMS;
+  ix->planes = cfg->dtype == RS_DTYPE_FP32 ? 2 : 1;
+  ix->plane_dtype = cfg->dtype == RS_DTYPE_BF16 ? RS_DTYPE_BF16 : RS_DTYPE_FP16;
+  ix->n_tiles = (int)((cfg->n_rows + RS_TILE_ROWS - 1) / RS_TILE_ROWS);
+  ix->tile_bytes = (size_t)ix->planes * ix->kc * RS_BLOCK_BYTES;
+  ix->corpus_bytes = ix->tile_bytes * ix->n_tiles;
+  memset(&ix->stats, 0, sizeof(ix->stats));
+  ix->stats.struct_size = sizeof(rs_stats);
+  ix->stats.sm_count = ix->sm_count;
+  ix->stats.corpus_bytes = (int64_t)ix->corpus_bytes;
+
+  const int grid = std::min(ix->sm_count, ix->n_tiles);
+  const int cap1 = max_cap_rows(ix->kc, 1, 1);
+  if (cap1 <= 0) {
+    delete ix;
+    return fail(RS_E_UNSUPPORTED, "dim=%d does not fit the shared-memory pipeline", cfg->dim);
+  }
+  const size_t pass_rows = 128;
+  const size_t qimg_bytes = (size_t)2 * ix->kc * pass_rows * RS_KCHUNK_BYTES;
+  const size_t cand_elems = (size_t)grid * pass_rows * cfg->max_k;
+  const size_t q_bytes = (size_t)cfg->max_batch * cfg->dim * sizeof(float);
+  const size_t out_elems = (size_t)cfg->max_batch * cfg->max_k;
+  ix->pinned_bytes = std::max<size_t>(kIngestChunkBytes, q_bytes + out_elems * 12 + 256);
+
+#define RS_ALLOC(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) {                                                                             \
+      int _rc = fail(RS_E_CUDA, "%s failed: %s (corpus image %.2f GB)", #expr, cudaGetErrorString(_e),   \
+                     ix->corpus_bytes / 1e9);                                                            \
+      free_all(ix);                                                                                      \
+      delete ix;                                                                                         \
+      return _rc;                                                                                        \
+    }                                                                                                    \
+  } while (0)
+
+  RS_ALLOC(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+  RS_ALLOC(cudaMalloc(&ix->corpus, ix->corpus_bytes));
+  RS_ALLOC(cudaMemsetAsync(ix->corpus, 0, ix->corpus_bytes, ix->stream));  // pad rows of the last tile stay zero
+  RS_ALLOC(cudaMalloc(&ix->dnorm, (size_t)ix->n_tiles * RS_TILE_ROWS * sizeof(float)));
+  RS_ALLOC(cudaMemsetAsync(ix->dnorm, 0, (size_t)ix->n_tiles * RS_TILE_ROWS * sizeof(float), ix->stream));
+  RS_ALLOC(cudaMalloc(&ix->minmax, (size_t)ix->n_tiles * sizeof(float2)));
+  RS_ALLOC(cudaMalloc(&ix->qimg, qimg_bytes));
+  RS_ALLOC(cudaMalloc(&ix->qnorm, pass_rows * sizeof(float)));
+  RS_ALLOC(cudaMalloc(&ix->qscale, pass_rows * sizeof(float)));
+  RS_ALLOC(cudaMalloc(&ix->cand_score, cand_elems * sizeof(float)));
+  RS_ALLOC(cudaMalloc(&ix->cand_idx, cand_elems * sizeof(int)));
+  RS_ALLOC(cudaMalloc(&ix->q_dev, q_bytes));
+  RS_ALLOC(cudaMalloc(&ix->out_idx_dev, out_elems * sizeof(long long)));
+  RS_ALLOC(cudaMalloc(&ix->out_score_dev, out_elems * sizeof(float)));
+  RS_ALLOC(cudaMalloc(&ix->ingest_dev, kIngestChunkBytes));
+  RS_ALLOC(cudaMallocHost(&ix->pinned, ix->pinned_bytes));
+  RS_ALLOC(cudaStreamSynchronize(ix->stream));
+#undef RS_ALLOC
+  *out = ix;
+  return RS_OK;
+}
+
+RS_API int rs_destroy(rs_index* ix) {
+  if (!ix) return RS_OK;
+  free_all(ix);
+  delete ix;
+  return RS_OK;
+}
+
+RS_API int rs_load_rows(rs_index* ix, const void* host_rows, int32_t src_dtype, int64_t row0, int64_t nrows) {
+  if (!ix || !host_rows) return fail(RS_E_INVALID, "null argument");
+  if (src_dtype < RS_DTYPE_BF16 || src_dtype > RS_DTYPE_FP32) return fail(RS_E_INVALID, "bad src_dtype %d", src_dtype);
+  if (row0 < 0 || nrows < 0 || row0 + nrows > ix->cfg.n_rows)
+    return fail(RS_E_INVALID, "rows [%lld,%lld) outside [0,%lld)", (long long)row0, (long long)(row0 + nrows), (long long)ix->cfg.n_rows);
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  const size_t esz = src_dtype == RS_DTYPE_FP32 ? 4 : 2;
+  const size_t row_bytes = (size_t)ix->cfg.dim * esz;
+  const int64_t chunk_rows = std::max<int64_t>(1, kIngestChunkBytes / (int64_t)row_bytes);
+  const char* src = static_cast<const char*>(host_rows);
+  for (int64_t r = 0; r < nrows; r += chunk_rows) {
+    const int64_t n = std::min(chunk_rows, nrows - r);
+    // pageable -> pinned -> device; the pinned hop keeps the copy asynchronous and full-speed
+    memcpy(ix->pinned, src + (size_t)r * row_bytes, (size_t)n * row_bytes);
+    RS_CUDA(cudaMemcpyAsync(ix->ingest_dev, ix->pinned, (size_t)n * row_bytes, cudaMemcpyHostToDevice, ix->stream));
+    RS_CUDA(rs::launch_tile_rows(ix->ingest_dev, src_dtype, row0 + r, (int)n, ix->cfg.dim, ix->cfg.dtype,
+                                 ix->cfg.scale_exp, ix->corpus, ix->dnorm, ix->stream));
+    RS_CUDA(cudaStreamSynchronize(ix->stream));
+    ix->stats.total_launches += 1;
+  }
+  ix->finalized = false;
+  return RS_OK;
+}
+
+RS_API int rs_fill_synthetic(rs_index* ix, uint64_t seed, int64_t global_row0) {
+  if (!ix) return fail(RS_E_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  const int64_t chunk = 1 << 20;
+  for (int64_t r = 0; r < ix->cfg.n_rows; r += chunk) {
+    const int n = (int)std::min<int64_t>(chunk, ix->cfg.n_rows - r);
+    RS_CUDA(rs::launch_synth_fill(seed, global_row0 + r, r, n, ix->cfg.dim, ix->cfg.dtype, ix->cfg.scale_exp,
+                                  ix->corpus, ix->dnorm, ix->stream));
+    ix->stats.total_launches += 1;
+  }
+  RS_CUDA(cudaStreamSynchronize(ix->stream));
+  ix->finalized = false;
+  return RS_OK;
+}
+
+RS_API int rs_finalize(rs_index* ix) {
+  if (!ix) return fail(RS_E_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  RS_CUDA(rs::launch_tile_minmax(ix->dnorm, (int)ix->cfg.n_rows, ix->n_tiles, ix->minmax, ix->stream));
+  RS_CUDA(cudaStreamSynchronize(ix->stream));
+  ix->stats.total_launches += 1;
+  ix->finalized = true;
+  return RS_OK;
+}
+
+RS_API int rs_search_device(rs_index* ix, const float* q_dev, int32_t B, int32_t k, int32_t metric, int32_t query_terms,
+                     int64_t* out_idx_dev, float* out_score_dev, void* stream) {
+  if (!ix || !q_dev || !out_idx_dev || !out_score_dev) return fail(RS_E_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  return search_device_locked(ix, q_dev, B, k, metric, query_terms, reinterpret_cast<long long*>(out_idx_dev),
+                              out_score_dev, static_cast<cudaStream_t>(stream));
+}
+
+RS_API int rs_search(rs_index* ix, const float* q_host, int32_t B, int32_t k, int32_t metric, int32_t query_terms,
+              int64_t* out_idx, float* out_score) {
+  if (!ix || !q_host || !out_idx || !out_score) return fail(RS_E_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  if (B <= 0 || B > ix->cfg.max_batch) return fail(RS_E_INVALID, "B=%d outside [1,%d]", B, ix->cfg.max_batch);
+  if (k <= 0 || k > ix->cfg.max_k) return fail(RS_E_INVALID, "k=%d outside [1,%d]", k, ix->cfg.max_k);
+  const size_t q_bytes = (size_t)B * ix->cfg.dim * sizeof(float);
+  const size_t n_out = (size_t)B * k;
+  char* pin = static_cast<char*>(ix->pinned);
+  long long* pin_idx = reinterpret_cast<long long*>(pin + ((q_bytes + 255) & ~size_t(255)));
+  float* pin_score = reinterpret_cast<float*>(pin_idx + n_out);
+  memcpy(pin, q_host, q_bytes);
+  RS_CUDA(cudaMemcpyAsync(ix->q_dev, pin, q_bytes, cudaMemcpyHostToDevice, ix->stream));
+  int rc = search_device_locked(ix, ix->q_dev, B, k, metric, query_terms, ix->out_idx_dev, ix->out_score_dev, ix->stream);
+  if (rc != RS_OK) return rc;
+  RS_CUDA(cudaMemcpyAsync(pin_idx, ix->out_idx_dev, n_out * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
+  RS_CUDA(cudaMemcpyAsync(pin_score, ix->out_score_dev, n_out * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+  RS_CUDA(cudaStreamSynchronize(ix->stream));
+  memcpy(out_idx, pin_idx, n_out * sizeof(long long));
+  memcpy(out_score, pin_score, n_out * sizeof(float));
+  return RS_OK;
+}
+
+RS_API int rs_merge_device(int32_t device, const float* scores_dev, const int64_t* idx_dev, int32_t n_lists, int32_t B,
+                    int32_t kc, int32_t k, int64_t* out_idx_dev, float* out_score_dev, void* stream) {
+  if (!scores_dev || !idx_dev || !out_idx_dev || !out_score_dev) return fail(RS_E_INVALID, "null argument");
+  if (n_lists <= 0 || n_lists > 256 || B <= 0 || kc <= 0 || k <= 0)
+    return fail(RS_E_INVALID, "bad merge shape n_lists=%d B=%d kc=%d k=%d", n_lists, B, kc, k);
+  RS_CUDA(cudaSetDevice(device));
+  RS_CUDA(rs::launch_merge_i64(scores_dev, reinterpret_cast<const long long*>(idx_dev), n_lists, B, kc, k,
+                               out_score_dev, reinterpret_cast<long long*>(out_idx_dev),
+                               static_cast<cudaStream_t>(stream)));
+  return RS_OK;
+}
+
+RS_API int rs_get_rows(rs_index* ix, int64_t row0, int64_t nrows, float* out_host) {
+  if (!ix || !out_host) return fail(RS_E_INVALID, "null argument");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > ix->cfg.n_rows) return fail(RS_E_INVALID, "row range out of bounds");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  const size_t row_bytes = (size_t)ix->cfg.dim * sizeof(float);
+  const int64_t chunk_rows = std::max<int64_t>(1, kIngestChunkBytes / (int64_t)row_bytes);
+  for (int64_t r = 0; r < nrows; r += chunk_rows) {
+    const int64_t n = std::min(chunk_rows, nrows - r);
+    RS_CUDA(rs::launch_untile_rows(ix->corpus, row0 + r, (int)n, ix->cfg.dim, ix->cfg.dtype, ix->cfg.scale_exp,
+                                   static_cast<float*>(ix->ingest_dev), ix->stream));
+    RS_CUDA(cudaMemcpyAsync(ix->pinned, ix->ingest_dev, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, ix->stream));
+    RS_CUDA(cudaStreamSynchronize(ix->stream));
+    memcpy(reinterpret_cast<char*>(out_host) + (size_t)r * row_bytes, ix->pinned, (size_t)n * row_bytes);
+    ix->stats.total_launches += 1;
+  }
+  return RS_OK;
+}
+
+RS_API int rs_get_norms(rs_index* ix, int64_t row0, int64_t nrows, float* out_host) {
+  if (!ix || !out_host) return fail(RS_E_INVALID, "null argument");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > ix->cfg.n_rows) return fail(RS_E_INVALID, "row range out of bounds");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  RS_CUDA(cudaMemcpy(out_host, ix->dnorm + row0, (size_t)nrows * sizeof(float), cudaMemcpyDeviceToHost));
+  return RS_OK;
+}
+
+RS_API int rs_get_image(rs_index* ix, int64_t off, int64_t nbytes, void* out_host) {
+  if (!ix || !out_host) return fail(RS_E_INVALID, "null argument");
+  if (off < 0 || nbytes < 0 || (size_t)(off + nbytes) > ix->corpus_bytes) return fail(RS_E_INVALID, "image range out of bounds");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  RS_CUDA(cudaMemcpy(out_host, ix->corpus + off, (size_t)nbytes, cudaMemcpyDeviceToHost));
+  return RS_OK;
+}
+
+RS_API int rs_get_stats(rs_index* ix, rs_stats* out) {
+  if (!ix || !out) return fail(RS_E_INVALID, "null argument");
+  if (out->struct_size != (int32_t)sizeof(rs_stats)) return fail(RS_E_INVALID, "rs_stats.struct_size mismatch");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  *out = ix->stats;
+  return RS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// Internal interface between the C-ABI host code (rs_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rs {
+
+struct SearchParams {
+  const uint8_t* corpus;             // tiled corpus image (rs_layout.h)
+  const uint8_t* qimg;               // Q image: terms x KC blocks of bpad rows
+  const float* qnorm;                // [bpad] L2 norm of each query (cosine)
+  const float* qscale;               // [bpad] power-of-two factor: raw accumulator -> dot product
+  const float* dnorm;                // [n_tiles*128] document L2 norms (cosine)
+  const float2* tile_norm_minmax;    // [n_tiles] (min, max) document norm per tile (cosine)
+  float* cand_score;                 // [grid][n_queries][k] per-CTA candidates, best first
+  int* cand_idx;                     // [grid][n_queries][k] local row ids, -1 = padding
+  int n_rows;                        // valid documents in this shard
+  int n_tiles;                       // ceil(n_rows / 128)
+  int n_queries;                     // B
+  int kc;                            // D / 64
+  int planes;                        // 1 (bf16/fp16 storage) or 2 (fp32 as split fp16)
+  int terms;                         // query terms: 1 (rounded) or 2 (hi + lo)
+  int bpad;                          // B rounded up to a multiple of 8
+  int k;
+  int metric;
+  int dtype;                         // element type of the 16-bit planes: RS_DTYPE_BF16 / RS_DTYPE_FP16
+  int stages;                        // depth of the 16 KiB bulk-copy ring
+  float lo_coef;                     // weight of the low-order accumulator (2^-11 for fp16 terms, 1 for bf16)
+};
+
+cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dtype, int terms, int corpus_scale_exp,
+                              uint8_t* qimg, float* qnorm, float* qscale, cudaStream_t stream);
+cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t stream);
+int fused_smem_bytes(int bpad, int kc, int terms, int stages, int k);
+int fused_reg_k();
+cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int kc, int k,
+                             long long idx_offset, float* out_score, long long* out_idx, cudaStream_t stream);
+cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx, int n_lists, int n_queries, int kc,
+                             int k, float* out_score, long long* out_idx, cudaStream_t stream);
+
+// ingest (rs_ingest.cu)
+cudaError_t launch_tile_rows(const void* rows_dev, int src_dtype, long long row0, int nrows, int D, int dtype,
+                             int scale_exp, uint8_t* corpus, float* dnorm, cudaStream_t stream);
+cudaError_t launch_untile_rows(const uint8_t* corpus, long long row0, int nrows, int D, int dtype, int scale_exp,
+                               float* out_rows_dev, cudaStream_t stream);
+cudaError_t launch_synth_fill(unsigned long long seed, long long global_row0, long long local_row0, int nrows, int D,
+                              int dtype, int scale_exp, uint8_t* corpus, float* dnorm, cudaStream_t stream);
+cudaError_t launch_tile_minmax(const float* dnorm, int n_rows, int n_tiles, float2* minmax, cudaStream_t stream);
+
+}  // namespace rs

@@ -1,0 +1,565 @@
+// Fused score-and-select for the retriever hot path (replaces retriever.py:594-611 + :750-769
+// of the reference: SGEMM + 5 elementwise temporaries + B full-length sorts).
+//
+//   query_prep_kernel      fp32 queries -> MMA-ready "Q image" (+ norms, power-of-two scales)
+//   fused_search_kernel    persistent, warp-specialised: bulk-copy (TMA engine) producer warp,
+//                          single-thread tcgen05.mma issuer, epilogue warps that read the score
+//                          tile from TMEM and keep one running top-k per query (one thread per
+//                          query) - the B x N score matrix never exists in HBM
+//   merge_topk_kernel      multi-way merge of the per-CTA (or per-GPU) sorted candidate lists
+//
+// Orientation: queries are the MMA A operand (M = 128 lanes of TMEM, one lane per query row),
+// documents are the B operand (N = 128 documents per tile).  Only Bpad <= 64 A rows exist in
+// shared memory; the remaining rows of the M=128 operand alias whatever follows in shared
+// memory and produce garbage in TMEM lanes that are never read (rows of D are independent).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "rs_kernels.h"
+#include "rs_layout.h"
+#include "rs_ptx.cuh"
+
+namespace rs {
+
+// ------------------------------------------------------------------------------------------
+// query prep
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint16_t f32_to_bf16_rn(float x) {
+  uint32_t u = __float_as_uint(x);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+__device__ __forceinline__ float bf16_to_f32(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
+__device__ __forceinline__ uint16_t f32_to_f16_rn(float x) { return __half_as_ushort(__float2half_rn(x)); }
+__device__ __forceinline__ float f16_to_f32(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+
+// One CTA per (padded) query row.  Writes terms x KC blocks of the Q image, the L2 norm of the
+// represented query (retriever.py:602) and the power-of-two factor that undoes the scaling.
+__global__ void __launch_bounds__(256) query_prep_kernel(const float* __restrict__ q, int B, int D, int bpad,
+                                                          int dtype, int terms, int corpus_scale_exp,
+                                                          uint8_t* __restrict__ qimg, float* __restrict__ qnorm,
+                                                          float* __restrict__ qscale) {
+  const int row = blockIdx.x;
+  const int kc_count = D / RS_KCHUNK_ELEMS;
+  __shared__ float red[256];
+  __shared__ int s_exp;
+  const bool live = row < B;
+  // 1. max |q| -> per-query power-of-two scale (keeps fp16 terms in range; exact)
+  float mx = 0.f;
+  if (live)
+    for (int c = threadIdx.x; c < D; c += blockDim.x) mx = fmaxf(mx, fabsf(q[(size_t)row * D + c]));
+  red[threadIdx.x] = mx;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    int e = 0;
+    if (m > 0.f && m < CUDART_INF_F) e = -ilogbf(m);  // scaled max in [1,2)
+    s_exp = e;
+  }
+  __syncthreads();
+  const int e = s_exp;
+  // 2. split into terms, write swizzled, accumulate the norm of the represented value
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float x = live ? q[(size_t)row * D + c] : 0.f;
+    float xs = ldexpf(x, e);
+    uint16_t t0, t1 = 0;
+    float rep;
+    if (dtype == RS_DTYPE_BF16) {
+      t0 = f32_to_bf16_rn(xs);
+      float h = bf16_to_f32(t0);
+      rep = h;
+      if (terms == 2) {
+        t1 = f32_to_bf16_rn(xs - h);
+        rep = h + bf16_to_f32(t1);
+      }
+    } else {
+      t0 = f32_to_f16_rn(xs);
+      float h = f16_to_f32(t0);
+      rep = h;
+      if (terms == 2) {
+        t1 = f32_to_f16_rn(ldexpf(xs - h, RS_FP16_SPLIT_SHIFT));
+        rep = h + ldexpf(f16_to_f32(t1), -RS_FP16_SPLIT_SHIFT);
+      }
+    }
+    rep = ldexpf(rep, -e);
+    ss += rep * rep;
+    const int kc = c >> 6;
+    const uint32_t off = rs_block_offset((uint32_t)row, (uint32_t)(c & 63));
+    const size_t blk = (size_t)bpad * RS_KCHUNK_BYTES;
+    *reinterpret_cast<uint16_t*>(qimg + (size_t)kc * blk + off) = t0;
+    if (terms == 2) *reinterpret_cast<uint16_t*>(qimg + (size_t)(kc_count + kc) * blk + off) = t1;
+  }
+  red[threadIdx.x] = ss;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    qnorm[row] = sqrtf(red[0]);
+    qscale[row] = ldexpf(1.0f, -(e + corpus_scale_exp));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused score + select
+// ------------------------------------------------------------------------------------------
+constexpr int kProducerWarp = 0;
+constexpr int kMmaWarp = 1;
+constexpr int kFirstEpiWarp = 2;
+constexpr int kNumEpiWarps = 4;
+constexpr int kThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;  // 192
+constexpr int kRegK = 16;                                       // register-resident list capacity
+
+struct SmemMap {
+  uint32_t q_bytes, stage_off, bar_off, list_off, total;
+};
+__host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, int stages, int k, bool reglist) {
+  SmemMap m;
+  m.q_bytes = (uint32_t)terms * kc * bpad * RS_KCHUNK_BYTES;
+  m.stage_off = m.q_bytes;  // multiple of 1024 because bpad % 8 == 0
+  m.bar_off = m.stage_off + (uint32_t)stages * RS_BLOCK_BYTES;
+  m.list_off = m.bar_off + 1024;
+  uint32_t nact = (uint32_t)((bpad + 31) / 32);
+  m.total = m.list_off + (reglist ? 0u : (uint32_t)k * nact * 32u * 8u);
+  return m;
+}
+
+__device__ __forceinline__ float max32(const float (&v)[32]) {
+  float m0 = fmaxf(fmaxf(v[0], v[1]), v[2]), m1 = fmaxf(fmaxf(v[3], v[4]), v[5]);
+  float m2 = fmaxf(fmaxf(v[6], v[7]), v[8]), m3 = fmaxf(fmaxf(v[9], v[10]), v[11]);
+#pragma unroll
+  for (int j = 12; j < 32; j += 4) {
+    m0 = fmaxf(m0, v[j]);
+    m1 = fmaxf(m1, v[j + 1]);
+    m2 = fmaxf(m2, v[j + 2]);
+    m3 = fmaxf(m3, v[j + 3]);
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// Conservative bound, in raw accumulator units, below which a document of this tile cannot beat
+// the current cosine threshold (see DESIGN.md "cosine epilogue").
+__device__ __forceinline__ float cosine_raw_bound(float thr_cos, float nq, float inv_qs, float ndmin, float ndmax) {
+  if (thr_cos == -CUDART_INF_F) return -CUDART_INF_F;
+  if (thr_cos >= 0.f) return thr_cos * nq * ndmin * inv_qs * (1.0f - 1e-6f);
+  return thr_cos * (nq * ndmax + 1e-8f) * inv_qs * (1.0f + 1e-6f);
+}
+
+template <int NACC, bool REGLIST>
+__global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned shared memory; the launcher over-allocates by 1 KiB
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.k, REGLIST);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t q_smem = smem_base;
+  const uint32_t stage_smem = smem_base + map.stage_off;
+  const uint32_t bar_base = smem_base + map.bar_off;
+  // barrier slots (8 B each): full[s], empty[s], tfull[2], tempty[2], qfull
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
+  const uint32_t qfull_bar = bar_base + 8u * (2 * p.stages + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + map.bar_off + 1016);
+
+  const int nact_warps = (p.bpad + 31) / 32;
+  constexpr uint32_t kTmemCols = NACC * 2 * RS_TILE_ROWS;  // 256 or 512
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), nact_warps);
+    }
+    mbar_init(qfull_bar, 1);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(smem_u32((const void*)tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int blocks_per_tile = p.planes * p.kc;
+  const size_t tile_bytes = (size_t)blocks_per_tile * RS_BLOCK_BYTES;
+
+  if (warp == kProducerWarp) {
+    // ===================== bulk-copy producer =====================
+    if (lane == 0) {
+      const uint64_t pol_stream = l2_policy_evict_first();
+      const uint64_t pol_keep = l2_policy_evict_last();
+      // queries: resident for the whole kernel
+      mbar_arrive_expect_tx(qfull_bar, map.q_bytes);
+      for (uint32_t off = 0; off < map.q_bytes; off += 32768u) {
+        uint32_t n = min(32768u, map.q_bytes - off);
+        bulk_g2s(q_smem + off, p.qimg + off, n, qfull_bar, pol_keep);
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const uint8_t* src = p.corpus + (size_t)t * tile_bytes;
+        for (int b = 0; b < blocks_per_tile; ++b) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), RS_BLOCK_BYTES);
+          bulk_g2s(stage_smem + (uint32_t)s * RS_BLOCK_BYTES, src + (size_t)b * RS_BLOCK_BYTES, RS_BLOCK_BYTES,
+                   full_bar(s), pol_stream);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(p.dtype == RS_DTYPE_BF16, RS_TILE_ROWS);
+      const uint32_t qblk = (uint32_t)p.bpad * RS_KCHUNK_BYTES;
+      mbar_wait(qfull_bar, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * NACC) * RS_TILE_ROWS;
+        for (int pl = 0; pl < p.planes; ++pl) {
+          for (int kc = 0; kc < p.kc; ++kc) {
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint64_t bdesc = umma_smem_desc(stage_smem + (uint32_t)s * RS_BLOCK_BYTES);
+            const uint64_t a0 = umma_smem_desc(q_smem + (uint32_t)kc * qblk);
+            const uint64_t a1 = umma_smem_desc(q_smem + (uint32_t)(p.kc + kc) * qblk);
+            // 16-byte units: one UMMA K step (16 elements x 2 B) advances the start address by 2
+            if (pl == 0) {
+#pragma unroll
+              for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
+                umma_f16(d0, a0 + 2u * ks, bdesc + 2u * ks, idesc, (kc | ks) != 0);
+              if (NACC == 2) {
+#pragma unroll
+                for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
+                  umma_f16(d0 + RS_TILE_ROWS, a1 + 2u * ks, bdesc + 2u * ks, idesc, (kc | ks) != 0);
+              }
+            } else {
+              // lo plane of an fp32 corpus: q_hi . d_lo joins the low-order accumulator
+#pragma unroll
+              for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
+                umma_f16(d0 + RS_TILE_ROWS, a0 + 2u * ks, bdesc + 2u * ks, idesc, 1u);
+            }
+            umma_commit(empty_bar(s));  // smem slot is free once these MMAs have read it
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_ph ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: one thread per query row =====================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
+    if (quarter < nact_warps) {
+      const int row = quarter * 32 + lane;
+      const bool live = row < p.n_queries;
+      const int k = p.k;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const bool cosine = p.metric == RS_METRIC_COSINE;
+      const float qs = live ? p.qscale[row] : 1.f;  // raw accumulator -> dot product (power of two)
+      const float inv_qs = 1.0f / qs;
+      const float nq = live ? p.qnorm[row] : 0.f;
+      const float lo_coef = p.lo_coef;
+
+      // running top-k, ascending: slot 0 is the current k-th best (the threshold)
+      float ls[REGLIST ? kRegK : 1];
+      int li[REGLIST ? kRegK : 1];
+      float* sl_s = nullptr;
+      int* sl_i = nullptr;
+      const int lstride = nact_warps * 32;
+      if (REGLIST) {
+#pragma unroll
+        for (int j = 0; j < kRegK; ++j) {
+          ls[j] = j < k ? -CUDART_INF_F : CUDART_INF_F;
+          li[j] = -1;
+        }
+      } else {
+        sl_s = reinterpret_cast<float*>(smem + map.list_off) + row;
+        sl_i = reinterpret_cast<int*>(smem + map.list_off + (size_t)k * lstride * 4) + row;
+        for (int j = 0; j < k; ++j) {
+          sl_s[j * lstride] = -CUDART_INF_F;
+          sl_i[j * lstride] = -1;
+        }
+      }
+      float thr = live ? -CUDART_INF_F : CUDART_INF_F;  // in metric units (dot: raw units)
+      float thr_raw = thr;
+
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        float ndmin = 1.f, ndmax = 1.f;
+        if (cosine) {
+          float2 mm = p.tile_norm_minmax[t];
+          ndmin = mm.x;
+          ndmax = mm.y;
+          thr_raw = live ? cosine_raw_bound(thr, nq, inv_qs, ndmin, ndmax) : CUDART_INF_F;
+        }
+        mbar_wait(tfull_bar(acc), acc_ph);
+        tc_fence_after();
+        const uint32_t tacc = lane_base + (uint32_t)(acc * NACC) * RS_TILE_ROWS;
+        const int tile_row0 = t * RS_TILE_ROWS;
+#pragma unroll 1
+        for (int c0 = 0; c0 < RS_TILE_ROWS; c0 += 32) {
+          float v[32];
+          {
+            uint32_t r0[32];
+            tmem_ld_x32(tacc + c0, r0);
+            if (NACC == 2) {
+              uint32_t r1[32];
+              tmem_ld_x32(tacc + RS_TILE_ROWS + c0, r1);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r1[j]), lo_coef, __uint_as_float(r0[j]));
+            } else {
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+            }
+          }
+          const float m = max32(v);
+          if (__any_sync(0xffffffffu, m > thr_raw)) {
+            // rare path: some query of this warp has a candidate in this 32-document chunk
+            uint32_t pm = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pm |= (v[j] > thr_raw) ? (1u << j) : 0u;
+            uint32_t any = __reduce_or_sync(0xffffffffu, pm);
+            while (any) {
+              const int j = __ffs(any) - 1;
+              any &= any - 1;
+              // re-read the single column from TMEM: warp-uniform address, no dynamic register index
+              float s = __uint_as_float(tmem_ld_x1(tacc + c0 + j));
+              if (NACC == 2) {
+                float s1 = __uint_as_float(tmem_ld_x1(tacc + RS_TILE_ROWS + c0 + j));
+                tmem_wait_ld();
+                s = fmaf(s1, lo_coef, s);
+              } else {
+                tmem_wait_ld();
+              }
+              const int idx = tile_row0 + c0 + j;
+              if (((pm >> j) & 1u) && idx < p.n_rows) {
+                float x = s;  // dot metric: compare and store raw units (exact power-of-two scale)
+                if (cosine) {
+                  const float nd = p.dnorm[idx];
+                  const float denom = __fadd_rn(__fmul_rn(nq, nd), 1e-8f);   // retriever.py:605,607
+                  x = __fdiv_rn(s * qs, denom);
+                  x = fminf(fmaxf(x, -1.0f), 1.0f);                          // retriever.py:609
+                }
+                if (x > thr) {
+                  if (REGLIST) {
+                    bool prev = true;  // "slot j-1 was shifted" (true for j == 0)
+#pragma unroll
+                    for (int jj = 0; jj < kRegK; ++jj) {
+                      const bool lt = (jj + 1 < kRegK) && (ls[jj + 1 < kRegK ? jj + 1 : jj] < x);
+                      const float ns = lt ? ls[jj + 1 < kRegK ? jj + 1 : jj] : (prev ? x : ls[jj]);
+                      const int ni = lt ? li[jj + 1 < kRegK ? jj + 1 : jj] : (prev ? idx : li[jj]);
+                      ls[jj] = ns;
+                      li[jj] = ni;
+                      prev = lt;
+                    }
+                    thr = ls[0];
+                  } else {
+                    int jj = 0;
+                    while (jj + 1 < k && sl_s[(jj + 1) * lstride] < x) {
+                      sl_s[jj * lstride] = sl_s[(jj + 1) * lstride];
+                      sl_i[jj * lstride] = sl_i[(jj + 1) * lstride];
+                      ++jj;
+                    }
+                    sl_s[jj * lstride] = x;
+                    sl_i[jj * lstride] = idx;
+                    thr = sl_s[0];
+                  }
+                  thr_raw = cosine ? cosine_raw_bound(thr, nq, inv_qs, ndmin, ndmax) : thr;
+                }
+              }
+            }
+          }
+        }
+        // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) {
+          acc = 0;
+          acc_ph ^= 1u;
+        }
+      }
+
+      // per-CTA candidates, best first; dot scores leave raw units here
+      if (live) {
+        float* cs = p.cand_score + ((size_t)blockIdx.x * p.n_queries + row) * k;
+        int* ci = p.cand_idx + ((size_t)blockIdx.x * p.n_queries + row) * k;
+        if (REGLIST) {
+#pragma unroll
+          for (int j = 0; j < kRegK; ++j) {
+            if (j < k) {
+              const float sc = cosine ? ls[j] : ls[j] * qs;
+              cs[k - 1 - j] = li[j] < 0 ? -CUDART_INF_F : sc;
+              ci[k - 1 - j] = li[j];
+            }
+          }
+        } else {
+          for (int j = 0; j < k; ++j) {
+            const float raw = sl_s[j * lstride];
+            const int id = sl_i[j * lstride];
+            cs[k - 1 - j] = id < 0 ? -CUDART_INF_F : (cosine ? raw : raw * qs);
+            ci[k - 1 - j] = id;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// merge of sorted candidate lists: one warp per query, each lane walks lists lane, lane+32, ...
+// Ordering everywhere is (score desc, index asc); index < 0 is padding.
+// ------------------------------------------------------------------------------------------
+template <typename IdxT>
+__global__ void __launch_bounds__(128) merge_topk_kernel(const float* __restrict__ cand_score,
+                                                         const IdxT* __restrict__ cand_idx, int n_lists,
+                                                         int n_queries, int kc, int k, long long idx_offset,
+                                                         float* __restrict__ out_score,
+                                                         long long* __restrict__ out_idx) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= n_queries) return;
+  constexpr int kMaxOwn = 8;  // up to 256 lists
+  int head[kMaxOwn];
+#pragma unroll
+  for (int i = 0; i < kMaxOwn; ++i) head[i] = 0;
+  for (int r = 0; r < k; ++r) {
+    float bs = -CUDART_INF_F;
+    long long bi = -1;
+    int bown = -1;
+#pragma unroll
+    for (int i = 0; i < kMaxOwn; ++i) {
+      const int l = lane + 32 * i;
+      if (l < n_lists && head[i] < kc) {
+        const size_t o = ((size_t)l * n_queries + q) * kc + head[i];
+        const long long id = (long long)cand_idx[o];
+        const float s = cand_score[o];
+        if (id >= 0 && (bi < 0 || s > bs || (s == bs && id < bi))) {
+          bs = s;
+          bi = id;
+          bown = i;
+        }
+      }
+    }
+    // warp arg-best on (score desc, idx asc); padding (bi < 0) always loses
+    float ws = bs;
+    long long wi = bi;
+    int wl = lane;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, ws, off);
+      const long long oi = __shfl_xor_sync(0xffffffffu, wi, off);
+      const int ol = __shfl_xor_sync(0xffffffffu, wl, off);
+      const bool take = (oi >= 0) && (wi < 0 || os > ws || (os == ws && oi < wi));
+      if (take) {
+        ws = os;
+        wi = oi;
+        wl = ol;
+      }
+    }
+    if (lane == wl && wi >= 0) {
+#pragma unroll
+      for (int i = 0; i < kMaxOwn; ++i)
+        if (i == bown) ++head[i];
+    }
+    if (lane == 0) {
+      out_score[(size_t)q * k + r] = wi >= 0 ? ws : -CUDART_INF_F;
+      out_idx[(size_t)q * k + r] = wi >= 0 ? wi + idx_offset : -1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dtype, int terms, int corpus_scale_exp,
+                              uint8_t* qimg, float* qnorm, float* qscale, cudaStream_t stream) {
+  query_prep_kernel<<<bpad, 256, 0, stream>>>(q_dev, B, D, bpad, dtype, terms, corpus_scale_exp, qimg, qnorm,
+                                              qscale);
+  return cudaGetLastError();
+}
+
+template <int NACC, bool REGLIST>
+static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t stream) {
+  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.k, REGLIST);
+  auto kern = fused_search_kernel<NACC, REGLIST>;
+  const int bytes = (int)map.total + 1024;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kThreads, bytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+int fused_smem_bytes(int bpad, int kc, int terms, int stages, int k) {
+  return (int)make_smem_map(bpad, kc, terms, stages, k, k <= kRegK).total + 1024;
+}
+int fused_reg_k() { return kRegK; }
+
+cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t stream) {
+  const bool reglist = p.k <= kRegK;
+  const int nacc = (p.terms == 2 || p.planes == 2) ? 2 : 1;
+  if (nacc == 1) return reglist ? launch_fused_t<1, true>(p, grid, stream) : launch_fused_t<1, false>(p, grid, stream);
+  return reglist ? launch_fused_t<2, true>(p, grid, stream) : launch_fused_t<2, false>(p, grid, stream);
+}
+
+cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int kc, int k,
+                             long long idx_offset, float* out_score, long long* out_idx, cudaStream_t stream) {
+  if (n_lists > 256) return cudaErrorInvalidValue;
+  const int warps = 4;
+  merge_topk_kernel<int><<<(n_queries + warps - 1) / warps, warps * 32, 0, stream>>>(
+      cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, out_score, out_idx);
+  return cudaGetLastError();
+}
+cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx, int n_lists, int n_queries, int kc,
+                             int k, float* out_score, long long* out_idx, cudaStream_t stream) {
+  if (n_lists > 256) return cudaErrorInvalidValue;
+  const int warps = 4;
+  merge_topk_kernel<long long><<<(n_queries + warps - 1) / warps, warps * 32, 0, stream>>>(
+      cand_score, cand_idx, n_lists, n_queries, kc, k, 0, out_score, out_idx);
+  return cudaGetLastError();
+}
+
+}  // namespace rs
