@@ -113,10 +113,13 @@ RS_API int rs_search_device(rs_index* ix, const float* q_dev, int32_t B, int32_t
                      int64_t* out_idx_dev, float* out_score_dev, void* stream);
 
 /* Final merge of n_lists sorted candidate lists per query (the multi-GPU step):
- * scores_dev/idx_dev are [n_lists][B][kc] device arrays as produced by an all-gather of
- * rs_search_device outputs; writes the global top-k [B][k]. */
+ * list l holds scores float[B][kc] at scores_dev + l*score_list_stride and indices int64[B][kc]
+ * at idx_dev + l*idx_list_stride (strides in ELEMENTS; 0 = densely packed B*kc), i.e. exactly
+ * what an all-gather of the rs_search_device outputs leaves in memory (one packed buffer per
+ * rank or two separate ones); writes the global top-k [B][k]. */
 RS_API int rs_merge_device(int32_t device, const float* scores_dev, const int64_t* idx_dev, int32_t n_lists, int32_t B,
-                    int32_t kc, int32_t k, int64_t* out_idx_dev, float* out_score_dev, void* stream);
+                    int32_t kc, int32_t k, int64_t score_list_stride, int64_t idx_list_stride,
+                    int64_t* out_idx_dev, float* out_score_dev, void* stream);
 
 /* Read back the represented values of rows [row0,row0+nrows) as float (inverse of the tiling);
  * used by the tests (ingest round trip) and by the CPU-baseline sampler. */
@@ -126,6 +129,9 @@ RS_API int rs_get_norms(rs_index* ix, int64_t row0, int64_t nrows, float* out_ho
 RS_API int rs_get_image(rs_index* ix, int64_t off, int64_t nbytes, void* out_host);
 
 RS_API int rs_get_stats(rs_index* ix, rs_stats* out);
+/* Durations (ms) of the last n fused score+select kernel launches, oldest first, from CUDA events
+ * recorded on the launching stream around each launch (ring of 256); synchronises on them. */
+RS_API int rs_get_kernel_times(rs_index* ix, float* out_ms, int32_t n);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ METRICS = {"dot": METRIC_DOT, "cosine": METRIC_COSINE}
 EXPORTS = (
     "rs_version", "rs_last_error", "rs_create", "rs_destroy", "rs_load_rows", "rs_fill_synthetic",
     "rs_finalize", "rs_search", "rs_search_device", "rs_merge_device", "rs_get_rows",
-    "rs_get_norms", "rs_get_image", "rs_get_stats",
+    "rs_get_norms", "rs_get_image", "rs_get_stats", "rs_get_kernel_times",
 )
 
 
@@ -75,7 +75,8 @@ def load() -> C.CDLL:
         "rs_finalize": [vp],
         "rs_search": [vp, vp, i32, i32, i32, i32, vp, vp],
         "rs_search_device": [vp, vp, i32, i32, i32, i32, vp, vp, vp],
-        "rs_merge_device": [i32, vp, vp, i32, i32, i32, i32, vp, vp, vp],
+        "rs_merge_device": [i32, vp, vp, i32, i32, i32, i32, i64, i64, vp, vp, vp],
+        "rs_get_kernel_times": [vp, vp, i32],
         "rs_get_rows": [vp, i64, i64, vp],
         "rs_get_norms": [vp, i64, i64, vp],
         "rs_get_image": [vp, i64, i64, vp],
@@ -167,6 +168,11 @@ class Index:
         check(self.lib.rs_get_image(self.h, off, nbytes, out.ctypes.data), "rs_get_image")
         return out
 
+    def kernel_times_ms(self, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.float32)
+        check(self.lib.rs_get_kernel_times(self.h, out.ctypes.data, n), "rs_get_kernel_times")
+        return out
+
     def stats(self) -> dict:
         st = rs_stats()
         st.struct_size = C.sizeof(rs_stats)
@@ -175,6 +181,7 @@ class Index:
 
 
 def merge_device(device: int, scores_ptr: int, idx_ptr: int, n_lists: int, B: int, kc: int, k: int,
-                 out_idx_ptr: int, out_score_ptr: int, stream: int = 0):
-    check(load().rs_merge_device(device, scores_ptr, idx_ptr, n_lists, B, kc, k, out_idx_ptr, out_score_ptr, stream),
-          "rs_merge_device")
+                 out_idx_ptr: int, out_score_ptr: int, stream: int = 0, score_list_stride: int = 0,
+                 idx_list_stride: int = 0):
+    check(load().rs_merge_device(device, scores_ptr, idx_ptr, n_lists, B, kc, k, score_list_stride,
+                                 idx_list_stride, out_idx_ptr, out_score_ptr, stream), "rs_merge_device")

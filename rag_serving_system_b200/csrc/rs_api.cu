@@ -71,6 +71,11 @@ struct rs_index {
   void* pinned = nullptr;  // pinned host staging (queries in, results out, ingest chunks)
   size_t pinned_bytes = 0;
   cudaStream_t stream = nullptr;
+  // CUDA-event pairs around every fused-kernel launch (on the launching stream) so callers can
+  // read the kernel's own duration without a profiler
+  static constexpr int kEventRing = 256;
+  cudaEvent_t ev_beg[kEventRing] = {}, ev_end[kEventRing] = {};
+  long long ev_count = 0;
   rs_stats stats;
   std::mutex mu;
 };
@@ -113,6 +118,10 @@ void free_all(rs_index* ix) {
   cudaFree(ix->out_score_dev);
   cudaFree(ix->ingest_dev);
   if (ix->pinned) cudaFreeHost(ix->pinned);
+  for (int i = 0; i < rs_index::kEventRing; ++i) {
+    if (ix->ev_beg[i]) cudaEventDestroy(ix->ev_beg[i]);
+    if (ix->ev_end[i]) cudaEventDestroy(ix->ev_end[i]);
+  }
   if (ix->stream) cudaStreamDestroy(ix->stream);
 }
 
@@ -162,7 +171,11 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.dtype = ix->plane_dtype;
     p.stages = pl.stages;
     p.lo_coef = ix->plane_dtype == RS_DTYPE_FP16 ? ldexpf(1.0f, -RS_FP16_SPLIT_SHIFT) : 1.0f;
+    const int slot = (int)(ix->ev_count % rs_index::kEventRing);
+    RS_CUDA(cudaEventRecord(ix->ev_beg[slot], stream));
     RS_CUDA(rs::launch_fused_search(p, grid, stream));
+    RS_CUDA(cudaEventRecord(ix->ev_end[slot], stream));
+    ++ix->ev_count;
     RS_CUDA(rs::launch_merge_i32(ix->cand_score, ix->cand_idx, grid, nb, k, k, ix->cfg.row_offset,
                                  out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, stream));
     ix->stats.launches += 3;
@@ -255,6 +268,10 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   RS_ALLOC(cudaMalloc(&ix->out_score_dev, out_elems * sizeof(float)));
   RS_ALLOC(cudaMalloc(&ix->ingest_dev, kIngestChunkBytes));
   RS_ALLOC(cudaMallocHost(&ix->pinned, ix->pinned_bytes));
+  for (int i = 0; i < rs_index::kEventRing; ++i) {
+    RS_ALLOC(cudaEventCreate(&ix->ev_beg[i]));
+    RS_ALLOC(cudaEventCreate(&ix->ev_end[i]));
+  }
   RS_ALLOC(cudaStreamSynchronize(ix->stream));
 #undef RS_ALLOC
   *out = ix;
@@ -354,13 +371,16 @@ RS_API int rs_search(rs_index* ix, const float* q_host, int32_t B, int32_t k, in
 }
 
 RS_API int rs_merge_device(int32_t device, const float* scores_dev, const int64_t* idx_dev, int32_t n_lists, int32_t B,
-                    int32_t kc, int32_t k, int64_t* out_idx_dev, float* out_score_dev, void* stream) {
+                    int32_t kc, int32_t k, int64_t score_list_stride, int64_t idx_list_stride,
+                    int64_t* out_idx_dev, float* out_score_dev, void* stream) {
   if (!scores_dev || !idx_dev || !out_idx_dev || !out_score_dev) return fail(RS_E_INVALID, "null argument");
   if (n_lists <= 0 || n_lists > 256 || B <= 0 || kc <= 0 || k <= 0)
     return fail(RS_E_INVALID, "bad merge shape n_lists=%d B=%d kc=%d k=%d", n_lists, B, kc, k);
   RS_CUDA(cudaSetDevice(device));
+  if (score_list_stride <= 0) score_list_stride = (int64_t)B * kc;
+  if (idx_list_stride <= 0) idx_list_stride = (int64_t)B * kc;
   RS_CUDA(rs::launch_merge_i64(scores_dev, reinterpret_cast<const long long*>(idx_dev), n_lists, B, kc, k,
-                               out_score_dev, reinterpret_cast<long long*>(out_idx_dev),
+                               score_list_stride, idx_list_stride, out_score_dev, reinterpret_cast<long long*>(out_idx_dev),
                                static_cast<cudaStream_t>(stream)));
   return RS_OK;
 }
@@ -399,6 +419,20 @@ RS_API int rs_get_image(rs_index* ix, int64_t off, int64_t nbytes, void* out_hos
   std::lock_guard<std::mutex> lock(ix->mu);
   RS_CUDA(cudaSetDevice(ix->cfg.device));
   RS_CUDA(cudaMemcpy(out_host, ix->corpus + off, (size_t)nbytes, cudaMemcpyDeviceToHost));
+  return RS_OK;
+}
+
+RS_API int rs_get_kernel_times(rs_index* ix, float* out_ms, int32_t n) {
+  if (!ix || !out_ms || n <= 0) return fail(RS_E_INVALID, "bad argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  if (n > rs_index::kEventRing || n > ix->ev_count)
+    return fail(RS_E_INVALID, "only %lld fused launches recorded (ring of %d)", ix->ev_count, rs_index::kEventRing);
+  for (int i = 0; i < n; ++i) {
+    const int slot = (int)((ix->ev_count - n + i) % rs_index::kEventRing);
+    RS_CUDA(cudaEventSynchronize(ix->ev_end[slot]));
+    RS_CUDA(cudaEventElapsedTime(&out_ms[i], ix->ev_beg[slot], ix->ev_end[slot]));
+  }
   return RS_OK;
 }
 

@@ -36,7 +36,8 @@ int fused_reg_k();
 cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int kc, int k,
                              long long idx_offset, float* out_score, long long* out_idx, cudaStream_t stream);
 cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx, int n_lists, int n_queries, int kc,
-                             int k, float* out_score, long long* out_idx, cudaStream_t stream);
+                             int k, long long score_list_stride, long long idx_list_stride, float* out_score,
+                             long long* out_idx, cudaStream_t stream);
 
 // ingest (rs_ingest.cu)
 cudaError_t launch_tile_rows(const void* rows_dev, int src_dtype, long long row0, int nrows, int D, int dtype,

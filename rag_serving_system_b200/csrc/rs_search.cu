@@ -457,6 +457,7 @@ template <typename IdxT>
 __global__ void __launch_bounds__(128) merge_topk_kernel(const float* __restrict__ cand_score,
                                                          const IdxT* __restrict__ cand_idx, int n_lists,
                                                          int n_queries, int kc, int k, long long idx_offset,
+                                                         long long score_list_stride, long long idx_list_stride,
                                                          float* __restrict__ out_score,
                                                          long long* __restrict__ out_idx) {
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -474,9 +475,9 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const float* __restrict
     for (int i = 0; i < kMaxOwn; ++i) {
       const int l = lane + 32 * i;
       if (l < n_lists && head[i] < kc) {
-        const size_t o = ((size_t)l * n_queries + q) * kc + head[i];
-        const long long id = (long long)cand_idx[o];
-        const float s = cand_score[o];
+        const size_t o = (size_t)q * kc + head[i];
+        const long long id = (long long)cand_idx[(size_t)l * idx_list_stride + o];
+        const float s = cand_score[(size_t)l * score_list_stride + o];
         if (id >= 0 && (bi < 0 || s > bs || (s == bs && id < bi))) {
           bs = s;
           bi = id;
@@ -550,15 +551,17 @@ cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n
   if (n_lists > 256) return cudaErrorInvalidValue;
   const int warps = 4;
   merge_topk_kernel<int><<<(n_queries + warps - 1) / warps, warps * 32, 0, stream>>>(
-      cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, out_score, out_idx);
+      cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, (long long)n_queries * kc,
+      (long long)n_queries * kc, out_score, out_idx);
   return cudaGetLastError();
 }
 cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx, int n_lists, int n_queries, int kc,
-                             int k, float* out_score, long long* out_idx, cudaStream_t stream) {
+                             int k, long long score_list_stride, long long idx_list_stride, float* out_score,
+                             long long* out_idx, cudaStream_t stream) {
   if (n_lists > 256) return cudaErrorInvalidValue;
   const int warps = 4;
   merge_topk_kernel<long long><<<(n_queries + warps - 1) / warps, warps * 32, 0, stream>>>(
-      cand_score, cand_idx, n_lists, n_queries, kc, k, 0, out_score, out_idx);
+      cand_score, cand_idx, n_lists, n_queries, kc, k, 0, score_list_stride, idx_list_stride, out_score, out_idx);
   return cudaGetLastError();
 }
 

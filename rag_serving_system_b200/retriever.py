@@ -1,0 +1,304 @@
+"""Drop-in retriever classes backed by the sm_100a C-ABI extension.
+
+The call surface is the reference's (``rag_service/core/retriever.py``; citations below are
+``retriever.py:<line>`` in the reference checkout):
+
+    CupyRetriever(doc_embeddings, documents)          retriever.py:566
+      .retrieve(query_emb, k=2)        -> List[str]   retriever.py:615
+      .batch_retrieve(Q, ks)           -> List[List[str]]   retriever.py:686
+      .documents / .N_A / .D                           retriever.py:589-591
+
+so ``main.py:52`` and ``batch_processor.py:95`` work unchanged when this module stands in for
+``rag_service.core.retriever``.  Added on top (north_star): ``search`` -> (indices, scores) and
+``retrieve_with_scores`` -> (indices, scores, contexts).
+
+There is NO CPU fallback: constructing a retriever without the built extension or without an
+sm_100 GPU raises (the reference's ctor also raises when the device copy fails,
+retriever.py:584-586).
+"""
+from __future__ import annotations
+
+import json
+import logging
+import math
+import threading
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _cabi
+
+log = logging.getLogger(__name__)
+
+_INGEST_ROWS = 1 << 16
+
+
+def _auto_query_terms(q: np.ndarray, dtype: str) -> int:
+    """1 if every query value is exactly representable in the corpus storage type (then a single
+    tensor-core pass is exact), else 2 (hi + lo split, so fp32 queries keep their value)."""
+    if dtype == "fp32":
+        return 2
+    if dtype == "bf16":
+        return 1 if not np.any(q.view(np.uint32) & np.uint32(0xFFFF)) else 2
+    with np.errstate(over="ignore"):
+        return 1 if np.array_equal(q.astype(np.float16).astype(np.float32), q) else 2
+
+
+def _fp32_scale_exp(max_abs: float) -> int:
+    """Power-of-two pre-scale for fp32 storage (two fp16 planes): put max|x| in [2^3, 2^4) so the
+    hi plane is far from fp16 overflow and the lo plane stays in the normal range."""
+    if not (max_abs > 0.0) or not math.isfinite(max_abs):
+        return 0
+    return 3 - math.frexp(max_abs)[1] + 1
+
+
+class B200Retriever:
+    """Similarity + top-k over a device-resident corpus, one shard per device.
+
+    metric="cosine" reproduces ``CupyRetriever.distance_cosine`` (retriever.py:594-611),
+    metric="dot" reproduces ``SimpleRetriever`` (retriever.py:112).  ``dtype`` is the HBM storage
+    type of the corpus ("fp32" keeps reference precision; "bf16"/"fp16" halve the bytes streamed).
+    Ties are broken by the lower index (north_star contract; the reference is inconsistent).
+    """
+
+    def __init__(self, doc_embeddings: np.ndarray, documents: Sequence[str], *, dtype: str = "fp32",
+                 metric: str = "cosine", devices: Optional[Sequence[int]] = None, max_batch: int = 256,
+                 max_k: int = 128, query_terms: Optional[int] = None):
+        if not isinstance(doc_embeddings, np.ndarray) or doc_embeddings.ndim != 2:
+            raise ValueError("doc_embeddings must be a 2-D numpy array")
+        if dtype not in _cabi.DTYPES or metric not in _cabi.METRICS:
+            raise ValueError(f"dtype in {list(_cabi.DTYPES)}, metric in {list(_cabi.METRICS)}")
+        if doc_embeddings.dtype not in (np.float32, np.float16):     # retriever.py:576-578
+            doc_embeddings = doc_embeddings.astype(np.float32)
+        self._setup(doc_embeddings.shape[0], doc_embeddings.shape[1], documents, dtype, metric, devices,
+                    max_batch, max_k, query_terms)
+        scale_exp = 0
+        if dtype == "fp32":
+            scale_exp = _fp32_scale_exp(float(np.abs(doc_embeddings).max()) if doc_embeddings.size else 0.0)
+        self._create_shards(scale_exp)
+        try:
+            for ix in self._shards:                                   # retriever.py:582 (H2D of the corpus)
+                lo = ix.row_offset
+                for r in range(0, ix.n_rows, _INGEST_ROWS):
+                    n = min(_INGEST_ROWS, ix.n_rows - r)
+                    ix.load_rows(doc_embeddings[lo + r: lo + r + n], r)
+                ix.finalize()
+        except Exception:
+            log.error("Failed to move document embeddings to the device", exc_info=True)   # retriever.py:584-586
+            self.close()
+            raise
+        log.info("Initialized B200Retriever with %d documents (Dim=%d, dtype=%s, metric=%s, devices=%s)",
+                 self.N_A, self.D, dtype, metric, self._devices)
+
+    # ------------------------------------------------------------------ alternative constructors
+    @classmethod
+    def from_npy(cls, embeddings_path: str, contexts_path: Optional[str] = None, **kw) -> "B200Retriever":
+        """main.py:20-23: a JSON list of strings + an .npy of embeddings (memory-mapped here)."""
+        emb = np.load(embeddings_path, mmap_mode="r")
+        docs = json.load(open(contexts_path)) if contexts_path else [str(i) for i in range(emb.shape[0])]
+        return cls(np.asarray(emb), docs, **kw)
+
+    @classmethod
+    def from_synthetic(cls, n_rows: int, dim: int = 1024, seed: int = 1234, documents=None, **kw) -> "B200Retriever":
+        """Corpus generated ON DEVICE per shard (oracle: retrieval_oracle.synth_rows)."""
+        self = cls.__new__(cls)
+        docs = documents if documents is not None else _LazyDocs(n_rows)
+        self._setup(n_rows, dim, docs, kw.pop("dtype", "bf16"), kw.pop("metric", "dot"), kw.pop("devices", None),
+                    kw.pop("max_batch", 256), kw.pop("max_k", 128), kw.pop("query_terms", None))
+        self._create_shards(4 if self._dtype == "fp32" else 0)   # unit-norm rows: |x| < 1
+        for ix in self._shards:
+            ix.fill_synthetic(seed)
+            ix.finalize()
+        return self
+
+    # ------------------------------------------------------------------ internals
+    def _setup(self, n, d, documents, dtype, metric, devices, max_batch, max_k, query_terms):
+        self.documents = documents            # retriever.py:589 (kept on host, not copied)
+        self.N_A = int(n)                     # retriever.py:590
+        self.D = int(d)                       # retriever.py:591
+        self._dtype, self._metric = dtype, metric
+        self._devices = list(devices) if devices else [0]
+        self._max_batch, self._max_k = int(max_batch), int(max_k)
+        self._query_terms = query_terms
+        self._shards: List[_cabi.Index] = []
+        self._lock = threading.Lock()
+
+    def _create_shards(self, scale_exp: int):
+        G = len(self._devices)
+        per = -(-self.N_A // G)
+        for g, dev in enumerate(self._devices):
+            lo = min(self.N_A, g * per)
+            hi = min(self.N_A, lo + per)
+            if hi > lo:
+                self._shards.append(_cabi.Index(hi - lo, self.D, self._dtype, device=dev, row_offset=lo,
+                                                max_batch=self._max_batch, max_k=self._max_k,
+                                                scale_exp=scale_exp))
+
+    def close(self):
+        for ix in getattr(self, "_shards", []):
+            ix.close()
+        self._shards = []
+
+    # ------------------------------------------------------------------ numeric API (added)
+    def search(self, queries: np.ndarray, k: int, metric: Optional[str] = None,
+               query_terms: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """(indices int64[B,k], scores float32[B,k]); rows past min(k, N) are (-1, -inf)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.D:
+            raise ValueError(f"queries must be [B, {self.D}]")
+        if k <= 0:
+            raise ValueError("k must be positive")
+        metric = metric or self._metric
+        terms = query_terms or self._query_terms or _auto_query_terms(q, self._dtype)
+        B = q.shape[0]
+        out_i = np.full((B, k), -1, dtype=np.int64)
+        out_s = np.full((B, k), -np.inf, dtype=np.float32)
+        kk = min(k, self._max_k)
+        if kk < k:
+            raise ValueError(f"k={k} exceeds max_k={self._max_k} given at construction")
+        with self._lock:
+            for b0 in range(0, B, self._max_batch):
+                qb = q[b0:b0 + self._max_batch]
+                if len(self._shards) == 1:
+                    i, s = self._shards[0].search(qb, k, metric, terms)
+                else:
+                    i, s = self._search_multi(qb, k, metric, terms)
+                out_i[b0:b0 + len(qb)] = i
+                out_s[b0:b0 + len(qb)] = s
+        return out_i, out_s
+
+    def _search_multi(self, q, k, metric, terms):
+        """Single-process multi-GPU: every shard searches concurrently (ctypes drops the GIL), the
+        B x k candidates of each GPU are gathered on the first device and merged there."""
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(self._shards)) as ex:
+            parts = list(ex.map(lambda ix: ix.search(q, k, metric, terms), self._shards))
+        dev = torch.device("cuda", self._shards[0].device)
+        B = q.shape[0]
+        ci = torch.from_numpy(np.stack([p[0] for p in parts])).to(dev)
+        cs = torch.from_numpy(np.stack([p[1] for p in parts])).to(dev)
+        oi = torch.empty((B, k), dtype=torch.int64, device=dev)
+        os_ = torch.empty((B, k), dtype=torch.float32, device=dev)
+        _cabi.merge_device(dev.index, cs.data_ptr(), ci.data_ptr(), len(parts), B, k, k, oi.data_ptr(),
+                           os_.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        return oi.cpu().numpy(), os_.cpu().numpy()
+
+    def retrieve_with_scores(self, queries: np.ndarray, k: int):
+        """north_star triple: (indices, scores, contexts)."""
+        idx, sc = self.search(queries, k)
+        ctx = [[self.documents[j] for j in row if j >= 0] for row in idx]
+        return idx, sc, ctx
+
+    # ------------------------------------------------------------------ reference surface
+    def retrieve(self, query_emb: np.ndarray, k: int = 2) -> List[str]:
+        """retriever.py:615-683: one query, (D,) or (1,D); [] on any error, never raises."""
+        if not isinstance(query_emb, np.ndarray):                         # :629-631
+            log.error("retrieve expects query_emb as NumPy array, got %s", type(query_emb))
+            return []
+        if query_emb.ndim == 2 and query_emb.shape[0] == 1:               # :632-634
+            query_emb = query_emb.flatten()
+        elif query_emb.ndim != 1:                                         # :635-637
+            log.error("retrieve expects a 1D query embedding or (1, dim), got shape %s", query_emb.shape)
+            return []
+        if query_emb.shape[0] != self.D:                                  # :638-640
+            log.error("Query embedding dimension (%d) does not match document embedding dimension (%d)",
+                      query_emb.shape[0], self.D)
+            return []
+        try:
+            actual_k = min(k, self.N_A)                                   # :643
+            if actual_k <= 0:                                             # :644-646
+                log.warning("Requested k=%s results in actual_k=%s. Returning empty list.", k, actual_k)
+                return []
+            idx, _ = self.search(query_emb.reshape(1, self.D), actual_k)
+            return [self.documents[i] for i in idx[0] if i >= 0]          # :675
+        except Exception as e:                                            # :681-683
+            log.error("Error during retrieve: %s", e, exc_info=True)
+            return []
+
+    def batch_retrieve(self, query_embeddings: np.ndarray, ks: List[int]) -> List[List[str]]:
+        """retriever.py:686-799: validation order and empty-list conventions preserved; the scores,
+        per-row select and ordering (:742-769) run in the fused kernel at max_k, rows are then
+        sliced to k_i (:776-790)."""
+        if not isinstance(query_embeddings, np.ndarray):                  # :705-707
+            log.error("batch_retrieve expects query_embeddings as NumPy array, got %s", type(query_embeddings))
+            return [[] for _ in ks]
+        if query_embeddings.ndim != 2:                                    # :708-710
+            log.error("batch_retrieve expects a 2D query_embeddings array, got %d dimensions.", query_embeddings.ndim)
+            return [[] for _ in ks]
+        batch_size = query_embeddings.shape[0]
+        if batch_size == 0:                                               # :711-713
+            return []
+        if not isinstance(ks, list) or batch_size != len(ks):             # :714-716
+            log.error("Batch retrieve size mismatch: %d embeddings vs %s k values.", batch_size,
+                      len(ks) if hasattr(ks, "__len__") else "?")
+            return [[] for _ in range(batch_size)]
+        if query_embeddings.shape[1] != self.D:                           # :717-719
+            log.error("Batch query embedding dimension (%d) does not match document embedding dimension (%d)",
+                      query_embeddings.shape[1], self.D)
+            return [[] for _ in ks]
+        if not all(isinstance(k_val, int) for k_val in ks):               # :720-722
+            log.error("List ks must contain only integers.")
+            return [[] for _ in ks]
+        valid_ks = [k_val for k_val in ks if k_val > 0]                   # :725
+        if not valid_ks:                                                  # :726-728
+            log.warning("All k values in ks are non-positive. Returning list of empty lists.")
+            return [[] for _ in ks]
+        max_k = min(max(valid_ks), self.N_A)                              # :729-730
+        if max_k <= 0:                                                    # :731-732
+            return [[] for _ in ks]
+        try:
+            idx, _ = self.search(query_embeddings, max_k)                 # :736-773
+            docs = self.documents
+            out: List[List[str]] = []
+            for i in range(batch_size):                                   # :776-790
+                k_i = ks[i]
+                if k_i <= 0:
+                    out.append([])
+                    continue
+                row = idx[i]
+                out.append([docs[j] for j in row[row >= 0][:k_i]])
+            return out
+        except Exception as e:                                            # :796-799
+            log.error("Error during batch_retrieve: %s", e, exc_info=True)
+            return [[] for _ in ks]
+
+    def stats(self) -> List[dict]:
+        return [ix.stats() for ix in self._shards]
+
+
+class _LazyDocs:
+    """Stand-in document list for synthetic corpora: documents[i] == "doc-i" without storing N strings."""
+
+    def __init__(self, n):
+        self._n = n
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        i = int(i)
+        if i < 0 or i >= self._n:
+            raise IndexError(i)
+        return f"doc-{i}"
+
+
+class CupyRetriever(B200Retriever):
+    """Name-compatible replacement for the class ``main.py:52`` constructs: cosine similarity,
+    fp32-precision storage, positional (doc_embeddings, documents) constructor."""
+
+    def __init__(self, doc_embeddings: np.ndarray, documents: List[str], **kw):
+        kw.setdefault("metric", "cosine")
+        kw.setdefault("dtype", "fp32")
+        super().__init__(doc_embeddings, documents, **kw)
+
+
+class SimpleRetriever(B200Retriever):
+    """GPU-backed replacement for the reference's NumPy class (retriever.py:57-166): raw dot product."""
+
+    def __init__(self, doc_embeddings: np.ndarray, documents: List[str], **kw):
+        kw.setdefault("metric", "dot")
+        kw.setdefault("dtype", "fp32")
+        super().__init__(doc_embeddings, documents, **kw)

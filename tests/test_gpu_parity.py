@@ -1,0 +1,347 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+the oracle on the same seeded inputs and against the reference-generated golden fixtures.
+
+Bars (north_star): top-k index sets identical (ties -> lower index; a substitution is accepted
+only inside the rounding band around the k-th score and is reported), scores within 1e-5
+relative for fp32 storage, 2e-3 for bf16/fp16."""
+import numpy as np
+import pytest
+
+from oracle import retrieval_oracle as o
+from rag_serving_system_b200 import CupyRetriever, SimpleRetriever, B200Retriever, _cabi
+
+pytestmark = pytest.mark.gpu
+
+DT = {"bf16": o.DTYPE_BF16, "fp16": o.DTYPE_FP16, "fp32": o.DTYPE_FP32}
+RTOL = {"bf16": 2e-3, "fp16": 2e-3, "fp32": 1e-5}
+
+
+def make_index(E, dtype, scale_exp=0, **kw):
+    ix = _cabi.Index(E.shape[0], E.shape[1], dtype, scale_exp=scale_exp, **kw)
+    ix.load_rows(E)
+    ix.finalize()
+    return ix
+
+
+def exact_scores(Q, E, dtype, metric, terms, scale_exp=0):
+    Dv = o.stored_values(E, DT[dtype], scale_exp)
+    Qv = Q.astype(np.float64) if (terms == 2 or dtype == "fp32") else o.round_to_dtype(Q, DT[dtype]).astype(np.float64)
+    return o.scores(Qv, Dv, metric, accum=np.float64)
+
+
+def run_case(E, Q, k, dtype, metric, terms, scale_exp=0, exact_idx=False):
+    ix = make_index(E, dtype, scale_exp, max_batch=max(64, len(Q)), max_k=max(16, k))
+    try:
+        idx, sc = ix.search(Q, k, metric, terms)
+        S = exact_scores(Q, E, dtype, metric, terms, scale_exp)
+        swaps = o.check_topk(idx, sc, S, k, rtol=RTOL[dtype], atol=1e-6)
+        if exact_idx:
+            eidx, _ = o.topk_rows(S, k)
+            assert (idx == eidx).all()
+        return idx, sc, swaps
+    finally:
+        ix.close()
+
+
+# ---------------------------------------------------------------- ingest / layout: bit-exact
+@pytest.mark.parametrize("dtype", ["bf16", "fp16", "fp32"])
+def test_ingest_image_and_roundtrip_bit_exact(squad, dtype):
+    E = squad.E[:333]                                     # ragged: not a multiple of the 128-row tile
+    se = 4 if dtype == "fp32" else 0
+    ix = make_index(E, dtype, se)
+    try:
+        img = ix.get_image(0, ix.stats()["corpus_bytes"]).view(np.uint16)
+        assert np.array_equal(img, o.tile_corpus(o.corpus_planes_u16(E, DT[dtype], se)))
+        rows = ix.get_rows(0, len(E))
+        assert np.array_equal(rows, o.stored_values(E, DT[dtype], se).astype(np.float32))
+        nr = ix.get_norms(0, len(E))
+        assert np.allclose(nr, np.linalg.norm(rows.astype(np.float64), axis=1), rtol=1e-6)
+        part = ix.get_rows(130, 70)
+        assert np.array_equal(part, rows[130:200])
+    finally:
+        ix.close()
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16", "fp32"])
+def test_synthetic_generator_bit_exact_any_shard(dtype):
+    N, D, g0 = 700, 1024, 123_456_789
+    ix = _cabi.Index(N, D, dtype, row_offset=g0, scale_exp=4 if dtype == "fp32" else 0)
+    try:
+        ix.fill_synthetic(1234)                           # local row i == global row g0 + i
+        ix.finalize()
+        exp32 = o.synth_rows(1234, g0 + np.arange(N), D)
+        se = 4 if dtype == "fp32" else 0
+        assert np.array_equal(ix.get_rows(0, N), o.stored_values(exp32, DT[dtype], se).astype(np.float32))
+    finally:
+        ix.close()
+
+
+def test_bf16_source_rows_load_bit_exact(squad):
+    bits = o.bf16_bits(squad.E[:200])
+    ix = _cabi.Index(200, 1024, "bf16")
+    try:
+        ix.load_rows(bits, 0, src_dtype="bf16")
+        ix.load_rows(squad.E[100:200], 100)               # chunked ingest at an offset, fp32 source
+        ix.finalize()
+        assert np.array_equal(ix.get_rows(0, 200), o.round_to_bf16(squad.E[:200]))
+    finally:
+        ix.close()
+
+
+# ---------------------------------------------------------------- golden fixtures (reference outputs)
+def test_fp32_dot_equals_reference_golden(golden):
+    idx, sc, _ = run_case(golden.E, golden.Q, golden.k, "fp32", "dot", 2, scale_exp=4)
+    assert (idx == golden.idx_fixed).all()               # identical to the unmodified SimpleRetriever
+
+
+def test_drop_in_classes_equal_reference_golden(golden):
+    s = SimpleRetriever(golden.E, golden.contexts)
+    assert s.batch_retrieve(golden.Q, [golden.k] * len(golden.Q)) == golden.texts
+    got = s.batch_retrieve(golden.Q, golden.ks_var)
+    for row, exp in zip(got, golden.idx_var):
+        assert row == [golden.contexts[i] for i in exp if i >= 0]
+    assert s.retrieve(golden.E[7], 1) == [golden.contexts[7]]
+    s.close()
+    c = CupyRetriever(golden.E, golden.contexts)          # cosine: same ranking on unit-norm corpora
+    assert c.batch_retrieve(golden.Q, [golden.k] * len(golden.Q)) == golden.texts
+    ref = o.CupyRetrieverPort(golden.E, golden.contexts)
+    assert c.batch_retrieve(golden.Q, golden.ks_var) == ref.batch_retrieve(golden.Q, golden.ks_var)
+    assert c.retrieve(golden.Q[1], 3) == ref.retrieve(golden.Q[1], 3)
+    assert c.batch_retrieve(golden.Q[:, :5], [1] * len(golden.Q)) == [[] for _ in golden.Q]
+    idx, sc, ctx = c.retrieve_with_scores(golden.Q, golden.k)
+    S = o.scores_cosine(golden.Q.astype(np.float64), golden.E.astype(np.float64), accum=np.float64)
+    o.check_topk(idx, sc, S, golden.k, rtol=1e-5, atol=1e-7)
+    assert ctx == golden.texts
+    c.close()
+
+
+def test_self_retrieval_kat_all_dtypes(golden):
+    for dtype in ("bf16", "fp16", "fp32"):
+        r = B200Retriever(golden.E, golden.contexts, dtype=dtype, metric="cosine")
+        idx, sc = r.search(golden.E[:64], 1)
+        assert (idx[:, 0] == np.arange(min(64, len(golden.E)))).all()
+        assert np.abs(sc[:, 0] - 1.0).max() < (3e-3 if dtype != "fp32" else 1e-5)
+        r.close()
+
+
+# ---------------------------------------------------------------- sweeps against the oracle
+@pytest.mark.parametrize("dtype,terms", [("bf16", 1), ("bf16", 2), ("fp16", 1), ("fp16", 2), ("fp32", 2)])
+@pytest.mark.parametrize("metric", ["dot", "cosine"])
+def test_squad_parity(squad, dtype, terms, metric):
+    run_case(squad.E, squad.Q, 10, dtype, metric, terms, scale_exp=4 if dtype == "fp32" else 0)
+
+
+@pytest.mark.parametrize("B", [1, 2, 7, 8, 31, 33, 64, 65, 100, 200])
+def test_batch_sizes(squad, B):
+    rng = np.random.default_rng(B)
+    Q = (squad.E[rng.integers(0, 1000, B)] + 0.05 * rng.standard_normal((B, 1024))).astype(np.float32)
+    run_case(squad.E, Q, 5, "bf16", "dot", 1)
+    if B in (1, 33, 100):
+        run_case(squad.E, Q, 5, "fp32", "cosine", 2, scale_exp=4)
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 10, 16, 17, 32, 100, 128])
+def test_k_values(squad, k):
+    run_case(squad.E, squad.Q[:16], k, "bf16", "dot", 1)
+    if k in (1, 16, 17, 100):
+        run_case(squad.E, squad.Q[:16], k, "fp32", "cosine", 2, scale_exp=4)
+
+
+@pytest.mark.parametrize("n", [1, 5, 127, 128, 129, 255, 1000])
+def test_ragged_and_tiny_corpora(squad, n):
+    idx, sc, _ = run_case(squad.E[:n], squad.Q[:8], 10, "bf16", "dot", 1)
+    if n < 10:                                            # N < k: -1 / -inf padding (retriever.py:767-769)
+        assert (idx[:, n:] == -1).all() and np.isneginf(sc[:, n:]).all()
+
+
+@pytest.mark.parametrize("D", [64, 128, 384, 768, 2048])
+def test_other_dims(D):
+    rng = np.random.default_rng(D)
+    E = rng.standard_normal((600, D)).astype(np.float32)
+    Q = rng.standard_normal((12, D)).astype(np.float32)   # un-normalised, like the service's queries
+    run_case(E, Q, 10, "bf16", "cosine", 2)
+    run_case(E, Q, 10, "fp32", "dot", 2, scale_exp=retriever_scale(E))
+
+
+def retriever_scale(E):
+    from rag_serving_system_b200.retriever import _fp32_scale_exp
+    return _fp32_scale_exp(float(np.abs(E).max()))
+
+
+def test_many_tiles_per_cta_and_all_ctas():
+    N = 128 * 148 * 3 + 77
+    E = o.synth_rows(7, np.arange(N))
+    rng = np.random.default_rng(1)
+    src = rng.integers(0, N, 32)
+    src[:4] = [0, N - 1, 128 * 148, 128 * 148 * 3]        # first row, last (ragged) row, tile boundaries
+    Q = o.round_to_bf16(E[src] + 0.02 * rng.standard_normal((32, 1024)).astype(np.float32))
+    for dtype, terms, metric in (("bf16", 1, "dot"), ("fp16", 1, "cosine"), ("fp32", 2, "dot")):
+        idx, sc, _ = run_case(E, Q, 10, dtype, metric, terms, scale_exp=4 if dtype == "fp32" else 0)
+        assert (idx[:, 0] == src).all()
+
+
+# ---------------------------------------------------------------- ties, degenerate inputs
+def test_duplicate_rows_tie_to_lower_index(squad):
+    E = squad.E[:600].copy()
+    E[100] = E[0]
+    E[599] = E[0]
+    E[300] = E[200]
+    Q = np.stack([E[0], E[200]])
+    for dtype, terms in (("bf16", 1), ("fp32", 2)):
+        for metric in ("dot", "cosine"):
+            idx, sc, _ = run_case(E, Q, 4, dtype, metric, terms, scale_exp=4 if dtype == "fp32" else 0)
+            assert idx[0, :3].tolist() == [0, 100, 599] and idx[1, :2].tolist() == [200, 300]
+            i1, _, _ = run_case(E, Q, 1, dtype, metric, terms, scale_exp=4 if dtype == "fp32" else 0)
+            assert i1[:, 0].tolist() == [0, 200]          # at the k boundary the LOWER index stays
+
+
+def test_all_equal_rows_and_zero_query():
+    E = np.tile(np.linspace(-1, 1, 256, dtype=np.float32), (700, 1))
+    Q = np.stack([E[0], -E[0], np.zeros(256, np.float32)])
+    for metric in ("dot", "cosine"):
+        idx, sc, _ = run_case(E, Q, 12, "bf16", metric, 1, exact_idx=True)
+        assert (idx == np.arange(12)).all()               # every score ties -> first k rows, in order
+
+
+def test_negative_scores_and_cosine_clip(squad):
+    E = squad.E[:500]
+    Q = -squad.Q[:8]                                      # every similarity negative (thr < 0 branch)
+    run_case(E, Q, 10, "bf16", "cosine", 1)
+    run_case(E, Q * 37.5, 10, "fp32", "cosine", 2, scale_exp=4)
+    big = (squad.E[:500] * 50).astype(np.float32)         # un-normalised corpus: norms vary per row
+    big[::3] *= 0.01
+    run_case(big, squad.Q[:8], 10, "bf16", "cosine", 2)
+    run_case(big, squad.Q[:8], 10, "fp32", "dot", 2, scale_exp=retriever_scale(big))
+
+
+# ---------------------------------------------------------------- merge + multi-shard
+def test_merge_device_matches_oracle():
+    import torch
+    rng = np.random.default_rng(3)
+    for G, B, kc, k in ((2, 32, 10, 10), (8, 5, 7, 7), (148, 3, 10, 10), (4, 2, 100, 100), (3, 4, 6, 4)):
+        s = np.sort(rng.integers(-5, 6, size=(G, B, kc)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+        i = rng.permutation(G * B * kc).reshape(G, B, kc).astype(np.int64)
+        i[-1, :, kc // 2:] = -1                            # padding entries
+        order = np.lexsort((i, -s), axis=2)                # each list sorted (score desc, idx asc)
+        s, i = np.take_along_axis(s, order, 2), np.take_along_axis(i, order, 2)
+        s[i < 0] = -np.inf
+        ts, ti = torch.from_numpy(s).cuda(), torch.from_numpy(i).cuda()
+        oi = torch.empty((B, k), dtype=torch.int64, device="cuda")
+        os_ = torch.empty((B, k), dtype=torch.float32, device="cuda")
+        _cabi.merge_device(0, ts.data_ptr(), ti.data_ptr(), G, B, kc, k, oi.data_ptr(), os_.data_ptr(),
+                           torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        ei, es = o.merge_candidates(s, i, k)
+        assert np.array_equal(oi.cpu().numpy(), ei) and np.array_equal(os_.cpu().numpy(), es)
+
+
+def test_row_offset_and_two_shards_equal_one(squad):
+    E, Q, k = squad.E, squad.Q, 10
+    full, _, _ = run_case(E, Q, k, "bf16", "dot", 1)
+    a = _cabi.Index(600, 1024, "bf16", row_offset=0)
+    b = _cabi.Index(400, 1024, "bf16", row_offset=600)
+    try:
+        a.load_rows(E[:600]); a.finalize()
+        b.load_rows(E[600:]); b.finalize()
+        ia, sa = a.search(Q, k, "dot", 1)
+        ib, sb = b.search(Q, k, "dot", 1)
+        assert ib.min() >= 600
+        mi, ms = o.merge_candidates(np.stack([sa, sb]), np.stack([ia, ib]), k)
+        assert (mi == full).all()
+    finally:
+        a.close(); b.close()
+
+
+def test_device_buffer_entry_point(squad):
+    import torch
+    ix = make_index(squad.E, "bf16")
+    try:
+        q = torch.from_numpy(squad.Q).cuda()
+        oi = torch.empty((32, 10), dtype=torch.int64, device="cuda")
+        os_ = torch.empty((32, 10), dtype=torch.float32, device="cuda")
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            ix.search_device(q.data_ptr(), 32, 10, oi.data_ptr(), os_.data_ptr(), "dot", 1, st.cuda_stream)
+        st.synchronize()
+        hi, hs = ix.search(squad.Q, 10, "dot", 1)
+        assert np.array_equal(oi.cpu().numpy(), hi) and np.array_equal(os_.cpu().numpy(), hs)
+        assert ix.kernel_times_ms(2).min() > 0
+    finally:
+        ix.close()
+
+
+def test_errors_are_loud(squad):
+    ix = _cabi.Index(100, 1024, "bf16", max_batch=8, max_k=4)
+    try:
+        with pytest.raises(_cabi.RsError, match="rs_finalize"):
+            ix.search(squad.Q[:2], 2)
+        ix.load_rows(squad.E[:100]); ix.finalize()
+        with pytest.raises(_cabi.RsError):
+            ix.search(squad.Q[:9], 2)                      # B > max_batch
+        with pytest.raises(_cabi.RsError):
+            ix.search(squad.Q[:2], 5)                      # k > max_k
+        with pytest.raises(_cabi.RsError):
+            ix.load_rows(squad.E[:10], 95)                 # rows out of range
+    finally:
+        ix.close()
+
+
+# ---------------------------------------------------------------- BASELINE sizes: size-independent properties
+def test_config3_1m_fp32_torch_crosscheck():
+    """1M x 1024 fp32 (BASELINE configs[2]): cross-check against a torch fp32 restatement
+    (TF32 off) of the same arithmetic - labelled a restatement, not the reference."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    N, D, k = 1_000_000, 1024, 10
+    ix = _cabi.Index(N, D, "fp32", scale_exp=4, max_batch=128, max_k=16)
+    try:
+        ix.fill_synthetic(1234, 0)
+        ix.finalize()
+        Q, src = o.synth_queries(11, N, 128, D, dtype=o.DTYPE_FP32)
+        rows = torch.empty((N, D), dtype=torch.float32, device="cuda")
+        step = 1 << 15
+        for r in range(0, N, step):
+            rows[r:r + step] = torch.from_numpy(ix.get_rows(r, min(step, N - r))).cuda()
+        for B in (1, 32, 128):
+            idx, sc = ix.search(Q[:B], k, "dot", 2)
+            assert (idx[:, 0] == src[:B]).all()
+            S = (torch.from_numpy(Q[:B]).cuda().double() @ rows.double().T).cpu().numpy()
+            o.check_topk(idx, sc, S, k, rtol=1e-5, atol=1e-7)
+    finally:
+        ix.close()
+
+
+def test_config4_10m_bf16_properties():
+    """10M x 1024 bf16, B=32, k=10 (the headline config) through size-independent properties:
+    self-retrieval across the whole index range, returned scores re-derived from regenerated
+    rows, determinism, and full search == merge of two half-corpus searches."""
+    N, D, B, k = 10_000_000, 1024, 32, 10
+    ix = _cabi.Index(N, D, "bf16", max_batch=64, max_k=16)
+    try:
+        ix.fill_synthetic(1234, 0)
+        ix.finalize()
+        rng = np.random.default_rng(0)
+        src = rng.integers(0, N, B)
+        src[:3] = [0, N - 1, N // 2]
+        rows = o.round_to_bf16(o.synth_rows(1234, src, D))
+        Q = o.round_to_bf16(rows + 0.01 * rng.standard_normal((B, D)).astype(np.float32) / 32)
+        idx, sc = ix.search(Q, k, "dot", 1)
+        assert (idx[:, 0] == src).all()
+        assert (np.diff(sc, axis=1) <= 0).all() and (idx >= 0).all() and (idx < N).all()
+        hit = o.round_to_bf16(o.synth_rows(1234, idx.reshape(-1), D)).astype(np.float64).reshape(B, k, D)
+        exact = np.einsum("bkd,bd->bk", hit, Q.astype(np.float64))
+        assert np.abs(sc - exact).max() <= 2e-3 * np.abs(exact).max()
+        idx2, sc2 = ix.search(Q, k, "dot", 1)
+        assert np.array_equal(idx, idx2) and np.array_equal(sc, sc2)
+    finally:
+        ix.close()
+    halves = []
+    for g in range(2):
+        lo, hi = o.shard_range(N, 2, g)
+        h = _cabi.Index(hi - lo, D, "bf16", row_offset=lo, max_batch=64, max_k=16)
+        h.fill_synthetic(1234)
+        h.finalize()
+        halves.append(h.search(Q, k, "dot", 1))
+        h.close()
+    mi, ms = o.merge_candidates(np.stack([h[1] for h in halves]), np.stack([h[0] for h in halves]), k)
+    assert np.array_equal(mi, idx) and np.array_equal(ms, sc)

@@ -1,0 +1,150 @@
+"""CPU tests of the host side above the C ABI: the retriever class's reference-compatible
+conventions (with the device index replaced by an oracle-backed fake - a test double, not a
+product path) and the multi-rank candidate exchange over gloo with world_size 2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import retrieval_oracle as o
+from rag_serving_system_b200 import _cabi, retriever, sharded
+
+
+class FakeIndex:
+    """Test double for _cabi.Index: same surface, answers come from the oracle."""
+
+    def __init__(self, n_rows, dim, dtype="bf16", device=0, row_offset=0, max_batch=256, max_k=128, scale_exp=0):
+        self.n_rows, self.dim, self.dtype, self.device, self.row_offset = n_rows, dim, dtype, device, row_offset
+        self.rows = np.zeros((n_rows, dim), np.float32)
+        self.finalized = False
+
+    def load_rows(self, rows, row0=0, src_dtype=None):
+        self.rows[row0:row0 + len(rows)] = rows
+
+    def finalize(self):
+        self.finalized = True
+
+    def search(self, q, k, metric="dot", query_terms=1):
+        assert self.finalized
+        i, s = o.search(q, self.rows, k, metric)
+        return np.where(i >= 0, i + self.row_offset, -1), s
+
+    def close(self):
+        pass
+
+
+@pytest.fixture()
+def fake_backend(monkeypatch):
+    monkeypatch.setattr(_cabi, "Index", FakeIndex)
+
+
+def test_class_surface_matches_reference(fake_backend, short_facts):
+    g = short_facts
+    r = retriever.CupyRetriever(g.E, g.contexts)
+    assert (r.N_A, r.D) == g.E.shape and r.documents is g.contexts       # retriever.py:589-591
+    ref = o.CupyRetrieverPort(g.E, g.contexts)
+    ks = [g.k] * len(g.Q)
+    assert r.batch_retrieve(g.Q, ks) == ref.batch_retrieve(g.Q, ks)
+    assert r.batch_retrieve(g.Q, g.ks_var) == ref.batch_retrieve(g.Q, g.ks_var)
+    assert r.retrieve(g.Q[3], 4) == ref.retrieve(g.Q[3], 4)
+    assert r.retrieve(g.Q[3].reshape(1, -1)) == ref.retrieve(g.Q[3])     # default k=2, (1,D) accepted
+    s = retriever.SimpleRetriever(g.E, g.contexts)
+    assert s.batch_retrieve(g.Q, ks) == g.texts                          # == unmodified reference output
+
+
+def test_error_conventions_never_raise(fake_backend, short_facts):
+    g = short_facts
+    r = retriever.CupyRetriever(g.E, g.contexts)
+    ref = o.CupyRetrieverPort(g.E, g.contexts)
+    Q = g.Q[:4]
+    cases = [
+        (Q[0], [1]), (Q[:0], []), (Q, [1, 2]), (Q, (1, 1, 1, 1)), (Q[:, :8], [1] * 4),
+        (Q, [1, 1, np.int64(1), 1]), (Q, [0, -1, 0, 0]), (Q, [0, 3, 1000, 1]), (Q.astype(np.float64), [2] * 4),
+    ]
+    for q, ks in cases:
+        assert r.batch_retrieve(q, ks) == ref.batch_retrieve(q, ks), (q.shape, ks)
+    assert r.batch_retrieve("nope", [1, 2]) == [[], []]
+    for q, k in (("nope", 1), (Q, 1), (Q[0], 0), (Q[0], -3), (Q[0, :5], 1), (Q[0], 10 ** 6)):
+        assert r.retrieve(q, k) == ref.retrieve(q, k)
+
+
+def test_retrieve_with_scores_triple_and_multi_shard(fake_backend, squad):
+    g = squad
+    r = retriever.B200Retriever(g.E, g.contexts, metric="dot", dtype="fp32")
+    idx, sc, ctx = r.retrieve_with_scores(g.Q, g.k)
+    assert (idx == g.idx_fixed).all() and ctx == g.texts and sc.shape == idx.shape
+    with pytest.raises(ValueError):
+        r.search(g.Q, 0)
+    with pytest.raises(ValueError):
+        r.search(g.Q[:, :3], 1)
+
+
+def test_auto_query_terms():
+    q = np.random.default_rng(0).standard_normal((4, 64)).astype(np.float32)
+    assert retriever._auto_query_terms(q, "bf16") == 2
+    assert retriever._auto_query_terms(o.round_to_bf16(q), "bf16") == 1
+    assert retriever._auto_query_terms(q, "fp16") == 2
+    assert retriever._auto_query_terms(o.round_to_fp16(q), "fp16") == 1
+    assert retriever._auto_query_terms(o.round_to_fp16(q), "fp32") == 2
+
+
+def test_fp32_scale_exp_keeps_split_in_fp16_range():
+    for m in (1e-3, 0.07, 1.0, 37.5, 6e4):
+        e = retriever._fp32_scale_exp(m)
+        assert 8.0 <= m * 2.0 ** e < 16.0
+    assert retriever._fp32_scale_exp(0.0) == 0
+
+
+# ---------------------------------------------------------------- N>1 exchange step over gloo
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _rank_main(rank, world, port, n, B, k, seed, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(seed)
+        D = rng.integers(-3, 4, size=(n, 16)).astype(np.float32)
+        Q = rng.integers(-3, 4, size=(B, 16)).astype(np.float32)
+        lo, hi = sharded.shard_range(n, world, rank)
+        i, s = o.search(Q, D[lo:hi], k, "dot")                 # stands in for the local fused kernel
+        i = np.where(i >= 0, i + lo, -1)
+        nb = sharded.packed_bytes(B, k)
+        local = torch.zeros(nb, dtype=torch.uint8)
+        li, ls = sharded.pack_views(local, B, k)
+        li.copy_(torch.from_numpy(i))
+        ls.copy_(torch.from_numpy(s))
+        gathered = torch.empty((world, nb), dtype=torch.uint8)
+        sharded.gather_candidates(local, gathered)
+        ci = np.stack([sharded.pack_views(gathered[g], B, k)[0].numpy() for g in range(world)])
+        cs = np.stack([sharded.pack_views(gathered[g], B, k)[1].numpy() for g in range(world)])
+        mi, ms = o.merge_candidates(cs, ci, k)                 # stands in for rs_merge_device
+        gi, gs = o.search(Q, D, k, "dot")
+        ret[rank] = bool((mi == gi).all() and np.array_equal(ms, gs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,B,k", [(1000, 8, 10), (37, 3, 7), (5, 1, 1)])
+def test_candidate_exchange_world2_gloo(n, B, k):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_rank_main, args=(world, _free_port(), n, B, k, 7, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+def test_packed_buffer_alignment():
+    for B, k in ((1, 1), (3, 7), (32, 10), (256, 100)):
+        nb = sharded.packed_bytes(B, k)
+        assert nb % 16 == 0 and nb >= B * k * 12
+        buf = torch.zeros(nb, dtype=torch.uint8)
+        i, s = sharded.pack_views(buf, B, k)
+        assert i.shape == (B, k) and s.shape == (B, k) and i.dtype == torch.int64 and s.dtype == torch.float32
