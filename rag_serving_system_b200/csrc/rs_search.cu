@@ -451,33 +451,59 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
 
 // ------------------------------------------------------------------------------------------
 // merge of sorted candidate lists: one warp per query, each lane walks lists lane, lane+32, ...
-// Ordering everywhere is (score desc, index asc); index < 0 is padding.
+// Ordering everywhere is (score desc, index asc); index < 0 is padding and only occurs at the end
+// of a list.  STAGED: the query's candidates are first copied (coalesced) into shared memory so
+// the k selection rounds run at shared-memory latency instead of k dependent global round trips.
 // ------------------------------------------------------------------------------------------
-template <typename IdxT>
-__global__ void __launch_bounds__(128) merge_topk_kernel(const float* __restrict__ cand_score,
-                                                         const IdxT* __restrict__ cand_idx, int n_lists,
-                                                         int n_queries, int kc, int k, long long idx_offset,
-                                                         long long score_list_stride, long long idx_list_stride,
-                                                         float* __restrict__ out_score,
-                                                         long long* __restrict__ out_idx) {
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (q >= n_queries) return;
-  constexpr int kMaxOwn = 8;  // up to 256 lists
-  int head[kMaxOwn];
+constexpr int kMergeMaxOwn = 8;  // up to 256 lists
+
+template <typename IdxT, bool STAGED>
+__global__ void __launch_bounds__(32) merge_topk_kernel(const float* __restrict__ cand_score,
+                                                        const IdxT* __restrict__ cand_idx, int n_lists,
+                                                        int n_queries, int kc, int k, long long idx_offset,
+                                                        long long score_list_stride, long long idx_list_stride,
+                                                        float* __restrict__ out_score,
+                                                        long long* __restrict__ out_idx) {
+  extern __shared__ __align__(16) uint8_t merge_smem[];
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x;
+  const int total = n_lists * kc;
+  IdxT* s_idx = reinterpret_cast<IdxT*>(merge_smem);
+  float* s_score = reinterpret_cast<float*>(merge_smem + (size_t)total * sizeof(IdxT));
+  if (STAGED) {
+    for (int e = lane; e < total; e += 32) {
+      const int l = e / kc, j = e - l * kc;
+      s_idx[e] = cand_idx[(size_t)l * idx_list_stride + (size_t)q * kc + j];
+      s_score[e] = cand_score[(size_t)l * score_list_stride + (size_t)q * kc + j];
+    }
+    __syncwarp();
+  }
+  auto load = [&](int l, int j, float& s, long long& id) {
+    if (STAGED) {
+      s = s_score[l * kc + j];
+      id = (long long)s_idx[l * kc + j];
+    } else {
+      id = (long long)cand_idx[(size_t)l * idx_list_stride + (size_t)q * kc + j];
+      s = cand_score[(size_t)l * score_list_stride + (size_t)q * kc + j];
+    }
+  };
+  int head[kMergeMaxOwn];
 #pragma unroll
-  for (int i = 0; i < kMaxOwn; ++i) head[i] = 0;
-  for (int r = 0; r < k; ++r) {
-    float bs = -CUDART_INF_F;
-    long long bi = -1;
-    int bown = -1;
+  for (int i = 0; i < kMergeMaxOwn; ++i) head[i] = 0;
+  float bs = -CUDART_INF_F;
+  long long bi = -1;
+  int bown = -1;
+  auto rescan = [&]() {  // best head among the lists this lane owns
+    bs = -CUDART_INF_F;
+    bi = -1;
+    bown = -1;
 #pragma unroll
-    for (int i = 0; i < kMaxOwn; ++i) {
+    for (int i = 0; i < kMergeMaxOwn; ++i) {
       const int l = lane + 32 * i;
       if (l < n_lists && head[i] < kc) {
-        const size_t o = (size_t)q * kc + head[i];
-        const long long id = (long long)cand_idx[(size_t)l * idx_list_stride + o];
-        const float s = cand_score[(size_t)l * score_list_stride + o];
+        float s;
+        long long id;
+        load(l, head[i], s, id);
         if (id >= 0 && (bi < 0 || s > bs || (s == bs && id < bi))) {
           bs = s;
           bi = id;
@@ -485,7 +511,10 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const float* __restrict
         }
       }
     }
-    // warp arg-best on (score desc, idx asc); padding (bi < 0) always loses
+  };
+  rescan();
+  for (int r = 0; r < k; ++r) {
+    // warp arg-best on (score desc, idx asc); padding (index < 0) always loses
     float ws = bs;
     long long wi = bi;
     int wl = lane;
@@ -501,15 +530,24 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const float* __restrict
         wl = ol;
       }
     }
-    if (lane == wl && wi >= 0) {
-#pragma unroll
-      for (int i = 0; i < kMaxOwn; ++i)
-        if (i == bown) ++head[i];
-    }
     if (lane == 0) {
       out_score[(size_t)q * k + r] = wi >= 0 ? ws : -CUDART_INF_F;
       out_idx[(size_t)q * k + r] = wi >= 0 ? wi + idx_offset : -1;
     }
+    if (wi < 0) {  // every list exhausted: the rest is padding
+      for (int rr = r + 1 + lane; rr < k; rr += 32) {
+        out_score[(size_t)q * k + rr] = -CUDART_INF_F;
+        out_idx[(size_t)q * k + rr] = -1;
+      }
+      break;
+    }
+    if (lane == wl) {  // only the winning lane's state changed
+#pragma unroll
+      for (int i = 0; i < kMergeMaxOwn; ++i)
+        if (i == bown) ++head[i];
+      rescan();
+    }
+    __syncwarp();
   }
 }
 
@@ -546,23 +584,39 @@ cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t st
   return reglist ? launch_fused_t<2, true>(p, grid, stream) : launch_fused_t<2, false>(p, grid, stream);
 }
 
+template <typename IdxT>
+static cudaError_t launch_merge_t(const float* cand_score, const IdxT* cand_idx, int n_lists, int n_queries, int kc,
+                                  int k, long long idx_offset, long long score_list_stride,
+                                  long long idx_list_stride, float* out_score, long long* out_idx,
+                                  cudaStream_t stream) {
+  if (n_lists > 32 * kMergeMaxOwn) return cudaErrorInvalidValue;
+  const size_t bytes = (size_t)n_lists * kc * (sizeof(IdxT) + sizeof(float));
+  if (bytes <= 200 * 1024) {
+    auto kern = merge_topk_kernel<IdxT, true>;
+    if (bytes > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e != cudaSuccess) return e;
+    }
+    kern<<<n_queries, 32, bytes, stream>>>(cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset,
+                                           score_list_stride, idx_list_stride, out_score, out_idx);
+  } else {
+    merge_topk_kernel<IdxT, false><<<n_queries, 32, 0, stream>>>(cand_score, cand_idx, n_lists, n_queries, kc, k,
+                                                                 idx_offset, score_list_stride, idx_list_stride,
+                                                                 out_score, out_idx);
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int kc, int k,
                              long long idx_offset, float* out_score, long long* out_idx, cudaStream_t stream) {
-  if (n_lists > 256) return cudaErrorInvalidValue;
-  const int warps = 4;
-  merge_topk_kernel<int><<<(n_queries + warps - 1) / warps, warps * 32, 0, stream>>>(
-      cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, (long long)n_queries * kc,
-      (long long)n_queries * kc, out_score, out_idx);
-  return cudaGetLastError();
+  return launch_merge_t<int>(cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, (long long)n_queries * kc,
+                             (long long)n_queries * kc, out_score, out_idx, stream);
 }
 cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx, int n_lists, int n_queries, int kc,
                              int k, long long score_list_stride, long long idx_list_stride, float* out_score,
                              long long* out_idx, cudaStream_t stream) {
-  if (n_lists > 256) return cudaErrorInvalidValue;
-  const int warps = 4;
-  merge_topk_kernel<long long><<<(n_queries + warps - 1) / warps, warps * 32, 0, stream>>>(
-      cand_score, cand_idx, n_lists, n_queries, kc, k, 0, score_list_stride, idx_list_stride, out_score, out_idx);
-  return cudaGetLastError();
+  return launch_merge_t<long long>(cand_score, cand_idx, n_lists, n_queries, kc, k, 0, score_list_stride,
+                                   idx_list_stride, out_score, out_idx, stream);
 }
 
 }  // namespace rs

@@ -221,10 +221,10 @@ def test_merge_device_matches_oracle():
     for G, B, kc, k in ((2, 32, 10, 10), (8, 5, 7, 7), (148, 3, 10, 10), (4, 2, 100, 100), (3, 4, 6, 4)):
         s = np.sort(rng.integers(-5, 6, size=(G, B, kc)).astype(np.float32), axis=2)[:, :, ::-1].copy()
         i = rng.permutation(G * B * kc).reshape(G, B, kc).astype(np.int64)
-        i[-1, :, kc // 2:] = -1                            # padding entries
-        order = np.lexsort((i, -s), axis=2)                # each list sorted (score desc, idx asc)
+        i[-1, :, kc // 2:] = -1                            # padding entries ...
+        s[i < 0] = -np.inf                                 # ... carry -inf and sit at the END of a list
+        order = np.lexsort((i, -s, i < 0), axis=2)         # each list sorted (score desc, idx asc), pads last
         s, i = np.take_along_axis(s, order, 2), np.take_along_axis(i, order, 2)
-        s[i < 0] = -np.inf
         ts, ti = torch.from_numpy(s).cuda(), torch.from_numpy(i).cuda()
         oi = torch.empty((B, k), dtype=torch.int64, device="cuda")
         os_ = torch.empty((B, k), dtype=torch.float32, device="cuda")
