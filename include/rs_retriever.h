@@ -68,6 +68,10 @@ typedef struct rs_stats {
   int32_t passes;           /* query sub-batches the last search needed */
   int32_t launches;         /* kernels launched by the last search (prep + fused + merge per pass) */
   int32_t query_terms;      /* 1 or 2 */
+  int32_t q_resident;       /* 1: query operand resident in shared memory; 0: streamed through the ring */
+  int32_t sub;              /* 128-document tiles per supertile */
+  int32_t nbuf;             /* TMEM accumulator buffers */
+  int32_t mma_m;            /* MMA M of the last fused kernel (64 or 128) */
   int64_t bytes_streamed;   /* corpus bytes read by the last search (passes * shard bytes) */
   int64_t corpus_bytes;     /* device bytes of the tiled corpus image */
   int64_t total_launches;   /* kernels launched since rs_create */

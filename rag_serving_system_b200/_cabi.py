@@ -40,7 +40,8 @@ class rs_stats(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("sm_count", C.c_int32), ("grid", C.c_int32),
         ("stages", C.c_int32), ("smem_bytes", C.c_int32), ("passes", C.c_int32),
-        ("launches", C.c_int32), ("query_terms", C.c_int32), ("bytes_streamed", C.c_int64),
+        ("launches", C.c_int32), ("query_terms", C.c_int32), ("q_resident", C.c_int32), ("sub", C.c_int32),
+        ("nbuf", C.c_int32), ("mma_m", C.c_int32), ("bytes_streamed", C.c_int64),
         ("corpus_bytes", C.c_int64), ("total_launches", C.c_int64),
     ]
 

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -35,7 +36,8 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 constexpr int kMaxSmem = 232448;  // 227 KiB opt-in dynamic shared memory per CTA on sm_100
-constexpr int kMinStages = 4;
+constexpr int kMinResidentStages = 6;   // resident-Q mode wants a deep ring beside the query image
+constexpr int kMinStreamStages = 7;     // streamed-Q mode: at least one full k-chunk group (<= 6 items) + 1
 constexpr int kMaxStages = 24;
 constexpr int64_t kIngestChunkBytes = 64ll << 20;
 
@@ -44,7 +46,16 @@ struct Plan {
   int passes;
   int bpad;
   int stages;
+  int q_resident;  // whole Q image in shared memory (small batches) vs. Q k-chunks through the ring
+  int sub;         // 128-document tiles per supertile
+  int nbuf;        // TMEM accumulator buffers
+  int mma_m;       // MMA M: 64 when the padded batch fits, else 128
 };
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
 
 }  // namespace
 
@@ -82,23 +93,50 @@ struct rs_index {
 
 namespace {
 
-int max_cap_rows(int kc, int terms, int k) {
-  // largest bpad (multiple of 8, <= 128) that leaves at least kMinStages ring slots
+int max_cap_rows(int kc, int terms, int k, int min_stages, int q_resident) {
+  // largest bpad (multiple of 8, <= 128) that leaves at least min_stages ring slots
   int best = 0;
   for (int bpad = 8; bpad <= 128; bpad += 8) {
-    if (rs::fused_smem_bytes(bpad, kc, terms, kMinStages, k) <= kMaxSmem) best = bpad;
+    if (rs::fused_smem_bytes(bpad, kc, terms, min_stages, k, q_resident) <= kMaxSmem) best = bpad;
   }
   return best;
 }
 
+// Small batches keep the query operand resident in shared memory (one tile per accumulator,
+// double-buffered TMEM).  Larger batches stream Q k-chunks through the ring and amortise each
+// chunk over `sub` document tiles that accumulate side by side in TMEM.
 int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
-  const int cap = max_cap_rows(ix->kc, terms, k);
+  const int nacc = (terms == 2 || ix->planes == 2) ? 2 : 1;
+  const int cap_res = max_cap_rows(ix->kc, terms, k, kMinResidentStages, 1);
+  const int cap_str = max_cap_rows(ix->kc, terms, k, kMinStreamStages, 0);
+  int resident = B <= cap_res ? 1 : 0;
+  resident = env_int("RS_QRESIDENT", resident);
+  const int cap = resident ? cap_res : cap_str;
   if (cap <= 0) return fail(RS_E_UNSUPPORTED, "k=%d with dim=%d does not fit in shared memory", k, ix->cfg.dim);
+  pl->q_resident = resident;
   pl->passes = (B + cap - 1) / cap;
   pl->per_pass = (B + pl->passes - 1) / pl->passes;
   pl->bpad = (pl->per_pass + 7) / 8 * 8;
-  int stages = kMinStages;
-  while (stages < kMaxStages && rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages + 1, k) <= kMaxSmem) ++stages;
+  if (resident) {
+    pl->sub = 1;
+    pl->nbuf = 2;
+  } else {
+    pl->sub = nacc == 1 ? 4 : 2;
+    pl->nbuf = 1;
+  }
+  pl->mma_m = env_int("RS_MMA_M", pl->bpad <= 64 ? 64 : 128);
+  if (pl->mma_m != 128 && !(pl->mma_m == 64 && pl->bpad <= 64)) return fail(RS_E_INVALID, "RS_MMA_M=%d invalid for bpad=%d", pl->mma_m, pl->bpad);
+  pl->sub = env_int("RS_SUB", pl->sub);
+  pl->nbuf = env_int("RS_NBUF", pl->nbuf);
+  const int cols = pl->sub * pl->nbuf * nacc;
+  if (pl->sub < 1 || pl->nbuf < 1 || pl->nbuf > 2 || (cols != 1 && cols != 2 && cols != 4))
+    return fail(RS_E_INVALID, "sub=%d nbuf=%d nacc=%d does not map onto 128/256/512 TMEM columns", pl->sub, pl->nbuf, nacc);
+  int stages = resident ? kMinResidentStages : kMinStreamStages;
+  while (stages < kMaxStages &&
+         rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages + 1, k, resident) <= kMaxSmem)
+    ++stages;
+  if (rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages, k, resident) > kMaxSmem)
+    return fail(RS_E_UNSUPPORTED, "B=%d k=%d does not fit in shared memory", B, k);
   pl->stages = stages;
   return RS_OK;
 }
@@ -140,7 +178,11 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   const int grid = std::min(ix->sm_count, ix->n_tiles);
   ix->stats.grid = grid;
   ix->stats.stages = pl.stages;
-  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, k);
+  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, k, pl.q_resident);
+  ix->stats.q_resident = pl.q_resident;
+  ix->stats.sub = pl.sub;
+  ix->stats.nbuf = pl.nbuf;
+  ix->stats.mma_m = pl.mma_m;
   ix->stats.passes = pl.passes;
   ix->stats.query_terms = terms;
   ix->stats.launches = 0;
@@ -170,6 +212,10 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.metric = metric;
     p.dtype = ix->plane_dtype;
     p.stages = pl.stages;
+    p.q_resident = pl.q_resident;
+    p.sub = pl.sub;
+    p.nbuf = pl.nbuf;
+    p.mma_m = pl.mma_m;
     p.lo_coef = ix->plane_dtype == RS_DTYPE_FP16 ? ldexpf(1.0f, -RS_FP16_SPLIT_SHIFT) : 1.0f;
     const int slot = (int)(ix->ev_count % rs_index::kEventRing);
     RS_CUDA(cudaEventRecord(ix->ev_beg[slot], stream));
@@ -228,7 +274,7 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   ix->stats.corpus_bytes = (int64_t)ix->corpus_bytes;
 
   const int grid = std::min(ix->sm_count, ix->n_tiles);
-  const int cap1 = max_cap_rows(ix->kc, 1, 1);
+  const int cap1 = max_cap_rows(ix->kc, 1, 1, kMinStreamStages, 0);
   if (cap1 <= 0) {
     delete ix;
     return fail(RS_E_UNSUPPORTED, "dim=%d does not fit the shared-memory pipeline", cfg->dim);

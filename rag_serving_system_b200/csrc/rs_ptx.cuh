@@ -120,11 +120,11 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
   const uint64_t hi = (uint64_t)(64u | (1u << 14) | (2u << 29)) << 32;
   return hi | (uint64_t)(((smem_addr >> 4) & 0x3FFFu) | (1u << 16));
 }
-// Instruction descriptor, kind::f16: D=f32, A/B = bf16 or f16, both K-major, M=128, N=n.
+// Instruction descriptor, kind::f16: D=f32, A/B = bf16 or f16, both K-major, M=m (64|128), N=n.
 //  [4,6) c_format=1 | [7,10) a_format | [10,13) b_format | [17,23) N>>3 | [24,29) M>>4
-__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(int is_bf16, int n) {
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(int is_bf16, int m, int n) {
   uint32_t fmt = is_bf16 ? 1u : 0u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 }  // namespace rs

@@ -121,14 +121,16 @@ constexpr int kRegK = 16;                                       // register-resi
 struct SmemMap {
   uint32_t q_bytes, stage_off, bar_off, list_off, total;
 };
-__host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, int stages, int k, bool reglist) {
+// q_resident: the whole Q image lives in shared memory for the kernel's lifetime (small batches);
+// otherwise Q k-chunks travel through the ring next to the document blocks (large batches).
+__host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, int stages, int k, bool reglist,
+                                                 bool q_resident) {
   SmemMap m;
-  m.q_bytes = (uint32_t)terms * kc * bpad * RS_KCHUNK_BYTES;
+  m.q_bytes = q_resident ? (uint32_t)terms * kc * bpad * RS_KCHUNK_BYTES : 0u;
   m.stage_off = m.q_bytes;  // multiple of 1024 because bpad % 8 == 0
   m.bar_off = m.stage_off + (uint32_t)stages * RS_BLOCK_BYTES;
   m.list_off = m.bar_off + 1024;
-  uint32_t nact = (uint32_t)((bpad + 31) / 32);
-  m.total = m.list_off + (reglist ? 0u : (uint32_t)k * nact * 32u * 8u);
+  m.total = m.list_off + (reglist ? 0u : (uint32_t)k * (uint32_t)bpad * 8u);
   return m;
 }
 
@@ -153,6 +155,9 @@ __device__ __forceinline__ float cosine_raw_bound(float thr_cos, float nq, float
   return thr_cos * (nq * ndmax + 1e-8f) * inv_qs * (1.0f + 1e-6f);
 }
 
+// One CTA walks "supertiles" of p.sub consecutive 128-document tiles.  Per supertile the K loop
+// is outermost: for every 64-element k-chunk the (optional) Q blocks arrive once and are reused
+// by the MMAs of all p.sub document blocks, each accumulating into its own TMEM columns.
 template <int NACC, bool REGLIST>
 __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -160,7 +165,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.k, REGLIST);
+  const bool q_resident = p.q_resident != 0;
+  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.k, REGLIST, q_resident);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t q_smem = smem_base;
   const uint32_t stage_smem = smem_base + map.stage_off;
@@ -173,8 +179,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   const uint32_t qfull_bar = bar_base + 8u * (2 * p.stages + 4);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + map.bar_off + 1016);
 
-  const int nact_warps = (p.bpad + 31) / 32;
-  constexpr uint32_t kTmemCols = NACC * 2 * RS_TILE_ROWS;  // 256 or 512
+  // M=128: query row r lives in TMEM lane r.  M=64 (half the tensor work, used when bpad <= 64):
+  // row r lives in lane (r/16)*32 + r%16, i.e. 16 live lanes in each of the four lane quarters.
+  const int rows_per_warp = p.mma_m == 64 ? 16 : 32;
+  const int nact_warps = (p.bpad + rows_per_warp - 1) / rows_per_warp;
+  const int S = p.sub;     // 128-document tiles per supertile
+  const int NB = p.nbuf;   // accumulator buffers in TMEM (2 = epilogue overlaps the next supertile's MMAs)
+  const uint32_t tmem_cols = (uint32_t)(NB * S * NACC) * RS_TILE_ROWS;  // 128, 256 or 512
+  const int n_super = (p.n_tiles + S - 1) / S;
+  const uint32_t qblk = (uint32_t)p.bpad * RS_KCHUNK_BYTES;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
     fence_proxy_async();
   }
   if (warp == kMmaWarp) {
-    tmem_alloc(smem_u32((const void*)tmem_slot), kTmemCols);
+    tmem_alloc(smem_u32((const void*)tmem_slot), tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -198,82 +211,109 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int blocks_per_tile = p.planes * p.kc;
-  const size_t tile_bytes = (size_t)blocks_per_tile * RS_BLOCK_BYTES;
+  const size_t tile_bytes = (size_t)p.planes * p.kc * RS_BLOCK_BYTES;
 
   if (warp == kProducerWarp) {
     // ===================== bulk-copy producer =====================
     if (lane == 0) {
       const uint64_t pol_stream = l2_policy_evict_first();
       const uint64_t pol_keep = l2_policy_evict_last();
-      // queries: resident for the whole kernel
-      mbar_arrive_expect_tx(qfull_bar, map.q_bytes);
-      for (uint32_t off = 0; off < map.q_bytes; off += 32768u) {
-        uint32_t n = min(32768u, map.q_bytes - off);
-        bulk_g2s(q_smem + off, p.qimg + off, n, qfull_bar, pol_keep);
+      if (q_resident) {
+        mbar_arrive_expect_tx(qfull_bar, map.q_bytes);
+        for (uint32_t off = 0; off < map.q_bytes; off += 32768u) {
+          uint32_t n = min(32768u, map.q_bytes - off);
+          bulk_g2s(q_smem + off, p.qimg + off, n, qfull_bar, pol_keep);
+        }
       }
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const uint8_t* src = p.corpus + (size_t)t * tile_bytes;
-        for (int b = 0; b < blocks_per_tile; ++b) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_arrive_expect_tx(full_bar(s), RS_BLOCK_BYTES);
-          bulk_g2s(stage_smem + (uint32_t)s * RS_BLOCK_BYTES, src + (size_t)b * RS_BLOCK_BYTES, RS_BLOCK_BYTES,
-                   full_bar(s), pol_stream);
-          if (++s == p.stages) {
-            s = 0;
-            ph ^= 1u;
-          }
+      auto push = [&](const void* src, uint32_t bytes, uint64_t pol) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_arrive_expect_tx(full_bar(s), bytes);
+        bulk_g2s(stage_smem + (uint32_t)s * RS_BLOCK_BYTES, src, bytes, full_bar(s), pol);
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      };
+      for (int u = blockIdx.x; u < n_super; u += gridDim.x) {
+        const int nsub = min(S, p.n_tiles - u * S);
+        const uint8_t* src = p.corpus + (size_t)u * S * tile_bytes;
+        for (int kc = 0; kc < p.kc; ++kc) {
+          if (!q_resident)
+            for (int j = 0; j < p.terms; ++j) push(p.qimg + (size_t)(j * p.kc + kc) * qblk, qblk, pol_keep);
+          for (int pl = 0; pl < p.planes; ++pl)
+            for (int sub = 0; sub < nsub; ++sub)
+              push(src + (size_t)sub * tile_bytes + (size_t)(pl * p.kc + kc) * RS_BLOCK_BYTES, RS_BLOCK_BYTES,
+                   pol_stream);
         }
       }
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(p.dtype == RS_DTYPE_BF16, RS_TILE_ROWS);
-      const uint32_t qblk = (uint32_t)p.bpad * RS_KCHUNK_BYTES;
-      mbar_wait(qfull_bar, 0);
+      const uint32_t idesc = umma_idesc_f16(p.dtype == RS_DTYPE_BF16, p.mma_m, RS_TILE_ROWS);
+      if (q_resident) mbar_wait(qfull_bar, 0);
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      // 16-byte units: one UMMA K step (16 elements x 2 B) advances the start address by 2
+      auto issue4 = [&](uint32_t d, uint64_t a, uint64_t b, bool fresh) {
+#pragma unroll
+        for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
+          umma_f16(d, a + 2u * ks, b + 2u * ks, idesc, (fresh && ks == 0) ? 0u : 1u);
+      };
+      for (int u = blockIdx.x; u < n_super; u += gridDim.x) {
+        const int nsub = min(S, p.n_tiles - u * S);
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * NACC) * RS_TILE_ROWS;
-        for (int pl = 0; pl < p.planes; ++pl) {
-          for (int kc = 0; kc < p.kc; ++kc) {
-            mbar_wait(full_bar(s), ph);
-            tc_fence_after();
-            const uint64_t bdesc = umma_smem_desc(stage_smem + (uint32_t)s * RS_BLOCK_BYTES);
-            const uint64_t a0 = umma_smem_desc(q_smem + (uint32_t)kc * qblk);
-            const uint64_t a1 = umma_smem_desc(q_smem + (uint32_t)(p.kc + kc) * qblk);
-            // 16-byte units: one UMMA K step (16 elements x 2 B) advances the start address by 2
-            if (pl == 0) {
-#pragma unroll
-              for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
-                umma_f16(d0, a0 + 2u * ks, bdesc + 2u * ks, idesc, (kc | ks) != 0);
-              if (NACC == 2) {
-#pragma unroll
-                for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
-                  umma_f16(d0 + RS_TILE_ROWS, a1 + 2u * ks, bdesc + 2u * ks, idesc, (kc | ks) != 0);
+        const uint32_t dbase = tmem_base + (uint32_t)(acc * S * NACC) * RS_TILE_ROWS;
+        for (int kc = 0; kc < p.kc; ++kc) {
+          uint64_t a0, a1 = 0;
+          int qslot[2] = {0, 0};
+          if (q_resident) {
+            a0 = umma_smem_desc(q_smem + (uint32_t)kc * qblk);
+            a1 = umma_smem_desc(q_smem + (uint32_t)(p.kc + kc) * qblk);
+          } else {
+            uint64_t a[2] = {0, 0};
+            for (int j = 0; j < p.terms; ++j) {
+              mbar_wait(full_bar(s), ph);
+              a[j] = umma_smem_desc(stage_smem + (uint32_t)s * RS_BLOCK_BYTES);
+              qslot[j] = s;
+              if (++s == p.stages) {
+                s = 0;
+                ph ^= 1u;
               }
-            } else {
-              // lo plane of an fp32 corpus: q_hi . d_lo joins the low-order accumulator
-#pragma unroll
-              for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
-                umma_f16(d0 + RS_TILE_ROWS, a0 + 2u * ks, bdesc + 2u * ks, idesc, 1u);
             }
-            umma_commit(empty_bar(s));  // smem slot is free once these MMAs have read it
-            if (++s == p.stages) {
-              s = 0;
-              ph ^= 1u;
+            a0 = a[0];
+            a1 = a[1];
+          }
+          for (int pl = 0; pl < p.planes; ++pl) {
+            for (int sub = 0; sub < nsub; ++sub) {
+              mbar_wait(full_bar(s), ph);
+              tc_fence_after();
+              const uint64_t bdesc = umma_smem_desc(stage_smem + (uint32_t)s * RS_BLOCK_BYTES);
+              const uint32_t d0 = dbase + (uint32_t)(sub * NACC) * RS_TILE_ROWS;
+              if (pl == 0) {
+                issue4(d0, a0, bdesc, kc == 0);
+                if (NACC == 2) issue4(d0 + RS_TILE_ROWS, a1, bdesc, kc == 0);
+              } else {
+                // lo plane of an fp32 corpus: q_hi . d_lo joins the low-order accumulator
+                issue4(d0 + RS_TILE_ROWS, a0, bdesc, false);
+              }
+              umma_commit(empty_bar(s));  // smem slot is free once these MMAs have read it
+              if (++s == p.stages) {
+                s = 0;
+                ph ^= 1u;
+              }
             }
           }
+          if (!q_resident)
+            for (int j = 0; j < p.terms; ++j) umma_commit(empty_bar(qslot[j]));  // Q chunk fully consumed
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-        if (++acc == 2) {
+        umma_commit(tfull_bar(acc));  // accumulators complete -> epilogue
+        if (++acc == NB) {
           acc = 0;
           acc_ph ^= 1u;
         }
@@ -283,8 +323,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
     // ===================== epilogue: one thread per query row =====================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
     if (quarter < nact_warps) {
-      const int row = quarter * 32 + lane;
-      const bool live = row < p.n_queries;
+      const int row = quarter * rows_per_warp + lane;
+      const bool live = lane < rows_per_warp && row < p.n_queries;
       const int k = p.k;
       const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
       const bool cosine = p.metric == RS_METRIC_COSINE;
@@ -298,14 +338,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       int li[REGLIST ? kRegK : 1];
       float* sl_s = nullptr;
       int* sl_i = nullptr;
-      const int lstride = nact_warps * 32;
+      const int lstride = p.bpad;
       if (REGLIST) {
 #pragma unroll
         for (int j = 0; j < kRegK; ++j) {
           ls[j] = j < k ? -CUDART_INF_F : CUDART_INF_F;
           li[j] = -1;
         }
-      } else {
+      } else if (live) {
         sl_s = reinterpret_cast<float*>(smem + map.list_off) + row;
         sl_i = reinterpret_cast<int*>(smem + map.list_off + (size_t)k * lstride * 4) + row;
         for (int j = 0; j < k; ++j) {
@@ -318,99 +358,103 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
 
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        float ndmin = 1.f, ndmax = 1.f;
-        if (cosine) {
-          float2 mm = p.tile_norm_minmax[t];
-          ndmin = mm.x;
-          ndmax = mm.y;
-          thr_raw = live ? cosine_raw_bound(thr, nq, inv_qs, ndmin, ndmax) : CUDART_INF_F;
-        }
+      for (int u = blockIdx.x; u < n_super; u += gridDim.x) {
+        const int nsub = min(S, p.n_tiles - u * S);
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
-        const uint32_t tacc = lane_base + (uint32_t)(acc * NACC) * RS_TILE_ROWS;
-        const int tile_row0 = t * RS_TILE_ROWS;
-#pragma unroll 1
-        for (int c0 = 0; c0 < RS_TILE_ROWS; c0 += 32) {
-          float v[32];
-          {
-            uint32_t r0[32];
-            tmem_ld_x32(tacc + c0, r0);
-            if (NACC == 2) {
-              uint32_t r1[32];
-              tmem_ld_x32(tacc + RS_TILE_ROWS + c0, r1);
-              tmem_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r1[j]), lo_coef, __uint_as_float(r0[j]));
-            } else {
-              tmem_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
-            }
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int t = u * S + sub;
+          float ndmin = 1.f, ndmax = 1.f;
+          if (cosine) {
+            float2 mm = p.tile_norm_minmax[t];
+            ndmin = mm.x;
+            ndmax = mm.y;
+            thr_raw = live ? cosine_raw_bound(thr, nq, inv_qs, ndmin, ndmax) : CUDART_INF_F;
           }
-          const float m = max32(v);
-          if (__any_sync(0xffffffffu, m > thr_raw)) {
-            // rare path: some query of this warp has a candidate in this 32-document chunk
-            uint32_t pm = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) pm |= (v[j] > thr_raw) ? (1u << j) : 0u;
-            uint32_t any = __reduce_or_sync(0xffffffffu, pm);
-            while (any) {
-              const int j = __ffs(any) - 1;
-              any &= any - 1;
-              // re-read the single column from TMEM: warp-uniform address, no dynamic register index
-              float s = __uint_as_float(tmem_ld_x1(tacc + c0 + j));
+          const uint32_t tacc = lane_base + (uint32_t)((acc * S + sub) * NACC) * RS_TILE_ROWS;
+          const int tile_row0 = t * RS_TILE_ROWS;
+#pragma unroll 1
+          for (int c0 = 0; c0 < RS_TILE_ROWS; c0 += 32) {
+            float v[32];
+            {
+              uint32_t r0[32];
+              tmem_ld_x32(tacc + c0, r0);
               if (NACC == 2) {
-                float s1 = __uint_as_float(tmem_ld_x1(tacc + RS_TILE_ROWS + c0 + j));
+                uint32_t r1[32];
+                tmem_ld_x32(tacc + RS_TILE_ROWS + c0, r1);
                 tmem_wait_ld();
-                s = fmaf(s1, lo_coef, s);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r1[j]), lo_coef, __uint_as_float(r0[j]));
               } else {
                 tmem_wait_ld();
-              }
-              const int idx = tile_row0 + c0 + j;
-              if (((pm >> j) & 1u) && idx < p.n_rows) {
-                float x = s;  // dot metric: compare and store raw units (exact power-of-two scale)
-                if (cosine) {
-                  const float nd = p.dnorm[idx];
-                  const float denom = __fadd_rn(__fmul_rn(nq, nd), 1e-8f);   // retriever.py:605,607
-                  x = __fdiv_rn(s * qs, denom);
-                  x = fminf(fmaxf(x, -1.0f), 1.0f);                          // retriever.py:609
-                }
-                if (x > thr) {
-                  if (REGLIST) {
-                    bool prev = true;  // "slot j-1 was shifted" (true for j == 0)
 #pragma unroll
-                    for (int jj = 0; jj < kRegK; ++jj) {
-                      const bool lt = (jj + 1 < kRegK) && (ls[jj + 1 < kRegK ? jj + 1 : jj] < x);
-                      const float ns = lt ? ls[jj + 1 < kRegK ? jj + 1 : jj] : (prev ? x : ls[jj]);
-                      const int ni = lt ? li[jj + 1 < kRegK ? jj + 1 : jj] : (prev ? idx : li[jj]);
-                      ls[jj] = ns;
-                      li[jj] = ni;
-                      prev = lt;
-                    }
-                    thr = ls[0];
-                  } else {
-                    int jj = 0;
-                    while (jj + 1 < k && sl_s[(jj + 1) * lstride] < x) {
-                      sl_s[jj * lstride] = sl_s[(jj + 1) * lstride];
-                      sl_i[jj * lstride] = sl_i[(jj + 1) * lstride];
-                      ++jj;
-                    }
-                    sl_s[jj * lstride] = x;
-                    sl_i[jj * lstride] = idx;
-                    thr = sl_s[0];
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+              }
+            }
+            const float m = max32(v);
+            if (__any_sync(0xffffffffu, m > thr_raw)) {
+              // rare path: some query of this warp has a candidate in this 32-document chunk
+              uint32_t pm = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) pm |= (v[j] > thr_raw) ? (1u << j) : 0u;
+              uint32_t any = __reduce_or_sync(0xffffffffu, pm);
+              while (any) {
+                const int j = __ffs(any) - 1;
+                any &= any - 1;
+                // re-read the single column from TMEM: warp-uniform address, no dynamic register index
+                float s = __uint_as_float(tmem_ld_x1(tacc + c0 + j));
+                if (NACC == 2) {
+                  float s1 = __uint_as_float(tmem_ld_x1(tacc + RS_TILE_ROWS + c0 + j));
+                  tmem_wait_ld();
+                  s = fmaf(s1, lo_coef, s);
+                } else {
+                  tmem_wait_ld();
+                }
+                const int idx = tile_row0 + c0 + j;
+                if (((pm >> j) & 1u) && idx < p.n_rows) {
+                  float x = s;  // dot metric: compare and store raw units (exact power-of-two scale)
+                  if (cosine) {
+                    const float nd = p.dnorm[idx];
+                    const float denom = __fadd_rn(__fmul_rn(nq, nd), 1e-8f);   // retriever.py:605,607
+                    x = __fdiv_rn(s * qs, denom);
+                    x = fminf(fmaxf(x, -1.0f), 1.0f);                          // retriever.py:609
                   }
-                  thr_raw = cosine ? cosine_raw_bound(thr, nq, inv_qs, ndmin, ndmax) : thr;
+                  if (x > thr) {
+                    if (REGLIST) {
+                      bool prev = true;  // "slot j-1 was shifted" (true for j == 0)
+#pragma unroll
+                      for (int jj = 0; jj < kRegK; ++jj) {
+                        const bool lt = (jj + 1 < kRegK) && (ls[jj + 1 < kRegK ? jj + 1 : jj] < x);
+                        const float ns = lt ? ls[jj + 1 < kRegK ? jj + 1 : jj] : (prev ? x : ls[jj]);
+                        const int ni = lt ? li[jj + 1 < kRegK ? jj + 1 : jj] : (prev ? idx : li[jj]);
+                        ls[jj] = ns;
+                        li[jj] = ni;
+                        prev = lt;
+                      }
+                      thr = ls[0];
+                    } else {
+                      int jj = 0;
+                      while (jj + 1 < k && sl_s[(jj + 1) * lstride] < x) {
+                        sl_s[jj * lstride] = sl_s[(jj + 1) * lstride];
+                        sl_i[jj * lstride] = sl_i[(jj + 1) * lstride];
+                        ++jj;
+                      }
+                      sl_s[jj * lstride] = x;
+                      sl_i[jj * lstride] = idx;
+                      thr = sl_s[0];
+                    }
+                    thr_raw = cosine ? cosine_raw_bound(thr, nq, inv_qs, ndmin, ndmax) : thr;
+                  }
                 }
               }
             }
           }
         }
-        // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back
+        // all TMEM reads of this accumulator buffer are complete (wait::ld above) -> hand it back
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
-        if (++acc == 2) {
+        if (++acc == NB) {
           acc = 0;
           acc_ph ^= 1u;
         }
@@ -445,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -563,7 +607,7 @@ cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dt
 
 template <int NACC, bool REGLIST>
 static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t stream) {
-  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.k, REGLIST);
+  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.k, REGLIST, p.q_resident != 0);
   auto kern = fused_search_kernel<NACC, REGLIST>;
   const int bytes = (int)map.total + 1024;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -572,8 +616,8 @@ static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t 
   return cudaGetLastError();
 }
 
-int fused_smem_bytes(int bpad, int kc, int terms, int stages, int k) {
-  return (int)make_smem_map(bpad, kc, terms, stages, k, k <= kRegK).total + 1024;
+int fused_smem_bytes(int bpad, int kc, int terms, int stages, int k, int q_resident) {
+  return (int)make_smem_map(bpad, kc, terms, stages, k, k <= kRegK, q_resident != 0).total + 1024;
 }
 int fused_reg_k() { return kRegK; }
 

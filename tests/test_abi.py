@@ -41,7 +41,7 @@ def test_every_declared_symbol_is_exported():
 def test_struct_layouts_match_header():
     # sizes the C side checks via struct_size
     assert C.sizeof(_cabi.rs_config) == 48
-    assert C.sizeof(_cabi.rs_stats) == 56
+    assert C.sizeof(_cabi.rs_stats) == 72
 
 
 def test_build_targets_sm100a_only():

@@ -180,6 +180,55 @@ def test_many_tiles_per_cta_and_all_ctas():
         assert (idx[:, 0] == src).all()
 
 
+# ---------------------------------------------------------------- every kernel mode the planner can pick
+MODES = [
+    {"RS_MMA_M": "128"}, {"RS_MMA_M": "64"},
+    {"RS_QRESIDENT": "0", "RS_SUB": "1", "RS_NBUF": "2"}, {"RS_QRESIDENT": "0", "RS_SUB": "2", "RS_NBUF": "2"},
+    {"RS_QRESIDENT": "0", "RS_SUB": "4", "RS_NBUF": "1"}, {"RS_QRESIDENT": "0", "RS_SUB": "2", "RS_NBUF": "1", "RS_MMA_M": "128"},
+    {"RS_QRESIDENT": "1", "RS_SUB": "2", "RS_NBUF": "2"},
+]
+
+
+@pytest.mark.parametrize("mode", MODES, ids=lambda m: ",".join(f"{k[3:]}={v}" for k, v in m.items()))
+def test_kernel_modes(monkeypatch, squad, mode):
+    for k_, v in mode.items():
+        monkeypatch.setenv(k_, v)
+    N = 128 * 148 * 2 + 300                                # supertiles that end in partial groups
+    E = o.synth_rows(11, np.arange(N))
+    rng = np.random.default_rng(2)
+    src = rng.integers(0, N, 24)
+    src[:2] = [0, N - 1]
+    Q = o.round_to_bf16(E[src] + 0.02 * rng.standard_normal((24, 1024)).astype(np.float32))
+    idx, _, _ = run_case(E, Q, 10, "bf16", "dot", 1)
+    assert (idx[:, 0] == src).all()
+    run_case(squad.E, squad.Q, 10, "bf16", "cosine", 1)
+    run_case(squad.E[:700], squad.Q[:9], 20, "bf16", "dot", 1)           # shared-memory list path
+    if mode.get("RS_SUB") != "4":                                       # two accumulators: sub*nbuf*2 <= 4
+        nb = {"RS_NBUF": "1"} if mode.get("RS_SUB") == "2" else {}
+        for k_, v in nb.items():
+            monkeypatch.setenv(k_, v)
+        run_case(squad.E, squad.Q, 10, "fp32", "dot", 2, scale_exp=4)
+        run_case(E[:40_000], Q, 10, "fp16", "cosine", 2)
+
+
+@pytest.mark.parametrize("B,dtype,terms", [(96, "bf16", 1), (128, "bf16", 1), (128, "fp32", 2), (128, "fp16", 2),
+                                           (65, "bf16", 2), (256, "bf16", 1)])
+def test_large_batches_stream_queries_single_pass(squad, B, dtype, terms):
+    rng = np.random.default_rng(B)
+    N = 128 * 148 + 50
+    E = o.synth_rows(5, np.arange(N))
+    Q = (E[rng.integers(0, N, B)] + 0.05 * rng.standard_normal((B, 1024))).astype(np.float32)
+    ix = make_index(E, dtype, 4 if dtype == "fp32" else 0, max_batch=256, max_k=16)
+    try:
+        idx, sc = ix.search(Q, 10, "dot", terms)
+        st = ix.stats()
+        assert st["passes"] == (1 if B <= 128 else 2) and st["q_resident"] == 0
+        S = exact_scores(Q, E, dtype, "dot", terms, 4 if dtype == "fp32" else 0)
+        o.check_topk(idx, sc, S, 10, rtol=RTOL[dtype], atol=1e-6)
+    finally:
+        ix.close()
+
+
 # ---------------------------------------------------------------- ties, degenerate inputs
 def test_duplicate_rows_tie_to_lower_index(squad):
     E = squad.E[:600].copy()
