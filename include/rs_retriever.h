@@ -55,7 +55,7 @@ typedef struct rs_config {
   int32_t dtype;       /* RS_DTYPE_* storage type */
   int32_t scale_exp;   /* RS_DTYPE_FP32 only: rows are multiplied by 2^scale_exp before the fp16 split */
   int32_t max_batch;   /* largest B a search call may pass */
-  int32_t max_k;       /* largest k a search call may pass */
+  int32_t max_k;       /* largest k a search call may pass (<= 128) */
   int32_t reserved;
 } rs_config;
 

@@ -37,7 +37,6 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kMaxSmem = 232448;  // 227 KiB opt-in dynamic shared memory per CTA on sm_100
 constexpr int kMinResidentStages = 6;   // resident-Q mode wants a deep ring beside the query image
-constexpr int kMinStreamStages = 7;     // streamed-Q mode: at least one full k-chunk group (<= 6 items) + 1
 constexpr int kMaxStages = 24;
 constexpr int64_t kIngestChunkBytes = 64ll << 20;
 
@@ -108,30 +107,48 @@ int max_cap_rows(int kc, int terms, int k, int min_stages, int q_resident) {
 int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
   const int nacc = (terms == 2 || ix->planes == 2) ? 2 : 1;
   const int cap_res = max_cap_rows(ix->kc, terms, k, kMinResidentStages, 1);
-  const int cap_str = max_cap_rows(ix->kc, terms, k, kMinStreamStages, 0);
   int resident = B <= cap_res ? 1 : 0;
   resident = env_int("RS_QRESIDENT", resident);
-  const int cap = resident ? cap_res : cap_str;
+  int min_stages = kMinResidentStages;
+  int cap = cap_res;
+  if (resident) {
+    pl->sub = 1;
+    pl->nbuf = 2;
+  } else {
+    // one k-chunk group (terms Q items + planes*sub document items) must fit in the ring with a
+    // slot to spare; prefer the fewest passes, then the largest sub (least Q re-reading)
+    int best_passes = 1 << 30;
+    for (int sub = (nacc == 1 ? 4 : 2); sub >= 1; sub >>= 1) {
+      const int need = terms + ix->planes * sub + 1;
+      const int c = max_cap_rows(ix->kc, terms, k, need, 0);
+      if (c <= 0) continue;
+      const int passes = (B + c - 1) / c;
+      if (passes < best_passes) {
+        best_passes = passes;
+        pl->sub = sub;
+        cap = c;
+        min_stages = need;
+      }
+    }
+    if (best_passes == (1 << 30)) cap = 0;
+    pl->nbuf = 1;
+  }
   if (cap <= 0) return fail(RS_E_UNSUPPORTED, "k=%d with dim=%d does not fit in shared memory", k, ix->cfg.dim);
   pl->q_resident = resident;
   pl->passes = (B + cap - 1) / cap;
   pl->per_pass = (B + pl->passes - 1) / pl->passes;
   pl->bpad = (pl->per_pass + 7) / 8 * 8;
-  if (resident) {
-    pl->sub = 1;
-    pl->nbuf = 2;
-  } else {
-    pl->sub = nacc == 1 ? 4 : 2;
-    pl->nbuf = 1;
-  }
   pl->mma_m = env_int("RS_MMA_M", pl->bpad <= 64 ? 64 : 128);
   if (pl->mma_m != 128 && !(pl->mma_m == 64 && pl->bpad <= 64)) return fail(RS_E_INVALID, "RS_MMA_M=%d invalid for bpad=%d", pl->mma_m, pl->bpad);
-  pl->sub = env_int("RS_SUB", pl->sub);
+  if (getenv("RS_SUB")) {
+    pl->sub = env_int("RS_SUB", pl->sub);
+    min_stages = resident ? kMinResidentStages : terms + ix->planes * pl->sub + 1;
+  }
   pl->nbuf = env_int("RS_NBUF", pl->nbuf);
   const int cols = pl->sub * pl->nbuf * nacc;
   if (pl->sub < 1 || pl->nbuf < 1 || pl->nbuf > 2 || (cols != 1 && cols != 2 && cols != 4))
     return fail(RS_E_INVALID, "sub=%d nbuf=%d nacc=%d does not map onto 128/256/512 TMEM columns", pl->sub, pl->nbuf, nacc);
-  int stages = resident ? kMinResidentStages : kMinStreamStages;
+  int stages = min_stages;
   while (stages < kMaxStages &&
          rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages + 1, k, resident) <= kMaxSmem)
     ++stages;
@@ -216,6 +233,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.sub = pl.sub;
     p.nbuf = pl.nbuf;
     p.mma_m = pl.mma_m;
+    p.debug_flags = env_int("RS_DEBUG_FLAGS", 0);
     p.lo_coef = ix->plane_dtype == RS_DTYPE_FP16 ? ldexpf(1.0f, -RS_FP16_SPLIT_SHIFT) : 1.0f;
     const int slot = (int)(ix->ev_count % rs_index::kEventRing);
     RS_CUDA(cudaEventRecord(ix->ev_beg[slot], stream));
@@ -246,7 +264,7 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   if (cfg->dim <= 0 || cfg->dim % 64 != 0 || cfg->dim > 4096) return fail(RS_E_INVALID, "dim=%d must be a multiple of 64 in [64,4096]", cfg->dim);
   if (cfg->dtype < RS_DTYPE_BF16 || cfg->dtype > RS_DTYPE_FP32) return fail(RS_E_INVALID, "bad dtype %d", cfg->dtype);
   if (cfg->max_batch <= 0 || cfg->max_batch > 65536) return fail(RS_E_INVALID, "bad max_batch %d", cfg->max_batch);
-  if (cfg->max_k <= 0 || cfg->max_k > 1024) return fail(RS_E_INVALID, "max_k=%d outside [1,1024]", cfg->max_k);
+  if (cfg->max_k <= 0 || cfg->max_k > 128) return fail(RS_E_INVALID, "max_k=%d outside [1,128]", cfg->max_k);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -274,7 +292,7 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   ix->stats.corpus_bytes = (int64_t)ix->corpus_bytes;
 
   const int grid = std::min(ix->sm_count, ix->n_tiles);
-  const int cap1 = max_cap_rows(ix->kc, 1, 1, kMinStreamStages, 0);
+  const int cap1 = max_cap_rows(ix->kc, 1, 1, 3, 0);
   if (cap1 <= 0) {
     delete ix;
     return fail(RS_E_UNSUPPORTED, "dim=%d does not fit the shared-memory pipeline", cfg->dim);

@@ -29,6 +29,7 @@ struct SearchParams {
   int sub;                           // 128-document tiles per supertile (share one Q k-chunk load)
   int mma_m;                         // 128, or 64 when bpad <= 64 (half the tensor work / operand reads)
   int nbuf;                          // TMEM accumulator buffers (1 or 2); nbuf*sub*NACC*128 <= 512 columns
+  int debug_flags;                   // timing experiments only (RS_DEBUG_FLAGS): 1 = skip MMAs, 2 = skip epilogue
   float lo_coef;                     // weight of the low-order accumulator (2^-11 for fp16 terms, 1 for bf16)
 };
 

@@ -117,6 +117,8 @@ constexpr int kFirstEpiWarp = 2;
 constexpr int kNumEpiWarps = 4;
 constexpr int kThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;  // 192
 constexpr int kRegK = 16;                                       // register-resident list capacity
+constexpr int kBufC = 32;                                       // k > kRegK: unsorted candidate buffer per query
+constexpr int kMaxListK = 128;                                  // k > kRegK: sorted list in smem, <= 4 slots per lane
 
 struct SmemMap {
   uint32_t q_bytes, stage_off, bar_off, list_off, total;
@@ -130,7 +132,7 @@ __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, in
   m.stage_off = m.q_bytes;  // multiple of 1024 because bpad % 8 == 0
   m.bar_off = m.stage_off + (uint32_t)stages * RS_BLOCK_BYTES;
   m.list_off = m.bar_off + 1024;
-  m.total = m.list_off + (reglist ? 0u : (uint32_t)k * (uint32_t)bpad * 8u);
+  m.total = m.list_off + (reglist ? 0u : (uint32_t)(k + kBufC) * (uint32_t)bpad * 8u);
   return m;
 }
 
@@ -153,6 +155,74 @@ __device__ __forceinline__ float cosine_raw_bound(float thr_cos, float nq, float
   if (thr_cos == -CUDART_INF_F) return -CUDART_INF_F;
   if (thr_cos >= 0.f) return thr_cos * nq * ndmin * inv_qs * (1.0f - 1e-6f);
   return thr_cos * (nq * ndmax + 1e-8f) * inv_qs * (1.0f + 1e-6f);
+}
+
+// k > kRegK selection state (per query, in shared memory, [slot][row] so rows are bank-parallel):
+// a sorted top-k list (best first) plus an unsorted buffer of kBufC candidates that passed the
+// (stale) threshold.  When a buffer fills, the whole warp merges it into the list: bitonic-sort the
+// 32 candidates across lanes, then every element computes its rank in the merged order by binary
+// search in the other sequence and is written straight to that position.  Ties: list elements were
+// seen earlier (lower index) so they win; candidates order by (score desc, index asc).
+// Must be called by the full, converged warp.  Returns the new k-th best score.
+__device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs, int* Bi, int stride, int qrow, int n,
+                                                  int k, int lane) {
+  float cs = lane < n ? Bs[lane * stride + qrow] : -CUDART_INF_F;
+  int ci = lane < n ? Bi[lane * stride + qrow] : 0x7fffffff;
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int st = size >> 1; st > 0; st >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, cs, st);
+      const int oi = __shfl_xor_sync(0xffffffffu, ci, st);
+      const bool desc = (lane & size) == 0;  // size == 32: always descending
+      const bool lower = (lane & st) == 0;
+      const bool mine_better = cs > os || (cs == os && ci < oi);
+      const bool keep = (lower == desc) ? mine_better : !mine_better;
+      if (!keep && !(cs == os && ci == oi)) {
+        cs = os;
+        ci = oi;
+      }
+    }
+  }
+  Bs[lane * stride + qrow] = cs;  // now sorted, best first
+  __syncwarp();
+  float es[kMaxListK / 32];
+  int ei[kMaxListK / 32], er[kMaxListK / 32];
+#pragma unroll
+  for (int g = 0; g < kMaxListK / 32; ++g) {
+    const int pos = lane + 32 * g;
+    er[g] = k;
+    if (pos < k) {
+      es[g] = Ls[pos * stride + qrow];
+      ei[g] = Li[pos * stride + qrow];
+      int lo = 0, hi = 32;  // candidates strictly better than this list element
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (Bs[mid * stride + qrow] > es[g]) lo = mid + 1; else hi = mid;
+      }
+      er[g] = pos + lo;
+    }
+  }
+  int lo = 0, hi = k;  // list elements at least as good as this candidate
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (Ls[mid * stride + qrow] >= cs) lo = mid + 1; else hi = mid;
+  }
+  const int cr = lane + lo;
+  __syncwarp();
+#pragma unroll
+  for (int g = 0; g < kMaxListK / 32; ++g) {
+    if (er[g] < k) {
+      Ls[er[g] * stride + qrow] = es[g];
+      Li[er[g] * stride + qrow] = ei[g];
+    }
+  }
+  if (lane < n && cr < k) {
+    Ls[cr * stride + qrow] = cs;
+    Li[cr * stride + qrow] = ci;
+  }
+  __syncwarp();
+  return Ls[(k - 1) * stride + qrow];
 }
 
 // One CTA walks "supertiles" of p.sub consecutive 128-document tiles.  Per supertile the K loop
@@ -260,6 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       uint32_t acc_ph = 0;
       // 16-byte units: one UMMA K step (16 elements x 2 B) advances the start address by 2
       auto issue4 = [&](uint32_t d, uint64_t a, uint64_t b, bool fresh) {
+        if (p.debug_flags & 1) return;  // timing experiment only: stream the corpus, issue no MMAs
 #pragma unroll
         for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
           umma_f16(d, a + 2u * ks, b + 2u * ks, idesc, (fresh && ks == 0) ? 0u : 1u);
@@ -333,25 +404,30 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       const float nq = live ? p.qnorm[row] : 0.f;
       const float lo_coef = p.lo_coef;
 
-      // running top-k, ascending: slot 0 is the current k-th best (the threshold)
+      // running top-k.  k <= kRegK: registers, ascending, slot 0 is the current k-th best (the
+      // threshold).  Larger k: sorted list + candidate buffer in shared memory (flush_candidates).
       float ls[REGLIST ? kRegK : 1];
       int li[REGLIST ? kRegK : 1];
-      float* sl_s = nullptr;
-      int* sl_i = nullptr;
       const int lstride = p.bpad;
+      float* Ls = reinterpret_cast<float*>(smem + map.list_off);
+      int* Li = reinterpret_cast<int*>(Ls + (size_t)k * lstride);
+      float* Bs = reinterpret_cast<float*>(Li + (size_t)k * lstride);
+      int* Bi = reinterpret_cast<int*>(Bs + (size_t)kBufC * lstride);
+      int cnt = 0;
       if (REGLIST) {
 #pragma unroll
         for (int j = 0; j < kRegK; ++j) {
           ls[j] = j < k ? -CUDART_INF_F : CUDART_INF_F;
           li[j] = -1;
         }
-      } else if (live) {
-        sl_s = reinterpret_cast<float*>(smem + map.list_off) + row;
-        sl_i = reinterpret_cast<int*>(smem + map.list_off + (size_t)k * lstride * 4) + row;
-        for (int j = 0; j < k; ++j) {
-          sl_s[j * lstride] = -CUDART_INF_F;
-          sl_i[j * lstride] = -1;
+      } else {
+        if (live) {
+          for (int j = 0; j < k; ++j) {
+            Ls[j * lstride + row] = -CUDART_INF_F;
+            Li[j * lstride + row] = -1;
+          }
         }
+        __syncwarp();
       }
       float thr = live ? -CUDART_INF_F : CUDART_INF_F;  // in metric units (dot: raw units)
       float thr_raw = thr;
@@ -362,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
         const int nsub = min(S, p.n_tiles - u * S);
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
-        for (int sub = 0; sub < nsub; ++sub) {
+        for (int sub = 0; sub < ((p.debug_flags & 2) ? 0 : nsub); ++sub) {
           const int t = u * S + sub;
           float ndmin = 1.f, ndmax = 1.f;
           if (cosine) {
@@ -432,18 +508,25 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
                         prev = lt;
                       }
                       thr = ls[0];
+                      thr_raw = cosine ? cosine_raw_bound(thr, nq, inv_qs, ndmin, ndmax) : thr;
                     } else {
-                      int jj = 0;
-                      while (jj + 1 < k && sl_s[(jj + 1) * lstride] < x) {
-                        sl_s[jj * lstride] = sl_s[(jj + 1) * lstride];
-                        sl_i[jj * lstride] = sl_i[(jj + 1) * lstride];
-                        ++jj;
-                      }
-                      sl_s[jj * lstride] = x;
-                      sl_i[jj * lstride] = idx;
-                      thr = sl_s[0];
+                      Bs[cnt * lstride + row] = x;  // O(1) append; threshold stays stale until the flush
+                      Bi[cnt * lstride + row] = idx;
+                      ++cnt;
                     }
-                    thr_raw = cosine ? cosine_raw_bound(thr, nq, inv_qs, ndmin, ndmax) : thr;
+                  }
+                }
+                if (!REGLIST) {
+                  uint32_t full = __ballot_sync(0xffffffffu, cnt == kBufC);
+                  while (full) {
+                    const int ql = __ffs(full) - 1;
+                    full &= full - 1;
+                    const float nt = flush_candidates(Ls, Li, Bs, Bi, lstride, quarter * rows_per_warp + ql, kBufC, k, lane);
+                    if (lane == ql) {
+                      thr = nt;
+                      cnt = 0;
+                      thr_raw = cosine ? cosine_raw_bound(thr, nq, inv_qs, ndmin, ndmax) : thr;
+                    }
                   }
                 }
               }
@@ -460,6 +543,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
         }
       }
 
+      if (!REGLIST) {  // drain the partially filled buffers
+        uint32_t rem = __ballot_sync(0xffffffffu, cnt > 0);
+        while (rem) {
+          const int ql = __ffs(rem) - 1;
+          rem &= rem - 1;
+          const int n = __shfl_sync(0xffffffffu, cnt, ql);
+          flush_candidates(Ls, Li, Bs, Bi, lstride, quarter * rows_per_warp + ql, n, k, lane);
+        }
+      }
       // per-CTA candidates, best first; dot scores leave raw units here
       if (live) {
         float* cs = p.cand_score + ((size_t)blockIdx.x * p.n_queries + row) * k;
@@ -475,10 +567,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
           }
         } else {
           for (int j = 0; j < k; ++j) {
-            const float raw = sl_s[j * lstride];
-            const int id = sl_i[j * lstride];
-            cs[k - 1 - j] = id < 0 ? -CUDART_INF_F : (cosine ? raw : raw * qs);
-            ci[k - 1 - j] = id;
+            const float raw = Ls[j * lstride + row];
+            const int id = Li[j * lstride + row];
+            cs[j] = id < 0 ? -CUDART_INF_F : (cosine ? raw : raw * qs);
+            ci[j] = id;
           }
         }
       }

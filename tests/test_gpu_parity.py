@@ -229,6 +229,27 @@ def test_large_batches_stream_queries_single_pass(squad, B, dtype, terms):
         ix.close()
 
 
+@pytest.mark.parametrize("k", [17, 33, 64, 100, 128])
+def test_large_k_buffered_selection(k):
+    """k > 16: sorted list + candidate buffer in shared memory, warp-cooperative merges."""
+    N = 128 * 148 * 2 + 99
+    E = o.synth_rows(21, np.arange(N))
+    E[5000:5040] = E[17]                                   # 41 identical rows: a long tie run inside the top-k
+    rng = np.random.default_rng(k)
+    src = rng.integers(0, N, 40)
+    src[0] = 17
+    Q = o.round_to_bf16(E[src] + 0.05 * rng.standard_normal((40, 1024)).astype(np.float32))
+    Q[0] = o.round_to_bf16(E[17])
+    idx, sc, _ = run_case(E, Q, k, "bf16", "dot", 1)
+    tie = [17] + list(range(5000, 5040))
+    assert idx[0, :min(k, 41)].tolist() == tie[:min(k, 41)]  # ties in ascending index order
+    run_case(E[:30_000], Q[:9], k, "fp32", "cosine", 2, scale_exp=4)
+    run_case(E[:k - 3], Q[:5], k, "bf16", "dot", 1)          # N < k
+    B = 128
+    Qb = o.round_to_bf16(E[rng.integers(0, N, B)] + 0.05 * rng.standard_normal((B, 1024)).astype(np.float32))
+    run_case(E[:50_000], Qb, k, "bf16", "dot", 1)            # streamed queries + shared-memory lists
+
+
 # ---------------------------------------------------------------- ties, degenerate inputs
 def test_duplicate_rows_tie_to_lower_index(squad):
     E = squad.E[:600].copy()
