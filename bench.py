@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--metric", default="dot", choices=["dot", "cosine"])
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default=None, choices=["nccl", "p2p"], help="multi-GPU candidate exchange")
     return ap.parse_args()
 
 
@@ -52,6 +53,7 @@ def workload_config(a, world):
                     f"BASELINE.json configs[3]",
         "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k, "similarity": a.metric,
         "sharding": f"row-sharded x{world}", "cache": "inputs larger than L2 (no flush needed)",
+        "exchange": (a.exchange or os.environ.get("RS_EXCHANGE", "p2p")) if world > 1 else "none",
     }
 
 
@@ -199,7 +201,8 @@ def main():
         print(f"warning: --gpus {a.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
 
     B, k = a.batch, a.k
-    s = ShardedSearcher(a.rows, a.dim, a.dtype, max_batch=max(B, 64), max_k=max(k, 16), device=local_rank)
+    s = ShardedSearcher(a.rows, a.dim, a.dtype, max_batch=max(B, 64), max_k=max(k, 16), device=local_rank,
+                        exchange=a.exchange)
     s.fill_synthetic(SEED)
 
     # queries: perturbed corpus rows (rank 0's shard), representable in the storage dtype so one
@@ -298,7 +301,7 @@ def main():
             "e2e": {"value": e2e_qps, "unit": METRIC, "h2d_bytes_per_step": B * a.dim * 4,
                     "d2h_bytes_per_step": B * k * 12, "api": "rs_search (C ABI, host buffers)" if world == 1
                     else "ShardedSearcher.search_host"},
-            "gpu_launches": st["launches"] * a.steps + (a.steps if world > 1 else 0),
+            "gpu_launches": st["launches"] * a.steps + (a.steps if (world > 1 and s.xchg is None) else 0),
             "clocks": clk.summary(),
             "kernel_stats": {"grid": st["grid"], "stages": st["stages"], "smem_bytes": st["smem_bytes"],
                              "passes": st["passes"], "query_terms": st["query_terms"]},

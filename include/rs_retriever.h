@@ -125,6 +125,22 @@ RS_API int rs_merge_device(int32_t device, const float* scores_dev, const int64_
                     int32_t kc, int32_t k, int64_t score_list_stride, int64_t idx_list_stride,
                     int64_t* out_idx_dev, float* out_score_dev, void* stream);
 
+/* Multi-GPU candidate exchange over NVLink peer memory, one process per GPU (an alternative to
+ * the NCCL all-gather + rs_merge_device above; same results).  Each rank creates an exchange
+ * buffer, exports its 64-byte CUDA IPC handle, and imports every peer's handle (exchanged by the
+ * host program, e.g. with torch.distributed.all_gather).  rs_search_exchange then runs
+ *   query prep -> fused score+select -> [local merge + peer stores of the B x k candidates into
+ *   every GPU's buffer + epoch flag] -> [wait for all ranks' flags + final merge]
+ * as four kernels with no collective call; every rank ends with the same global top-k.
+ * All ranks must call it in the same order with the same B and k. */
+typedef struct rs_xchg rs_xchg;
+RS_API int rs_xchg_create(int32_t device, int32_t world, int32_t rank, int32_t max_batch, int32_t max_k, rs_xchg** out);
+RS_API int rs_xchg_export(rs_xchg* x, void* handle64);
+RS_API int rs_xchg_import(rs_xchg* x, int32_t peer_rank, const void* handle64);
+RS_API int rs_xchg_destroy(rs_xchg* x);
+RS_API int rs_search_exchange(rs_index* ix, rs_xchg* x, const float* q_dev, int32_t B, int32_t k, int32_t metric,
+                       int32_t query_terms, int64_t* out_idx_dev, float* out_score_dev, void* stream);
+
 /* Read back the represented values of rows [row0,row0+nrows) as float (inverse of the tiling);
  * used by the tests (ingest round trip) and by the CPU-baseline sampler. */
 RS_API int rs_get_rows(rs_index* ix, int64_t row0, int64_t nrows, float* out_host);

@@ -20,6 +20,7 @@ EXPORTS = (
     "rs_version", "rs_last_error", "rs_create", "rs_destroy", "rs_load_rows", "rs_fill_synthetic",
     "rs_finalize", "rs_search", "rs_search_device", "rs_merge_device", "rs_get_rows",
     "rs_get_norms", "rs_get_image", "rs_get_stats", "rs_get_kernel_times",
+    "rs_xchg_create", "rs_xchg_export", "rs_xchg_import", "rs_xchg_destroy", "rs_search_exchange",
 )
 
 
@@ -78,6 +79,11 @@ def load() -> C.CDLL:
         "rs_search_device": [vp, vp, i32, i32, i32, i32, vp, vp, vp],
         "rs_merge_device": [i32, vp, vp, i32, i32, i32, i32, i64, i64, vp, vp, vp],
         "rs_get_kernel_times": [vp, vp, i32],
+        "rs_xchg_create": [i32, i32, i32, i32, i32, C.POINTER(vp)],
+        "rs_xchg_export": [vp, vp],
+        "rs_xchg_import": [vp, i32, vp],
+        "rs_xchg_destroy": [vp],
+        "rs_search_exchange": [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
         "rs_get_rows": [vp, i64, i64, vp],
         "rs_get_norms": [vp, i64, i64, vp],
         "rs_get_image": [vp, i64, i64, vp],
@@ -179,6 +185,37 @@ class Index:
         st.struct_size = C.sizeof(rs_stats)
         check(self.lib.rs_get_stats(self.h, C.byref(st)), "rs_get_stats")
         return {f: getattr(st, f) for f, _ in rs_stats._fields_}
+
+
+class Exchange:
+    """One rank's candidate exchange buffer (CUDA IPC, peer stores over NVLink)."""
+
+    def __init__(self, device: int, world: int, rank: int, max_batch: int, max_k: int):
+        self.lib = load()
+        h = C.c_void_p()
+        check(self.lib.rs_xchg_create(device, world, rank, max_batch, max_k, C.byref(h)), "rs_xchg_create")
+        self.h, self.world, self.rank = h, world, rank
+
+    def export_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(self.lib.rs_xchg_export(self.h, buf), "rs_xchg_export")
+        return buf.raw
+
+    def import_handle(self, peer_rank: int, handle: bytes):
+        buf = C.create_string_buffer(bytes(handle), 64)
+        check(self.lib.rs_xchg_import(self.h, peer_rank, buf), "rs_xchg_import")
+
+    def search(self, index: "Index", q_ptr: int, B: int, k: int, out_idx_ptr: int, out_score_ptr: int,
+               metric: str = "dot", query_terms: int = 1, stream: int = 0):
+        check(self.lib.rs_search_exchange(index.h, self.h, q_ptr, B, k, METRICS[metric], query_terms, out_idx_ptr,
+                                          out_score_ptr, stream), "rs_search_exchange")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rs_xchg_destroy(self.h)
+            self.h = None
+
+    __del__ = close
 
 
 def merge_device(device: int, scores_ptr: int, idx_ptr: int, n_lists: int, B: int, kc: int, k: int,

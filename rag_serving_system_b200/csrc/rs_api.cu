@@ -90,7 +90,21 @@ struct rs_index {
   std::mutex mu;
 };
 
+// Candidate exchange buffer of one rank (one process per GPU).  Every peer maps it through CUDA
+// IPC and stores its B x k candidates straight into its slot; flags carry the search epoch.
+struct rs_xchg {
+  int device = 0, world = 1, rank = 0, max_batch = 0, max_k = 0;
+  size_t slot_bytes = 0, parity_bytes = 0, total_bytes = 0;
+  uint8_t* local = nullptr;              // [flags 2 x 8 x u32 | pad to 256 B][parity 0: world slots][parity 1]
+  uint8_t* peer[rs::kMaxPeers] = {};     // peer[g] = GPU g's buffer mapped into this process (peer[rank] = local)
+  bool opened[rs::kMaxPeers] = {};
+  unsigned int* done_counter = nullptr;
+  unsigned int epoch = 0;
+};
+
 namespace {
+
+constexpr size_t kXchgHeader = 256;
 
 int max_cap_rows(int kc, int terms, int k, int min_stages, int q_resident) {
   // largest bpad (multiple of 8, <= 128) that leaves at least min_stages ring slots
@@ -131,7 +145,7 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
       }
     }
     if (best_passes == (1 << 30)) cap = 0;
-    pl->nbuf = 1;
+    pl->nbuf = pl->sub * nacc <= 2 ? 2 : 1;  // double-buffer the accumulators whenever TMEM has room
   }
   if (cap <= 0) return fail(RS_E_UNSUPPORTED, "k=%d with dim=%d does not fit in shared memory", k, ix->cfg.dim);
   pl->q_resident = resident;
@@ -182,7 +196,7 @@ void free_all(rs_index* ix) {
 
 // one search on device buffers; all launches go to `stream`
 int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int metric, int terms, long long* out_idx,
-                         float* out_score, cudaStream_t stream) {
+                         float* out_score, cudaStream_t stream, rs_xchg* xg = nullptr) {
   if (!ix->finalized) return fail(RS_E_STATE, "rs_finalize has not been called");
   if (B <= 0 || B > ix->cfg.max_batch) return fail(RS_E_INVALID, "B=%d outside [1,%d]", B, ix->cfg.max_batch);
   if (k <= 0 || k > ix->cfg.max_k) return fail(RS_E_INVALID, "k=%d outside [1,%d]", k, ix->cfg.max_k);
@@ -204,6 +218,14 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   ix->stats.query_terms = terms;
   ix->stats.launches = 0;
   ix->stats.bytes_streamed = 0;
+  unsigned int epoch = 0, parity = 0;
+  if (xg) {
+    if (B > xg->max_batch || k > xg->max_k) return fail(RS_E_INVALID, "B=%d k=%d exceed the exchange buffer (%d, %d)", B, k, xg->max_batch, xg->max_k);
+    for (int g = 0; g < xg->world; ++g)
+      if (!xg->peer[g]) return fail(RS_E_STATE, "exchange buffer of rank %d has not been imported", g);
+    epoch = ++xg->epoch;
+    parity = epoch & 1u;
+  }
   for (int pass = 0; pass < pl.passes; ++pass) {
     const int b0 = pass * pl.per_pass;
     const int nb = std::min(pl.per_pass, B - b0);
@@ -240,10 +262,42 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     RS_CUDA(rs::launch_fused_search(p, grid, stream));
     RS_CUDA(cudaEventRecord(ix->ev_end[slot], stream));
     ++ix->ev_count;
-    RS_CUDA(rs::launch_merge_i32(ix->cand_score, ix->cand_idx, grid, nb, k, k, ix->cfg.row_offset,
-                                 out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, stream));
+    if (!xg) {
+      RS_CUDA(rs::launch_merge_i32(ix->cand_score, ix->cand_idx, grid, nb, k, k, ix->cfg.row_offset,
+                                   out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, nullptr, stream));
+    } else {
+      // local merge + exchange in one kernel: rows go straight into every GPU's buffer
+      rs::MergeXchg mx;
+      memset(&mx, 0, sizeof(mx));
+      mx.n_dest = xg->world;
+      for (int g = 0; g < xg->world; ++g) {
+        uint8_t* slot = xg->peer[g] + kXchgHeader + parity * xg->parity_bytes + (size_t)xg->rank * xg->slot_bytes;
+        mx.dest_idx[g] = reinterpret_cast<long long*>(slot) + (size_t)b0 * k;
+        mx.dest_score[g] = reinterpret_cast<float*>(slot + (size_t)B * k * 8) + (size_t)b0 * k;
+        mx.dest_flag[g] = reinterpret_cast<unsigned int*>(xg->peer[g]) + parity * rs::kMaxPeers + xg->rank;
+      }
+      mx.done_counter = xg->done_counter;
+      mx.done_target = (unsigned int)B;
+      mx.epoch = epoch;
+      RS_CUDA(rs::launch_merge_i32(ix->cand_score, ix->cand_idx, grid, nb, k, k, ix->cfg.row_offset, nullptr, nullptr,
+                                   &mx, stream));
+    }
     ix->stats.launches += 3;
     ix->stats.bytes_streamed += (int64_t)ix->corpus_bytes;
+  }
+  if (xg) {
+    // final merge: wait for every rank's flag of this epoch, then merge the world lists
+    rs::MergeXchg mw;
+    memset(&mw, 0, sizeof(mw));
+    mw.n_wait = xg->world;
+    mw.wait_flags = reinterpret_cast<const unsigned int*>(xg->local) + parity * rs::kMaxPeers;
+    mw.epoch = epoch;
+    const uint8_t* base = xg->local + kXchgHeader + parity * xg->parity_bytes;
+    RS_CUDA(rs::launch_merge_i64(reinterpret_cast<const float*>(base + (size_t)B * k * 8),
+                                 reinterpret_cast<const long long*>(base), xg->world, B, k, k,
+                                 (long long)(xg->slot_bytes / 4), (long long)(xg->slot_bytes / 8), out_score, out_idx,
+                                 &mw, stream));
+    ix->stats.launches += 1;
   }
   ix->stats.total_launches += ix->stats.launches;
   return RS_OK;
@@ -445,8 +499,86 @@ RS_API int rs_merge_device(int32_t device, const float* scores_dev, const int64_
   if (idx_list_stride <= 0) idx_list_stride = (int64_t)B * kc;
   RS_CUDA(rs::launch_merge_i64(scores_dev, reinterpret_cast<const long long*>(idx_dev), n_lists, B, kc, k,
                                score_list_stride, idx_list_stride, out_score_dev, reinterpret_cast<long long*>(out_idx_dev),
-                               static_cast<cudaStream_t>(stream)));
+                               nullptr, static_cast<cudaStream_t>(stream)));
   return RS_OK;
+}
+
+RS_API int rs_xchg_create(int32_t device, int32_t world, int32_t rank, int32_t max_batch, int32_t max_k, rs_xchg** out) {
+  if (!out) return fail(RS_E_INVALID, "null argument");
+  *out = nullptr;
+  if (world < 1 || world > rs::kMaxPeers || rank < 0 || rank >= world) return fail(RS_E_INVALID, "world=%d rank=%d (at most %d GPUs)", world, rank, rs::kMaxPeers);
+  if (max_batch <= 0 || max_k <= 0) return fail(RS_E_INVALID, "bad max_batch/max_k");
+  RS_CUDA(cudaSetDevice(device));
+  rs_xchg* x = new (std::nothrow) rs_xchg();
+  if (!x) return fail(RS_E_INVALID, "out of host memory");
+  x->device = device;
+  x->world = world;
+  x->rank = rank;
+  x->max_batch = max_batch;
+  x->max_k = max_k;
+  x->slot_bytes = (((size_t)max_batch * max_k * 12) + 255) & ~size_t(255);
+  x->parity_bytes = x->slot_bytes * world;
+  x->total_bytes = kXchgHeader + 2 * x->parity_bytes;
+  cudaError_t e = cudaMalloc(&x->local, x->total_bytes);
+  if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->total_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&x->done_counter, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(x->done_counter, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(x->local);
+    cudaFree(x->done_counter);
+    delete x;
+    return fail(RS_E_CUDA, "exchange buffer allocation failed: %s", cudaGetErrorString(e));
+  }
+  x->peer[rank] = x->local;
+  *out = x;
+  return RS_OK;
+}
+
+RS_API int rs_xchg_export(rs_xchg* x, void* handle64) {
+  if (!x || !handle64) return fail(RS_E_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  RS_CUDA(cudaSetDevice(x->device));
+  cudaIpcMemHandle_t h;
+  RS_CUDA(cudaIpcGetMemHandle(&h, x->local));
+  memcpy(handle64, &h, 64);
+  return RS_OK;
+}
+
+RS_API int rs_xchg_import(rs_xchg* x, int32_t peer_rank, const void* handle64) {
+  if (!x || !handle64) return fail(RS_E_INVALID, "null argument");
+  if (peer_rank < 0 || peer_rank >= x->world) return fail(RS_E_INVALID, "peer_rank %d of %d", peer_rank, x->world);
+  if (peer_rank == x->rank) return RS_OK;
+  RS_CUDA(cudaSetDevice(x->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  RS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  x->peer[peer_rank] = static_cast<uint8_t*>(p);
+  x->opened[peer_rank] = true;
+  return RS_OK;
+}
+
+RS_API int rs_xchg_destroy(rs_xchg* x) {
+  if (!x) return RS_OK;
+  cudaSetDevice(x->device);
+  cudaDeviceSynchronize();
+  for (int g = 0; g < x->world; ++g)
+    if (x->opened[g]) cudaIpcCloseMemHandle(x->peer[g]);
+  cudaFree(x->local);
+  cudaFree(x->done_counter);
+  delete x;
+  return RS_OK;
+}
+
+RS_API int rs_search_exchange(rs_index* ix, rs_xchg* x, const float* q_dev, int32_t B, int32_t k, int32_t metric,
+                              int32_t query_terms, int64_t* out_idx_dev, float* out_score_dev, void* stream) {
+  if (!ix || !x || !q_dev || !out_idx_dev || !out_score_dev) return fail(RS_E_INVALID, "null argument");
+  if (x->device != ix->cfg.device) return fail(RS_E_INVALID, "index and exchange buffer live on different devices");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  return search_device_locked(ix, q_dev, B, k, metric, query_terms, reinterpret_cast<long long*>(out_idx_dev),
+                              out_score_dev, static_cast<cudaStream_t>(stream), x);
 }
 
 RS_API int rs_get_rows(rs_index* ix, int64_t row0, int64_t nrows, float* out_host) {

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "rs_kernels.h"
 #include "rs_layout.h"
@@ -195,12 +196,14 @@ __device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs,
     if (pos < k) {
       es[g] = Ls[pos * stride + qrow];
       ei[g] = Li[pos * stride + qrow];
-      int lo = 0, hi = 32;  // candidates strictly better than this list element
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (Bs[mid * stride + qrow] > es[g]) lo = mid + 1; else hi = mid;
-      }
-      er[g] = pos + lo;
+      // candidates strictly better than this list element: fixed-trip binary search (count in
+      // [0,32]) so the four independent searches of a lane interleave their shared-memory loads
+      int c = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1)
+        if (Bs[(c + step - 1) * stride + qrow] > es[g]) c += step;
+      if (c == 31 && Bs[31 * stride + qrow] > es[g]) c = 32;
+      er[g] = pos + c;
     }
   }
   int lo = 0, hi = k;  // list elements at least as good as this candidate
@@ -593,24 +596,51 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
 // ------------------------------------------------------------------------------------------
 constexpr int kMergeMaxOwn = 8;  // up to 256 lists
 
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One warp per query.  With x.n_wait > 0 the warp first waits until every source rank has
+// published its candidates for this epoch (flags written by PEER GPUs over NVLink).  With
+// x.n_dest > 0 the merged row is written to n_dest destinations - the exchange buffers of every
+// GPU of the box, reached through peer pointers - and the last warp to finish raises this
+// rank's flag on every peer.  That makes "local merge + candidate exchange" ONE kernel whose
+// stores travel over NVLink while other queries are still being merged.
 template <typename IdxT, bool STAGED>
 __global__ void __launch_bounds__(32) merge_topk_kernel(const float* __restrict__ cand_score,
                                                         const IdxT* __restrict__ cand_idx, int n_lists,
                                                         int n_queries, int kc, int k, long long idx_offset,
                                                         long long score_list_stride, long long idx_list_stride,
                                                         float* __restrict__ out_score,
-                                                        long long* __restrict__ out_idx) {
+                                                        long long* __restrict__ out_idx, const MergeXchg x) {
   extern __shared__ __align__(16) uint8_t merge_smem[];
   const int q = blockIdx.x;
   const int lane = threadIdx.x;
   const int total = n_lists * kc;
-  IdxT* s_idx = reinterpret_cast<IdxT*>(merge_smem);
-  float* s_score = reinterpret_cast<float*>(merge_smem + (size_t)total * sizeof(IdxT));
+  long long* res_i = reinterpret_cast<long long*>(merge_smem);
+  float* res_s = reinterpret_cast<float*>(res_i + k);
+  uint8_t* stage = merge_smem + (((size_t)k * 12 + 15) & ~size_t(15));
+  IdxT* s_idx = reinterpret_cast<IdxT*>(stage);
+  float* s_score = reinterpret_cast<float*>(stage + (size_t)total * sizeof(IdxT));
+  if (x.n_wait > 0) {
+    if (lane < x.n_wait) {
+      long long spins = 0;
+      while ((int)(ld_volatile_u32(x.wait_flags + lane) - x.epoch) < 0 && ++spins < (1ll << 28)) {
+      }
+    }
+    __threadfence_system();
+    __syncwarp();
+  }
   if (STAGED) {
     for (int e = lane; e < total; e += 32) {
       const int l = e / kc, j = e - l * kc;
-      s_idx[e] = cand_idx[(size_t)l * idx_list_stride + (size_t)q * kc + j];
-      s_score[e] = cand_score[(size_t)l * score_list_stride + (size_t)q * kc + j];
+      s_idx[e] = __ldcg(cand_idx + (size_t)l * idx_list_stride + (size_t)q * kc + j);
+      s_score[e] = __ldcg(cand_score + (size_t)l * score_list_stride + (size_t)q * kc + j);
     }
     __syncwarp();
   }
@@ -619,8 +649,8 @@ __global__ void __launch_bounds__(32) merge_topk_kernel(const float* __restrict_
       s = s_score[l * kc + j];
       id = (long long)s_idx[l * kc + j];
     } else {
-      id = (long long)cand_idx[(size_t)l * idx_list_stride + (size_t)q * kc + j];
-      s = cand_score[(size_t)l * score_list_stride + (size_t)q * kc + j];
+      id = (long long)__ldcg(cand_idx + (size_t)l * idx_list_stride + (size_t)q * kc + j);
+      s = __ldcg(cand_score + (size_t)l * score_list_stride + (size_t)q * kc + j);
     }
   };
   int head[kMergeMaxOwn];
@@ -649,7 +679,8 @@ __global__ void __launch_bounds__(32) merge_topk_kernel(const float* __restrict_
     }
   };
   rescan();
-  for (int r = 0; r < k; ++r) {
+  int r = 0;
+  for (; r < k; ++r) {
     // warp arg-best on (score desc, idx asc); padding (index < 0) always loses
     float ws = bs;
     long long wi = bi;
@@ -666,16 +697,10 @@ __global__ void __launch_bounds__(32) merge_topk_kernel(const float* __restrict_
         wl = ol;
       }
     }
+    if (wi < 0) break;  // every list exhausted: the rest is padding
     if (lane == 0) {
-      out_score[(size_t)q * k + r] = wi >= 0 ? ws : -CUDART_INF_F;
-      out_idx[(size_t)q * k + r] = wi >= 0 ? wi + idx_offset : -1;
-    }
-    if (wi < 0) {  // every list exhausted: the rest is padding
-      for (int rr = r + 1 + lane; rr < k; rr += 32) {
-        out_score[(size_t)q * k + rr] = -CUDART_INF_F;
-        out_idx[(size_t)q * k + rr] = -1;
-      }
-      break;
+      res_s[r] = ws;
+      res_i[r] = wi + idx_offset;
     }
     if (lane == wl) {  // only the winning lane's state changed
 #pragma unroll
@@ -684,6 +709,34 @@ __global__ void __launch_bounds__(32) merge_topk_kernel(const float* __restrict_
       rescan();
     }
     __syncwarp();
+  }
+  for (int rr = r + lane; rr < k; rr += 32) {
+    res_s[rr] = -CUDART_INF_F;
+    res_i[rr] = -1;
+  }
+  __syncwarp();
+  if (x.n_dest == 0) {
+    for (int j = lane; j < k; j += 32) {
+      out_score[(size_t)q * k + j] = res_s[j];
+      out_idx[(size_t)q * k + j] = res_i[j];
+    }
+  } else {
+    // fan the row out to every GPU's exchange buffer (peer stores over NVLink)
+    for (int e = lane; e < k * x.n_dest; e += 32) {
+      const int g = e / k, j = e - g * k;
+      x.dest_score[g][(size_t)q * k + j] = res_s[j];
+      x.dest_idx[g][(size_t)q * k + j] = res_i[j];
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned int prev = atomicAdd(x.done_counter, 1u);
+      if (prev == x.done_target - 1u) {  // last query of this search: publish
+        *x.done_counter = 0u;
+        __threadfence_system();
+        for (int g = 0; g < x.n_dest; ++g) st_volatile_u32(x.dest_flag[g], x.epoch);
+      }
+    }
   }
 }
 
@@ -724,35 +777,41 @@ template <typename IdxT>
 static cudaError_t launch_merge_t(const float* cand_score, const IdxT* cand_idx, int n_lists, int n_queries, int kc,
                                   int k, long long idx_offset, long long score_list_stride,
                                   long long idx_list_stride, float* out_score, long long* out_idx,
-                                  cudaStream_t stream) {
+                                  const MergeXchg* xc, cudaStream_t stream) {
   if (n_lists > 32 * kMergeMaxOwn) return cudaErrorInvalidValue;
-  const size_t bytes = (size_t)n_lists * kc * (sizeof(IdxT) + sizeof(float));
-  if (bytes <= 200 * 1024) {
+  MergeXchg x;
+  memset(&x, 0, sizeof(x));
+  if (xc) x = *xc;
+  const size_t res_bytes = ((size_t)k * 12 + 15) & ~size_t(15);
+  const size_t stage_bytes = (size_t)n_lists * kc * (sizeof(IdxT) + sizeof(float));
+  if (res_bytes + stage_bytes <= 200 * 1024) {
     auto kern = merge_topk_kernel<IdxT, true>;
+    const size_t bytes = res_bytes + stage_bytes;
     if (bytes > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
       if (e != cudaSuccess) return e;
     }
     kern<<<n_queries, 32, bytes, stream>>>(cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset,
-                                           score_list_stride, idx_list_stride, out_score, out_idx);
+                                           score_list_stride, idx_list_stride, out_score, out_idx, x);
   } else {
-    merge_topk_kernel<IdxT, false><<<n_queries, 32, 0, stream>>>(cand_score, cand_idx, n_lists, n_queries, kc, k,
-                                                                 idx_offset, score_list_stride, idx_list_stride,
-                                                                 out_score, out_idx);
+    merge_topk_kernel<IdxT, false><<<n_queries, 32, res_bytes, stream>>>(
+        cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, score_list_stride, idx_list_stride, out_score,
+        out_idx, x);
   }
   return cudaGetLastError();
 }
 
 cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int kc, int k,
-                             long long idx_offset, float* out_score, long long* out_idx, cudaStream_t stream) {
+                             long long idx_offset, float* out_score, long long* out_idx, const MergeXchg* xc,
+                             cudaStream_t stream) {
   return launch_merge_t<int>(cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, (long long)n_queries * kc,
-                             (long long)n_queries * kc, out_score, out_idx, stream);
+                             (long long)n_queries * kc, out_score, out_idx, xc, stream);
 }
 cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx, int n_lists, int n_queries, int kc,
                              int k, long long score_list_stride, long long idx_list_stride, float* out_score,
-                             long long* out_idx, cudaStream_t stream) {
+                             long long* out_idx, const MergeXchg* xc, cudaStream_t stream) {
   return launch_merge_t<long long>(cand_score, cand_idx, n_lists, n_queries, kc, k, 0, score_list_stride,
-                                   idx_list_stride, out_score, out_idx, stream);
+                                   idx_list_stride, out_score, out_idx, xc, stream);
 }
 
 }  // namespace rs

@@ -3,16 +3,20 @@
 Each rank owns a contiguous row shard behind one ``_cabi.Index``.  A search is
 
     local fused score+select  ->  B x k (score, global index) candidates per rank
-    ONE all-gather of the packed candidates over NCCL / NVLink  (B*k*12 bytes per rank)
-    on-device merge of the G sorted lists per query (rs_merge_device) on every rank
+    exchange of the candidates over NVLink (B*k*12 bytes per rank), either
+      exchange="nccl": ONE all-gather of the packed candidates (north_star (c)), or
+      exchange="p2p" : the local merge kernel itself stores each row into every GPU's buffer
+                       through CUDA-IPC peer pointers and raises an epoch flag (no collective call)
+    on-device merge of the G sorted lists per query on every rank
 
-The path has exactly one exchange step, so exactly one collective.  The reference has no
-multi-GPU search at all (it scales by whole-corpus replicas, request_queue.py:49).
+The path has exactly one exchange step.  The reference has no multi-GPU search at all (it scales
+by whole-corpus replicas, request_queue.py:49).
 
 ``gather_candidates`` is backend-agnostic (NCCL on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -53,7 +57,8 @@ class ShardedSearcher:
     every rank (device tensors)."""
 
     def __init__(self, n_rows_total: int, dim: int, dtype: str = "bf16", *, max_batch: int = 256,
-                 max_k: int = 128, device: Optional[int] = None, group=None, scale_exp: int = 0):
+                 max_k: int = 128, device: Optional[int] = None, group=None, scale_exp: int = 0,
+                 exchange: Optional[str] = None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -65,6 +70,17 @@ class ShardedSearcher:
         self.index = _cabi.Index(self.row1 - self.row0, dim, dtype, device=self.device, row_offset=self.row0,
                                  max_batch=max_batch, max_k=max_k, scale_exp=scale_exp)
         self._bufs = {}
+        self.exchange = exchange or os.environ.get("RS_EXCHANGE", "p2p")
+        if self.exchange not in ("nccl", "p2p"):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        self.xchg = None
+        if self.world > 1 and self.exchange == "p2p":
+            self.xchg = _cabi.Exchange(self.device, self.world, self.rank, max_batch, max_k)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.xchg.export_handle(), group=group)
+            for g, h in enumerate(handles):
+                self.xchg.import_handle(g, h)
+            dist.barrier(group=group)
 
     # ---- ingest
     def fill_synthetic(self, seed: int):
@@ -102,6 +118,10 @@ class ShardedSearcher:
             self.index.search_device(q_dev.data_ptr(), B, k, out_i.data_ptr(), out_s.data_ptr(), metric,
                                      query_terms, stream)
             return out_i, out_s
+        if self.xchg is not None:
+            self.xchg.search(self.index, q_dev.data_ptr(), B, k, out_i.data_ptr(), out_s.data_ptr(), metric,
+                             query_terms, stream)
+            return out_i, out_s
         li, ls = pack_views(local, B, k)
         self.index.search_device(q_dev.data_ptr(), B, k, li.data_ptr(), ls.data_ptr(), metric, query_terms, stream)
         gather_candidates(local, gathered, self.group)
@@ -119,4 +139,10 @@ class ShardedSearcher:
         return oi.cpu(), os_.cpu()
 
     def close(self):
+        if self.xchg is not None:
+            torch.cuda.synchronize(self.device)
+            if dist.is_initialized():
+                dist.barrier(group=self.group)      # nobody unmaps a buffer a peer may still write
+            self.xchg.close()
+            self.xchg = None
         self.index.close()

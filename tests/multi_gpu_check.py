@@ -24,13 +24,17 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     N, D = 100_003, 1024                       # uneven shards
     ok = True
-    for dtype, metric, k, B in (("bf16", "dot", 10, 32), ("fp32", "cosine", 5, 7), ("fp16", "dot", 100, 3)):
-        s = ShardedSearcher(N, D, dtype, max_batch=64, max_k=128, scale_exp=4 if dtype == "fp32" else 0)
+    for dtype, metric, k, B, exch in (("bf16", "dot", 10, 32, "p2p"), ("bf16", "dot", 10, 32, "nccl"),
+                                      ("fp32", "cosine", 5, 7, "p2p"), ("fp16", "dot", 100, 3, "nccl"),
+                                      ("bf16", "dot", 17, 100, "p2p")):
+        s = ShardedSearcher(N, D, dtype, max_batch=128, max_k=128, scale_exp=4 if dtype == "fp32" else 0,
+                            exchange=exch)
         s.fill_synthetic(1234)
         Q, src = o.synth_queries(9, N, B, D, dtype=o.DTYPE_NAMES[dtype])
         q_dev = torch.from_numpy(Q).cuda()
         terms = 2 if dtype == "fp32" else 1
-        idx, sc = s.search(q_dev, k, metric, terms)
+        for _ in range(3):                      # repeated calls exercise both parities of the exchange buffer
+            idx, sc = s.search(q_dev, k, metric, terms)
         torch.cuda.synchronize()
         idx, sc = idx.cpu().numpy(), sc.cpu().numpy()
         hidx, hsc = s.search_host(torch.from_numpy(Q).pin_memory(), k, metric, terms)
@@ -45,7 +49,7 @@ def main():
                          metric, accum=np.float64)
             sw = o.check_topk(idx, sc, S, k, rtol=1e-5 if dtype == "fp32" else 2e-3, atol=1e-6)
             assert (idx[:, 0] == src).all()
-            print(f"multi-gpu ok world={world} {dtype} {metric} k={k} B={B} near-tie swaps={sw}", flush=True)
+            print(f"multi-gpu ok world={world} {dtype} {metric} k={k} B={B} exchange={exch} near-tie swaps={sw}", flush=True)
         s.close()
     dist.barrier()
     dist.destroy_process_group()
