@@ -257,11 +257,15 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.mma_m = pl.mma_m;
     p.debug_flags = env_int("RS_DEBUG_FLAGS", 0);
     p.lo_coef = ix->plane_dtype == RS_DTYPE_FP16 ? ldexpf(1.0f, -RS_FP16_SPLIT_SHIFT) : 1.0f;
-    const int slot = (int)(ix->ev_count % rs_index::kEventRing);
-    RS_CUDA(cudaEventRecord(ix->ev_beg[slot], stream));
-    RS_CUDA(rs::launch_fused_search(p, grid, stream));
-    RS_CUDA(cudaEventRecord(ix->ev_end[slot], stream));
-    ++ix->ev_count;
+    if (env_int("RS_NO_EVENTS", 0)) {
+      RS_CUDA(rs::launch_fused_search(p, grid, stream));
+    } else {
+      const int slot = (int)(ix->ev_count % rs_index::kEventRing);
+      RS_CUDA(cudaEventRecord(ix->ev_beg[slot], stream));
+      RS_CUDA(rs::launch_fused_search(p, grid, stream));
+      RS_CUDA(cudaEventRecord(ix->ev_end[slot], stream));
+      ++ix->ev_count;
+    }
     if (!xg) {
       RS_CUDA(rs::launch_merge_i32(ix->cand_score, ix->cand_idx, grid, nb, k, k, ix->cfg.row_offset,
                                    out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, nullptr, stream));

@@ -12,8 +12,8 @@ struct SearchParams {
   const float* qscale;               // [bpad] power-of-two factor: raw accumulator -> dot product
   const float* dnorm;                // [n_tiles*128] document L2 norms (cosine)
   const float2* tile_norm_minmax;    // [n_tiles] (min, max) document norm per tile (cosine)
-  float* cand_score;                 // [grid][n_queries][k] per-CTA candidates, best first
-  int* cand_idx;                     // [grid][n_queries][k] local row ids, -1 = padding
+  float* cand_score;                 // [n_queries][grid][k] per-CTA candidates, best first
+  int* cand_idx;                     // [n_queries][grid][k] local row ids, -1 = padding
   int n_rows;                        // valid documents in this shard
   int n_tiles;                       // ceil(n_rows / 128)
   int n_queries;                     // B

@@ -122,7 +122,7 @@ constexpr int kBufC = 32;                                       // k > kRegK: un
 constexpr int kMaxListK = 128;                                  // k > kRegK: sorted list in smem, <= 4 slots per lane
 
 struct SmemMap {
-  uint32_t q_bytes, stage_off, bar_off, list_off, total;
+  uint32_t q_bytes, stage_off, bar_off, dump_off, list_off, total;
 };
 // q_resident: the whole Q image lives in shared memory for the kernel's lifetime (small batches);
 // otherwise Q k-chunks travel through the ring next to the document blocks (large batches).
@@ -132,7 +132,8 @@ __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, in
   m.q_bytes = q_resident ? (uint32_t)terms * kc * bpad * RS_KCHUNK_BYTES : 0u;
   m.stage_off = m.q_bytes;  // multiple of 1024 because bpad % 8 == 0
   m.bar_off = m.stage_off + (uint32_t)stages * RS_BLOCK_BYTES;
-  m.list_off = m.bar_off + 1024;
+  m.dump_off = m.bar_off + 1024;                       // per epilogue warp: one 32x32 fp32 chunk
+  m.list_off = m.dump_off + kNumEpiWarps * 4096;
   m.total = m.list_off + (reglist ? 0u : (uint32_t)(k + kBufC) * (uint32_t)bpad * 8u);
   return m;
 }
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       float* Bs = reinterpret_cast<float*>(Li + (size_t)k * lstride);
       int* Bi = reinterpret_cast<int*>(Bs + (size_t)kBufC * lstride);
       int cnt = 0;
+      float* dump = reinterpret_cast<float*>(smem + map.dump_off) + (size_t)quarter * 1024;  // 32 x 32 floats per warp
       if (REGLIST) {
 #pragma unroll
         for (int j = 0; j < kRegK; ++j) {
@@ -472,25 +474,27 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
             }
             const float m = max32(v);
             if (__any_sync(0xffffffffu, m > thr_raw)) {
-              // rare path: some query of this warp has a candidate in this 32-document chunk
+              // rare path: some query of this warp has a candidate in this 32-document chunk.  The
+              // chunk is parked in shared memory ([column][lane], conflict-free) so that every lane
+              // can walk ITS OWN passing columns with a dynamic index; the warp iterates
+              // max-over-lanes(popcount) times, not once per column that passes for anybody.
               uint32_t pm = 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) pm |= (v[j] > thr_raw) ? (1u << j) : 0u;
-              uint32_t any = __reduce_or_sync(0xffffffffu, pm);
-              while (any) {
-                const int j = __ffs(any) - 1;
-                any &= any - 1;
-                // re-read the single column from TMEM: warp-uniform address, no dynamic register index
-                float s = __uint_as_float(tmem_ld_x1(tacc + c0 + j));
-                if (NACC == 2) {
-                  float s1 = __uint_as_float(tmem_ld_x1(tacc + RS_TILE_ROWS + c0 + j));
-                  tmem_wait_ld();
-                  s = fmaf(s1, lo_coef, s);
-                } else {
-                  tmem_wait_ld();
-                }
-                const int idx = tile_row0 + c0 + j;
-                if (((pm >> j) & 1u) && idx < p.n_rows) {
+              for (int j = 0; j < 32; ++j) {
+                pm |= (v[j] > thr_raw) ? (1u << j) : 0u;
+                dump[j * 32 + lane] = v[j];
+              }
+              if (tile_row0 + c0 + 32 > p.n_rows) {  // ragged last tile: mask padded rows
+                const int valid = p.n_rows - (tile_row0 + c0);
+                pm = valid <= 0 ? 0u : (pm & (0xffffffffu >> (32 - valid)));
+              }
+              __syncwarp();
+              while (__any_sync(0xffffffffu, pm != 0u)) {
+                if (pm != 0u) {
+                  const int j = __ffs(pm) - 1;
+                  pm &= pm - 1;
+                  const float s = dump[j * 32 + lane];
+                  const int idx = tile_row0 + c0 + j;
                   float x = s;  // dot metric: compare and store raw units (exact power-of-two scale)
                   if (cosine) {
                     const float nd = p.dnorm[idx];
@@ -533,6 +537,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
                   }
                 }
               }
+              __syncwarp();
             }
           }
         }
@@ -557,8 +562,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       }
       // per-CTA candidates, best first; dot scores leave raw units here
       if (live) {
-        float* cs = p.cand_score + ((size_t)blockIdx.x * p.n_queries + row) * k;
-        int* ci = p.cand_idx + ((size_t)blockIdx.x * p.n_queries + row) * k;
+        float* cs = p.cand_score + ((size_t)row * gridDim.x + blockIdx.x) * k;   // [query][cta][k]
+        int* ci = p.cand_idx + ((size_t)row * gridDim.x + blockIdx.x) * k;
         if (REGLIST) {
 #pragma unroll
           for (int j = 0; j < kRegK; ++j) {
@@ -616,7 +621,7 @@ __global__ void __launch_bounds__(32) merge_topk_kernel(const float* __restrict_
                                                         const IdxT* __restrict__ cand_idx, int n_lists,
                                                         int n_queries, int kc, int k, long long idx_offset,
                                                         long long score_list_stride, long long idx_list_stride,
-                                                        float* __restrict__ out_score,
+                                                        long long query_stride, float* __restrict__ out_score,
                                                         long long* __restrict__ out_idx, const MergeXchg x) {
   extern __shared__ __align__(16) uint8_t merge_smem[];
   const int q = blockIdx.x;
@@ -636,11 +641,30 @@ __global__ void __launch_bounds__(32) merge_topk_kernel(const float* __restrict_
     __threadfence_system();
     __syncwarp();
   }
+  const size_t qoff = (size_t)q * query_stride;
   if (STAGED) {
-    for (int e = lane; e < total; e += 32) {
-      const int l = e / kc, j = e - l * kc;
-      s_idx[e] = __ldcg(cand_idx + (size_t)l * idx_list_stride + (size_t)q * kc + j);
-      s_score[e] = __ldcg(cand_score + (size_t)l * score_list_stride + (size_t)q * kc + j);
+    // element (list l, slot j) of this query sits at l*list_stride + q*query_stride + j; issue the
+    // loads four deep so the L2 round trips overlap
+    for (int e0 = lane; e0 < total; e0 += 128) {
+      IdxT ti[4];
+      float ts[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + 32 * u;
+        if (e < total) {
+          const int l = e / kc, j = e - l * kc;
+          ti[u] = __ldcg(cand_idx + (size_t)l * idx_list_stride + qoff + j);
+          ts[u] = __ldcg(cand_score + (size_t)l * score_list_stride + qoff + j);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + 32 * u;
+        if (e < total) {
+          s_idx[e] = ti[u];
+          s_score[e] = ts[u];
+        }
+      }
     }
     __syncwarp();
   }
@@ -649,8 +673,8 @@ __global__ void __launch_bounds__(32) merge_topk_kernel(const float* __restrict_
       s = s_score[l * kc + j];
       id = (long long)s_idx[l * kc + j];
     } else {
-      id = (long long)__ldcg(cand_idx + (size_t)l * idx_list_stride + (size_t)q * kc + j);
-      s = __ldcg(cand_score + (size_t)l * score_list_stride + (size_t)q * kc + j);
+      id = (long long)__ldcg(cand_idx + (size_t)l * idx_list_stride + qoff + j);
+      s = __ldcg(cand_score + (size_t)l * score_list_stride + qoff + j);
     }
   };
   int head[kMergeMaxOwn];
@@ -776,8 +800,8 @@ cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t st
 template <typename IdxT>
 static cudaError_t launch_merge_t(const float* cand_score, const IdxT* cand_idx, int n_lists, int n_queries, int kc,
                                   int k, long long idx_offset, long long score_list_stride,
-                                  long long idx_list_stride, float* out_score, long long* out_idx,
-                                  const MergeXchg* xc, cudaStream_t stream) {
+                                  long long idx_list_stride, long long query_stride, float* out_score,
+                                  long long* out_idx, const MergeXchg* xc, cudaStream_t stream) {
   if (n_lists > 32 * kMergeMaxOwn) return cudaErrorInvalidValue;
   MergeXchg x;
   memset(&x, 0, sizeof(x));
@@ -792,11 +816,11 @@ static cudaError_t launch_merge_t(const float* cand_score, const IdxT* cand_idx,
       if (e != cudaSuccess) return e;
     }
     kern<<<n_queries, 32, bytes, stream>>>(cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset,
-                                           score_list_stride, idx_list_stride, out_score, out_idx, x);
+                                           score_list_stride, idx_list_stride, query_stride, out_score, out_idx, x);
   } else {
     merge_topk_kernel<IdxT, false><<<n_queries, 32, res_bytes, stream>>>(
-        cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, score_list_stride, idx_list_stride, out_score,
-        out_idx, x);
+        cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, score_list_stride, idx_list_stride, query_stride,
+        out_score, out_idx, x);
   }
   return cudaGetLastError();
 }
@@ -804,14 +828,15 @@ static cudaError_t launch_merge_t(const float* cand_score, const IdxT* cand_idx,
 cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int kc, int k,
                              long long idx_offset, float* out_score, long long* out_idx, const MergeXchg* xc,
                              cudaStream_t stream) {
-  return launch_merge_t<int>(cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, (long long)n_queries * kc,
-                             (long long)n_queries * kc, out_score, out_idx, xc, stream);
+  // per-CTA candidates are stored [query][cta][k]: one query's lists are contiguous (coalesced staging)
+  return launch_merge_t<int>(cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, (long long)kc,
+                             (long long)kc, (long long)n_lists * kc, out_score, out_idx, xc, stream);
 }
 cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx, int n_lists, int n_queries, int kc,
                              int k, long long score_list_stride, long long idx_list_stride, float* out_score,
                              long long* out_idx, const MergeXchg* xc, cudaStream_t stream) {
   return launch_merge_t<long long>(cand_score, cand_idx, n_lists, n_queries, kc, k, 0, score_list_stride,
-                                   idx_list_stride, out_score, out_idx, xc, stream);
+                                   idx_list_stride, (long long)kc, out_score, out_idx, xc, stream);
 }
 
 }  // namespace rs
