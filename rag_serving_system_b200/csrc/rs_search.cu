@@ -232,14 +232,14 @@ __device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs,
 // One CTA walks "supertiles" of p.sub consecutive 128-document tiles.  Per supertile the K loop
 // is outermost: for every 64-element k-chunk the (optional) Q blocks arrive once and are reused
 // by the MMAs of all p.sub document blocks, each accumulating into its own TMEM columns.
-template <int NACC, bool REGLIST>
+template <int NACC, bool REGLIST, bool QRES>
 __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned shared memory; the launcher over-allocates by 1 KiB
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool q_resident = p.q_resident != 0;
+  constexpr bool q_resident = QRES;
   const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.k, REGLIST, q_resident);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t q_smem = smem_base;
@@ -346,23 +346,27 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
         const uint32_t dbase = tmem_base + (uint32_t)(acc * S * NACC) * RS_TILE_ROWS;
         for (int kc = 0; kc < p.kc; ++kc) {
           uint64_t a0, a1 = 0;
-          int qslot[2] = {0, 0};
+          int qslot0 = 0, qslot1 = 0;
           if (q_resident) {
             a0 = umma_smem_desc(q_smem + (uint32_t)kc * qblk);
             a1 = umma_smem_desc(q_smem + (uint32_t)(p.kc + kc) * qblk);
           } else {
-            uint64_t a[2] = {0, 0};
-            for (int j = 0; j < p.terms; ++j) {
+            mbar_wait(full_bar(s), ph);
+            a0 = umma_smem_desc(stage_smem + (uint32_t)s * RS_BLOCK_BYTES);
+            qslot0 = s;
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1u;
+            }
+            if (p.terms == 2) {
               mbar_wait(full_bar(s), ph);
-              a[j] = umma_smem_desc(stage_smem + (uint32_t)s * RS_BLOCK_BYTES);
-              qslot[j] = s;
+              a1 = umma_smem_desc(stage_smem + (uint32_t)s * RS_BLOCK_BYTES);
+              qslot1 = s;
               if (++s == p.stages) {
                 s = 0;
                 ph ^= 1u;
               }
             }
-            a0 = a[0];
-            a1 = a[1];
           }
           for (int pl = 0; pl < p.planes; ++pl) {
             for (int sub = 0; sub < nsub; ++sub) {
@@ -384,8 +388,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
               }
             }
           }
-          if (!q_resident)
-            for (int j = 0; j < p.terms; ++j) umma_commit(empty_bar(qslot[j]));  // Q chunk fully consumed
+          if (!q_resident) {  // Q chunk(s) fully consumed by this k-chunk group
+            umma_commit(empty_bar(qslot0));
+            if (p.terms == 2) umma_commit(empty_bar(qslot1));
+          }
         }
         umma_commit(tfull_bar(acc));  // accumulators complete -> epilogue
         if (++acc == NB) {
@@ -774,10 +780,10 @@ cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dt
   return cudaGetLastError();
 }
 
-template <int NACC, bool REGLIST>
+template <int NACC, bool REGLIST, bool QRES>
 static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t stream) {
-  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.k, REGLIST, p.q_resident != 0);
-  auto kern = fused_search_kernel<NACC, REGLIST>;
+  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.k, REGLIST, QRES);
+  auto kern = fused_search_kernel<NACC, REGLIST, QRES>;
   const int bytes = (int)map.total + 1024;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
@@ -790,11 +796,17 @@ int fused_smem_bytes(int bpad, int kc, int terms, int stages, int k, int q_resid
 }
 int fused_reg_k() { return kRegK; }
 
+template <int NACC, bool REGLIST>
+static cudaError_t launch_fused_q(const SearchParams& p, int grid, cudaStream_t stream) {
+  return p.q_resident ? launch_fused_t<NACC, REGLIST, true>(p, grid, stream)
+                      : launch_fused_t<NACC, REGLIST, false>(p, grid, stream);
+}
+
 cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t stream) {
   const bool reglist = p.k <= kRegK;
   const int nacc = (p.terms == 2 || p.planes == 2) ? 2 : 1;
-  if (nacc == 1) return reglist ? launch_fused_t<1, true>(p, grid, stream) : launch_fused_t<1, false>(p, grid, stream);
-  return reglist ? launch_fused_t<2, true>(p, grid, stream) : launch_fused_t<2, false>(p, grid, stream);
+  if (nacc == 1) return reglist ? launch_fused_q<1, true>(p, grid, stream) : launch_fused_q<1, false>(p, grid, stream);
+  return reglist ? launch_fused_q<2, true>(p, grid, stream) : launch_fused_q<2, false>(p, grid, stream);
 }
 
 template <typename IdxT>
