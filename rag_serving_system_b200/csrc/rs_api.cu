@@ -36,7 +36,6 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 constexpr int kMaxSmem = 232448;  // 227 KiB opt-in dynamic shared memory per CTA on sm_100
-constexpr int kMinResidentStages = 6;   // resident-Q mode wants a deep ring beside the query image
 constexpr int kMaxStages = 24;
 constexpr int64_t kIngestChunkBytes = 64ll << 20;
 
@@ -49,6 +48,7 @@ struct Plan {
   int sub;         // 128-document tiles per supertile
   int nbuf;        // TMEM accumulator buffers
   int mma_m;       // MMA M: 64 when the padded batch fits, else 128
+  int cps;         // k-chunks per ring stage
 };
 
 int env_int(const char* name, int dflt) {
@@ -106,11 +106,11 @@ namespace {
 
 constexpr size_t kXchgHeader = 256;
 
-int max_cap_rows(int kc, int terms, int k, int min_stages, int q_resident) {
+int max_cap_rows(int kc, int terms, int k, int min_stages, int cps, int q_resident) {
   // largest bpad (multiple of 8, <= 128) that leaves at least min_stages ring slots
   int best = 0;
   for (int bpad = 8; bpad <= 128; bpad += 8) {
-    if (rs::fused_smem_bytes(bpad, kc, terms, min_stages, k, q_resident) <= kMaxSmem) best = bpad;
+    if (rs::fused_smem_bytes(bpad, kc, terms, min_stages, cps, k, q_resident) <= kMaxSmem) best = bpad;
   }
   return best;
 }
@@ -120,7 +120,17 @@ int max_cap_rows(int kc, int terms, int k, int min_stages, int q_resident) {
 // chunk over `sub` document tiles that accumulate side by side in TMEM.
 int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
   const int nacc = (terms == 2 || ix->planes == 2) ? 2 : 1;
-  const int cap_res = max_cap_rows(ix->kc, terms, k, kMinResidentStages, 1);
+  // two k-chunks (32 KiB) per ring stage halve the barrier round trips per byte
+  int cps = env_int("RS_CPS", ix->kc % 2 == 0 ? 2 : 1);
+  if (cps != 1 && !(cps == 2 && ix->kc % 2 == 0)) return fail(RS_E_INVALID, "RS_CPS=%d invalid for dim=%d", cps, ix->cfg.dim);
+  int kMinResidentStages = cps == 2 ? 3 : 6;
+  int cap_res = max_cap_rows(ix->kc, terms, k, kMinResidentStages, cps, 1);
+  if (B > cap_res && cps == 2 && B <= max_cap_rows(ix->kc, terms, k, 6, 1, 1)) {
+    cps = 1;  // the batch still fits next to a ring of six 16 KiB stages
+    kMinResidentStages = 6;
+    cap_res = max_cap_rows(ix->kc, terms, k, 6, 1, 1);
+  }
+  pl->cps = cps;
   int resident = B <= cap_res ? 1 : 0;
   resident = env_int("RS_QRESIDENT", resident);
   int min_stages = kMinResidentStages;
@@ -131,17 +141,22 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
   } else {
     // one k-chunk group (terms Q items + planes*sub document items) must fit in the ring with a
     // slot to spare; prefer the fewest passes, then the largest sub (least Q re-reading)
-    int best_passes = 1 << 30;
-    for (int sub = (nacc == 1 ? 4 : 2); sub >= 1; sub >>= 1) {
-      const int need = terms + ix->planes * sub + 1;
-      const int c = max_cap_rows(ix->kc, terms, k, need, 0);
-      if (c <= 0) continue;
-      const int passes = (B + c - 1) / c;
-      if (passes < best_passes) {
-        best_passes = passes;
-        pl->sub = sub;
-        cap = c;
-        min_stages = need;
+    int best_passes = 1 << 30, best_sub = 0;
+    const int cps_hi = cps;
+    for (int c2 = cps_hi; c2 >= 1; --c2) {
+      for (int sub = (nacc == 1 ? 4 : 2); sub >= 1; sub >>= 1) {
+        const int need = terms + ix->planes * sub + 1;
+        const int c = max_cap_rows(ix->kc, terms, k, need, c2, 0);
+        if (c <= 0) continue;
+        const int passes = (B + c - 1) / c;
+        if (passes < best_passes || (passes == best_passes && sub > best_sub)) {
+          best_passes = passes;
+          best_sub = sub;
+          pl->sub = sub;
+          pl->cps = cps = c2;
+          cap = c;
+          min_stages = need;
+        }
       }
     }
     if (best_passes == (1 << 30)) cap = 0;
@@ -164,9 +179,9 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
     return fail(RS_E_INVALID, "sub=%d nbuf=%d nacc=%d does not map onto 128/256/512 TMEM columns", pl->sub, pl->nbuf, nacc);
   int stages = min_stages;
   while (stages < kMaxStages &&
-         rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages + 1, k, resident) <= kMaxSmem)
+         rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages + 1, cps, k, resident) <= kMaxSmem)
     ++stages;
-  if (rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages, k, resident) > kMaxSmem)
+  if (rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages, cps, k, resident) > kMaxSmem)
     return fail(RS_E_UNSUPPORTED, "B=%d k=%d does not fit in shared memory", B, k);
   pl->stages = stages;
   return RS_OK;
@@ -209,7 +224,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   const int grid = std::min(ix->sm_count, ix->n_tiles);
   ix->stats.grid = grid;
   ix->stats.stages = pl.stages;
-  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, k, pl.q_resident);
+  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident);
   ix->stats.q_resident = pl.q_resident;
   ix->stats.sub = pl.sub;
   ix->stats.nbuf = pl.nbuf;
@@ -251,6 +266,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.metric = metric;
     p.dtype = ix->plane_dtype;
     p.stages = pl.stages;
+    p.cps = pl.cps;
     p.q_resident = pl.q_resident;
     p.sub = pl.sub;
     p.nbuf = pl.nbuf;
@@ -350,7 +366,7 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   ix->stats.corpus_bytes = (int64_t)ix->corpus_bytes;
 
   const int grid = std::min(ix->sm_count, ix->n_tiles);
-  const int cap1 = max_cap_rows(ix->kc, 1, 1, 3, 0);
+  const int cap1 = max_cap_rows(ix->kc, 1, 1, 3, 1, 0);
   if (cap1 <= 0) {
     delete ix;
     return fail(RS_E_UNSUPPORTED, "dim=%d does not fit the shared-memory pipeline", cfg->dim);

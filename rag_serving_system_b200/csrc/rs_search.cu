@@ -126,12 +126,12 @@ struct SmemMap {
 };
 // q_resident: the whole Q image lives in shared memory for the kernel's lifetime (small batches);
 // otherwise Q k-chunks travel through the ring next to the document blocks (large batches).
-__host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, int stages, int k, bool reglist,
-                                                 bool q_resident) {
+__host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, int stages, int cps, int k,
+                                                 bool reglist, bool q_resident) {
   SmemMap m;
   m.q_bytes = q_resident ? (uint32_t)terms * kc * bpad * RS_KCHUNK_BYTES : 0u;
   m.stage_off = m.q_bytes;  // multiple of 1024 because bpad % 8 == 0
-  m.bar_off = m.stage_off + (uint32_t)stages * RS_BLOCK_BYTES;
+  m.bar_off = m.stage_off + (uint32_t)stages * (uint32_t)cps * RS_BLOCK_BYTES;
   m.dump_off = m.bar_off + 1024;                       // per epilogue warp: one 32x32 fp32 chunk
   m.list_off = m.dump_off + kNumEpiWarps * 4096;
   m.total = m.list_off + (reglist ? 0u : (uint32_t)(k + kBufC) * (uint32_t)bpad * 8u);
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr bool q_resident = QRES;
-  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.k, REGLIST, q_resident);
+  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, q_resident);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t q_smem = smem_base;
   const uint32_t stage_smem = smem_base + map.stage_off;
@@ -287,117 +287,129 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
 
   const size_t tile_bytes = (size_t)p.planes * p.kc * RS_BLOCK_BYTES;
 
+  // Both single-issuer roles run their loops with the WHOLE warp converged (uniform control flow,
+  // descriptors and counters stay in uniform registers); only the copy / MMA / commit instructions
+  // themselves are predicated on lane 0.  The per-stage latency of these two loops is on the
+  // critical path of the ring, so they are kept as short as possible.
+  const int cps = p.cps;                                   // 64-element k-chunks per ring stage (1 or 2)
+  const uint32_t stage_bytes = (uint32_t)cps * RS_BLOCK_BYTES;
   if (warp == kProducerWarp) {
     // ===================== bulk-copy producer =====================
-    if (lane == 0) {
-      const uint64_t pol_stream = l2_policy_evict_first();
-      const uint64_t pol_keep = l2_policy_evict_last();
-      if (q_resident) {
-        mbar_arrive_expect_tx(qfull_bar, map.q_bytes);
-        for (uint32_t off = 0; off < map.q_bytes; off += 32768u) {
-          uint32_t n = min(32768u, map.q_bytes - off);
-          bulk_g2s(q_smem + off, p.qimg + off, n, qfull_bar, pol_keep);
-        }
+    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_keep = l2_policy_evict_last();
+    if (q_resident && lane == 0) {
+      mbar_arrive_expect_tx(qfull_bar, map.q_bytes);
+      for (uint32_t off = 0; off < map.q_bytes; off += 32768u) {
+        uint32_t n = min(32768u, map.q_bytes - off);
+        bulk_g2s(q_smem + off, p.qimg + off, n, qfull_bar, pol_keep);
       }
-      int s = 0;
-      uint32_t ph = 0;
-      auto push = [&](const void* src, uint32_t bytes, uint64_t pol) {
-        mbar_wait(empty_bar(s), ph ^ 1u);
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    auto push = [&](const void* src, uint32_t bytes, uint64_t pol) {
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      if (lane == 0) {
         mbar_arrive_expect_tx(full_bar(s), bytes);
-        bulk_g2s(stage_smem + (uint32_t)s * RS_BLOCK_BYTES, src, bytes, full_bar(s), pol);
-        if (++s == p.stages) {
-          s = 0;
-          ph ^= 1u;
-        }
-      };
-      for (int u = blockIdx.x; u < n_super; u += gridDim.x) {
-        const int nsub = min(S, p.n_tiles - u * S);
-        const uint8_t* src = p.corpus + (size_t)u * S * tile_bytes;
-        for (int kc = 0; kc < p.kc; ++kc) {
-          if (!q_resident)
-            for (int j = 0; j < p.terms; ++j) push(p.qimg + (size_t)(j * p.kc + kc) * qblk, qblk, pol_keep);
-          for (int pl = 0; pl < p.planes; ++pl)
-            for (int sub = 0; sub < nsub; ++sub)
-              push(src + (size_t)sub * tile_bytes + (size_t)(pl * p.kc + kc) * RS_BLOCK_BYTES, RS_BLOCK_BYTES,
-                   pol_stream);
-        }
+        bulk_g2s(stage_smem + (uint32_t)s * stage_bytes, src, bytes, full_bar(s), pol);
+      }
+      if (++s == p.stages) {
+        s = 0;
+        ph ^= 1u;
+      }
+    };
+    for (int u = blockIdx.x; u < n_super; u += gridDim.x) {
+      const int nsub = min(S, p.n_tiles - u * S);
+      const uint8_t* src = p.corpus + (size_t)u * S * tile_bytes;
+      for (int kc = 0; kc < p.kc; kc += cps) {
+        if (!q_resident)
+          for (int j = 0; j < p.terms; ++j) push(p.qimg + (size_t)(j * p.kc + kc) * qblk, cps * qblk, pol_keep);
+        for (int pl = 0; pl < p.planes; ++pl)
+          for (int sub = 0; sub < nsub; ++sub)
+            push(src + (size_t)sub * tile_bytes + (size_t)(pl * p.kc + kc) * RS_BLOCK_BYTES, stage_bytes, pol_stream);
       }
     }
   } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(p.dtype == RS_DTYPE_BF16, p.mma_m, RS_TILE_ROWS);
-      if (q_resident) mbar_wait(qfull_bar, 0);
-      int s = 0;
-      uint32_t ph = 0;
-      int acc = 0;
-      uint32_t acc_ph = 0;
-      // 16-byte units: one UMMA K step (16 elements x 2 B) advances the start address by 2
-      auto issue4 = [&](uint32_t d, uint64_t a, uint64_t b, bool fresh) {
-        if (p.debug_flags & 1) return;  // timing experiment only: stream the corpus, issue no MMAs
+    // ===================== MMA issuer (lane 0 issues) =====================
+    const uint32_t idesc = umma_idesc_f16(p.dtype == RS_DTYPE_BF16, p.mma_m, RS_TILE_ROWS);
+    if (q_resident) mbar_wait(qfull_bar, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    const bool skip_mma = (p.debug_flags & 1) != 0;  // timing experiment only
+    // 16-byte units: one UMMA K step (16 elements x 2 B) advances the start address by 2
+    auto issue = [&](uint32_t d, uint32_t a_smem, uint32_t b_smem, bool fresh) {
+      if (lane == 0 && !skip_mma) {
+        const uint64_t a = umma_smem_desc(a_smem), b = umma_smem_desc(b_smem);
 #pragma unroll
         for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
           umma_f16(d, a + 2u * ks, b + 2u * ks, idesc, (fresh && ks == 0) ? 0u : 1u);
-      };
-      for (int u = blockIdx.x; u < n_super; u += gridDim.x) {
-        const int nsub = min(S, p.n_tiles - u * S);
-        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
-        tc_fence_after();
-        const uint32_t dbase = tmem_base + (uint32_t)(acc * S * NACC) * RS_TILE_ROWS;
-        for (int kc = 0; kc < p.kc; ++kc) {
-          uint64_t a0, a1 = 0;
-          int qslot0 = 0, qslot1 = 0;
-          if (q_resident) {
-            a0 = umma_smem_desc(q_smem + (uint32_t)kc * qblk);
-            a1 = umma_smem_desc(q_smem + (uint32_t)(p.kc + kc) * qblk);
-          } else {
+      }
+    };
+    for (int u = blockIdx.x; u < n_super; u += gridDim.x) {
+      const int nsub = min(S, p.n_tiles - u * S);
+      mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+      tc_fence_after();
+      const uint32_t dbase = tmem_base + (uint32_t)(acc * S * NACC) * RS_TILE_ROWS;
+      for (int kc = 0; kc < p.kc; kc += cps) {
+        uint32_t qa0, qa1 = 0;
+        int qslot0 = 0, qslot1 = 0;
+        if (q_resident) {
+          qa0 = q_smem + (uint32_t)kc * qblk;
+          qa1 = q_smem + (uint32_t)(p.kc + kc) * qblk;
+        } else {
+          mbar_wait(full_bar(s), ph);
+          qa0 = stage_smem + (uint32_t)s * stage_bytes;
+          qslot0 = s;
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+          if (p.terms == 2) {
             mbar_wait(full_bar(s), ph);
-            a0 = umma_smem_desc(stage_smem + (uint32_t)s * RS_BLOCK_BYTES);
-            qslot0 = s;
+            qa1 = stage_smem + (uint32_t)s * stage_bytes;
+            qslot1 = s;
             if (++s == p.stages) {
               s = 0;
               ph ^= 1u;
             }
-            if (p.terms == 2) {
-              mbar_wait(full_bar(s), ph);
-              a1 = umma_smem_desc(stage_smem + (uint32_t)s * RS_BLOCK_BYTES);
-              qslot1 = s;
-              if (++s == p.stages) {
-                s = 0;
-                ph ^= 1u;
-              }
-            }
           }
-          for (int pl = 0; pl < p.planes; ++pl) {
-            for (int sub = 0; sub < nsub; ++sub) {
-              mbar_wait(full_bar(s), ph);
-              tc_fence_after();
-              const uint64_t bdesc = umma_smem_desc(stage_smem + (uint32_t)s * RS_BLOCK_BYTES);
-              const uint32_t d0 = dbase + (uint32_t)(sub * NACC) * RS_TILE_ROWS;
+        }
+        for (int pl = 0; pl < p.planes; ++pl) {
+          for (int sub = 0; sub < nsub; ++sub) {
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t b_smem = stage_smem + (uint32_t)s * stage_bytes;
+            const uint32_t d0 = dbase + (uint32_t)(sub * NACC) * RS_TILE_ROWS;
+            for (int c = 0; c < cps; ++c) {
+              const bool fresh = (kc + c) == 0;
+              const uint32_t bc = b_smem + (uint32_t)c * RS_BLOCK_BYTES;
               if (pl == 0) {
-                issue4(d0, a0, bdesc, kc == 0);
-                if (NACC == 2) issue4(d0 + RS_TILE_ROWS, a1, bdesc, kc == 0);
+                issue(d0, qa0 + (uint32_t)c * qblk, bc, fresh);
+                if (NACC == 2) issue(d0 + RS_TILE_ROWS, qa1 + (uint32_t)c * qblk, bc, fresh);
               } else {
                 // lo plane of an fp32 corpus: q_hi . d_lo joins the low-order accumulator
-                issue4(d0 + RS_TILE_ROWS, a0, bdesc, false);
-              }
-              umma_commit(empty_bar(s));  // smem slot is free once these MMAs have read it
-              if (++s == p.stages) {
-                s = 0;
-                ph ^= 1u;
+                issue(d0 + RS_TILE_ROWS, qa0 + (uint32_t)c * qblk, bc, false);
               }
             }
-          }
-          if (!q_resident) {  // Q chunk(s) fully consumed by this k-chunk group
-            umma_commit(empty_bar(qslot0));
-            if (p.terms == 2) umma_commit(empty_bar(qslot1));
+            __syncwarp();
+            if (lane == 0) umma_commit(empty_bar(s));  // smem slot is free once these MMAs have read it
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1u;
+            }
           }
         }
-        umma_commit(tfull_bar(acc));  // accumulators complete -> epilogue
-        if (++acc == NB) {
-          acc = 0;
-          acc_ph ^= 1u;
+        if (!q_resident && lane == 0) {  // Q chunk(s) fully consumed by this k-chunk group
+          umma_commit(empty_bar(qslot0));
+          if (p.terms == 2) umma_commit(empty_bar(qslot1));
         }
+      }
+      __syncwarp();
+      if (lane == 0) umma_commit(tfull_bar(acc));  // accumulators complete -> epilogue
+      if (++acc == NB) {
+        acc = 0;
+        acc_ph ^= 1u;
       }
     }
   } else {
@@ -782,7 +794,7 @@ cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dt
 
 template <int NACC, bool REGLIST, bool QRES>
 static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t stream) {
-  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.k, REGLIST, QRES);
+  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, QRES);
   auto kern = fused_search_kernel<NACC, REGLIST, QRES>;
   const int bytes = (int)map.total + 1024;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -791,8 +803,8 @@ static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t 
   return cudaGetLastError();
 }
 
-int fused_smem_bytes(int bpad, int kc, int terms, int stages, int k, int q_resident) {
-  return (int)make_smem_map(bpad, kc, terms, stages, k, k <= kRegK, q_resident != 0).total + 1024;
+int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident) {
+  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0).total + 1024;
 }
 int fused_reg_k() { return kRegK; }
 

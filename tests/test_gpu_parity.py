@@ -182,7 +182,7 @@ def test_many_tiles_per_cta_and_all_ctas():
 
 # ---------------------------------------------------------------- every kernel mode the planner can pick
 MODES = [
-    {"RS_MMA_M": "128"}, {"RS_MMA_M": "64"},
+    {"RS_MMA_M": "128"}, {"RS_MMA_M": "64"}, {"RS_CPS": "1"}, {"RS_CPS": "1", "RS_QRESIDENT": "0", "RS_SUB": "2", "RS_NBUF": "2"},
     {"RS_QRESIDENT": "0", "RS_SUB": "1", "RS_NBUF": "2"}, {"RS_QRESIDENT": "0", "RS_SUB": "2", "RS_NBUF": "2"},
     {"RS_QRESIDENT": "0", "RS_SUB": "4", "RS_NBUF": "1"}, {"RS_QRESIDENT": "0", "RS_SUB": "2", "RS_NBUF": "1", "RS_MMA_M": "128"},
     {"RS_QRESIDENT": "1", "RS_SUB": "2", "RS_NBUF": "2"},

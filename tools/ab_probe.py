@@ -1,0 +1,20 @@
+"""A/B of kernel knobs on one box: 10M x 1024 bf16, B=32, k=10."""
+import os, sys, json
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
+from rag_serving_system_b200 import _cabi
+from perf_sweep import run
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+ix = _cabi.Index(rows, 1024, "bf16", max_batch=256, max_k=128)
+ix.fill_synthetic(1234, 0); ix.finalize()
+g = torch.Generator().manual_seed(0)
+q = torch.randn(256, 1024, generator=g); q = (q / q.norm(dim=1, keepdim=True)).bfloat16().float().cuda()
+out = []
+for rep in range(2):
+    for env in ({"RS_CPS": 2, "RS_MMA_M": 64}, {"RS_CPS": 1, "RS_MMA_M": 64}, {"RS_CPS": 2, "RS_MMA_M": 128}, {"RS_CPS": 1, "RS_MMA_M": 128}):
+        run(ix, q, 32, 10, "dot", 1, steps, env, "B32", out)
+for B in (64, 128):
+    run(ix, q, B, 10, "dot", 1, steps, {}, f"B{B}", out)
+    run(ix, q, B, 10, "dot", 1, steps, {"RS_CPS": 1}, f"B{B}", out)

@@ -43,7 +43,7 @@ class Power:
 
 
 def run(ix, q_dev, B, k, metric, terms, steps, env, label, out):
-    for key in ("RS_MMA_M", "RS_QRESIDENT", "RS_SUB", "RS_NBUF"):
+    for key in ("RS_MMA_M", "RS_QRESIDENT", "RS_SUB", "RS_NBUF", "RS_CPS"):
         os.environ.pop(key, None)
     os.environ.update({k_: str(v) for k_, v in env.items()})
     oi = torch.empty((B, k), dtype=torch.int64, device="cuda")
@@ -70,7 +70,7 @@ def run(ix, q_dev, B, k, metric, terms, steps, env, label, out):
             "kernel_ms": round(kms, 4), "step_ms": round(step_ms, 4),
             "GBps": round(stats["corpus_bytes"] / (kms / 1e3) / 1e9, 1), "qps": round(B / (step_ms / 1e3), 1),
             "passes": stats["passes"], "stages": stats["stages"], "q_resident": stats["q_resident"],
-            "sub": stats["sub"], "nbuf": stats["nbuf"], "mma_m": stats["mma_m"],
+            "sub": stats["sub"], "nbuf": stats["nbuf"], "mma_m": stats["mma_m"], "smem": stats["smem_bytes"],
             "sm_mhz": float(np.median(pw.c)) if pw.c else None, "power_w": float(np.median(pw.p)) if pw.p else None,
             "reasons": hex(pw.r), "kmin": round(float(kt.min()), 4), "kmax": round(float(kt.max()), 4),
         }
