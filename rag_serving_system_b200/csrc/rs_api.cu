@@ -110,7 +110,7 @@ int max_cap_rows(int kc, int terms, int k, int min_stages, int cps, int q_reside
   // largest bpad (multiple of 8, <= 128) that leaves at least min_stages ring slots
   int best = 0;
   for (int bpad = 8; bpad <= 128; bpad += 8) {
-    if (rs::fused_smem_bytes(bpad, kc, terms, min_stages, cps, k, q_resident) <= kMaxSmem) best = bpad;
+    if (rs::fused_smem_bytes(bpad, kc, terms, min_stages, cps, k, q_resident, 2 * terms) <= kMaxSmem) best = bpad;
   }
   return best;
 }
@@ -122,10 +122,10 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
   const int nacc = (terms == 2 || ix->planes == 2) ? 2 : 1;
   // two k-chunks (32 KiB) per ring stage halve the barrier round trips per byte
   int cps = env_int("RS_CPS", ix->kc % 2 == 0 ? 2 : 1);
-  if (cps != 1 && !(cps == 2 && ix->kc % 2 == 0)) return fail(RS_E_INVALID, "RS_CPS=%d invalid for dim=%d", cps, ix->cfg.dim);
-  int kMinResidentStages = cps == 2 ? 3 : 6;
+  if ((cps != 1 && cps != 2 && cps != 4) || ix->kc % cps != 0) return fail(RS_E_INVALID, "RS_CPS=%d invalid for dim=%d", cps, ix->cfg.dim);
+  int kMinResidentStages = cps == 4 ? 2 : (cps == 2 ? 3 : 6);
   int cap_res = max_cap_rows(ix->kc, terms, k, kMinResidentStages, cps, 1);
-  if (B > cap_res && cps == 2 && B <= max_cap_rows(ix->kc, terms, k, 6, 1, 1)) {
+  if (B > cap_res && cps >= 2 && B <= max_cap_rows(ix->kc, terms, k, 6, 1, 1)) {
     cps = 1;  // the batch still fits next to a ring of six 16 KiB stages
     kMinResidentStages = 6;
     cap_res = max_cap_rows(ix->kc, terms, k, 6, 1, 1);
@@ -145,7 +145,7 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
     const int cps_hi = cps;
     for (int c2 = cps_hi; c2 >= 1; --c2) {
       for (int sub = (nacc == 1 ? 4 : 2); sub >= 1; sub >>= 1) {
-        const int need = terms + ix->planes * sub + 1;
+        const int need = ix->planes * sub + 1;   // one k-chunk group of document blocks + 1 (Q has its own ring)
         const int c = max_cap_rows(ix->kc, terms, k, need, c2, 0);
         if (c <= 0) continue;
         const int passes = (B + c - 1) / c;
@@ -171,7 +171,7 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
   if (pl->mma_m != 128 && !(pl->mma_m == 64 && pl->bpad <= 64)) return fail(RS_E_INVALID, "RS_MMA_M=%d invalid for bpad=%d", pl->mma_m, pl->bpad);
   if (getenv("RS_SUB")) {
     pl->sub = env_int("RS_SUB", pl->sub);
-    min_stages = resident ? kMinResidentStages : terms + ix->planes * pl->sub + 1;
+    min_stages = resident ? kMinResidentStages : ix->planes * pl->sub + 1;
   }
   pl->nbuf = env_int("RS_NBUF", pl->nbuf);
   const int cols = pl->sub * pl->nbuf * nacc;
@@ -179,9 +179,9 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
     return fail(RS_E_INVALID, "sub=%d nbuf=%d nacc=%d does not map onto 128/256/512 TMEM columns", pl->sub, pl->nbuf, nacc);
   int stages = min_stages;
   while (stages < kMaxStages &&
-         rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages + 1, cps, k, resident) <= kMaxSmem)
+         rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages + 1, cps, k, resident, 2 * terms) <= kMaxSmem)
     ++stages;
-  if (rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages, cps, k, resident) > kMaxSmem)
+  if (rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages, cps, k, resident, 2 * terms) > kMaxSmem)
     return fail(RS_E_UNSUPPORTED, "B=%d k=%d does not fit in shared memory", B, k);
   pl->stages = stages;
   return RS_OK;
@@ -224,7 +224,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   const int grid = std::min(ix->sm_count, ix->n_tiles);
   ix->stats.grid = grid;
   ix->stats.stages = pl.stages;
-  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident);
+  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms);
   ix->stats.q_resident = pl.q_resident;
   ix->stats.sub = pl.sub;
   ix->stats.nbuf = pl.nbuf;
@@ -267,6 +267,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.dtype = ix->plane_dtype;
     p.stages = pl.stages;
     p.cps = pl.cps;
+    p.qstages = 2 * terms;
     p.q_resident = pl.q_resident;
     p.sub = pl.sub;
     p.nbuf = pl.nbuf;

@@ -25,6 +25,7 @@ struct SearchParams {
   int metric;
   int dtype;                         // element type of the 16-bit planes: RS_DTYPE_BF16 / RS_DTYPE_FP16
   int stages;                        // depth of the bulk-copy ring
+  int qstages;                       // streamed-Q mode: slots of the private Q ring (each cps k-chunks)
   int cps;                           // 64-element k-chunks per ring stage: 1 (16 KiB) or 2 (32 KiB)
   int q_resident;                    // 1: whole Q image resident in smem; 0: Q k-chunks stream through the ring
   int sub;                           // 128-document tiles per supertile (share one Q k-chunk load)
@@ -51,7 +52,7 @@ struct MergeXchg {
 cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dtype, int terms, int corpus_scale_exp,
                               uint8_t* qimg, float* qnorm, float* qscale, cudaStream_t stream);
 cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t stream);
-int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident);
+int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages);
 int fused_reg_k();
 cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int kc, int k,
                              long long idx_offset, float* out_score, long long* out_idx, const MergeXchg* xc,

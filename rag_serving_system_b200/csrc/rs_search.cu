@@ -127,9 +127,11 @@ struct SmemMap {
 // q_resident: the whole Q image lives in shared memory for the kernel's lifetime (small batches);
 // otherwise Q k-chunks travel through the ring next to the document blocks (large batches).
 __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, int stages, int cps, int k,
-                                                 bool reglist, bool q_resident) {
+                                                 bool reglist, bool q_resident, int qstages) {
   SmemMap m;
-  m.q_bytes = q_resident ? (uint32_t)terms * kc * bpad * RS_KCHUNK_BYTES : 0u;
+  // resident: the whole Q image; streamed: a private ring of qstages slots of cps k-chunks each
+  m.q_bytes = q_resident ? (uint32_t)terms * kc * bpad * RS_KCHUNK_BYTES
+                         : (uint32_t)qstages * cps * bpad * RS_KCHUNK_BYTES;
   m.stage_off = m.q_bytes;  // multiple of 1024 because bpad % 8 == 0
   m.bar_off = m.stage_off + (uint32_t)stages * (uint32_t)cps * RS_BLOCK_BYTES;
   m.dump_off = m.bar_off + 1024;                       // per epilogue warp: one 32x32 fp32 chunk
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr bool q_resident = QRES;
-  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, q_resident);
+  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, q_resident, p.qstages);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t q_smem = smem_base;
   const uint32_t stage_smem = smem_base + map.stage_off;
@@ -251,6 +253,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
   const uint32_t qfull_bar = bar_base + 8u * (2 * p.stages + 4);
+  auto qring_full = [&](int s) { return bar_base + 8u * (2 * p.stages + 5 + s); };              // streamed Q ring
+  auto qring_empty = [&](int s) { return bar_base + 8u * (2 * p.stages + 5 + p.qstages + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + map.bar_off + 1016);
 
   // M=128: query row r lives in TMEM lane r.  M=64 (half the tensor work, used when bpad <= 64):
@@ -273,6 +277,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       mbar_init(tempty_bar(a), nact_warps);
     }
     mbar_init(qfull_bar, 1);
+    if (!q_resident)
+      for (int s = 0; s < p.qstages; ++s) {
+        mbar_init(qring_full(s), 1);
+        mbar_init(qring_empty(s), 1);
+      }
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -317,12 +326,25 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
         ph ^= 1u;
       }
     };
+    int qs = 0;
+    uint32_t qph = 0;
+    auto push_q = [&](const void* src, uint32_t bytes) {
+      mbar_wait(qring_empty(qs), qph ^ 1u);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(qring_full(qs), bytes);
+        bulk_g2s(q_smem + (uint32_t)qs * (uint32_t)cps * qblk, src, bytes, qring_full(qs), pol_keep);
+      }
+      if (++qs == p.qstages) {
+        qs = 0;
+        qph ^= 1u;
+      }
+    };
     for (int u = blockIdx.x; u < n_super; u += gridDim.x) {
       const int nsub = min(S, p.n_tiles - u * S);
       const uint8_t* src = p.corpus + (size_t)u * S * tile_bytes;
       for (int kc = 0; kc < p.kc; kc += cps) {
         if (!q_resident)
-          for (int j = 0; j < p.terms; ++j) push(p.qimg + (size_t)(j * p.kc + kc) * qblk, cps * qblk, pol_keep);
+          for (int j = 0; j < p.terms; ++j) push_q(p.qimg + (size_t)(j * p.kc + kc) * qblk, cps * qblk);
         for (int pl = 0; pl < p.planes; ++pl)
           for (int sub = 0; sub < nsub; ++sub)
             push(src + (size_t)sub * tile_bytes + (size_t)(pl * p.kc + kc) * RS_BLOCK_BYTES, stage_bytes, pol_stream);
@@ -336,6 +358,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
     uint32_t ph = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
+    int qs = 0;
+    uint32_t qph = 0;
     const bool skip_mma = (p.debug_flags & 1) != 0;  // timing experiment only
     // 16-byte units: one UMMA K step (16 elements x 2 B) advances the start address by 2
     auto issue = [&](uint32_t d, uint32_t a_smem, uint32_t b_smem, bool fresh) {
@@ -358,20 +382,20 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
           qa0 = q_smem + (uint32_t)kc * qblk;
           qa1 = q_smem + (uint32_t)(p.kc + kc) * qblk;
         } else {
-          mbar_wait(full_bar(s), ph);
-          qa0 = stage_smem + (uint32_t)s * stage_bytes;
-          qslot0 = s;
-          if (++s == p.stages) {
-            s = 0;
-            ph ^= 1u;
+          mbar_wait(qring_full(qs), qph);
+          qa0 = q_smem + (uint32_t)qs * (uint32_t)cps * qblk;
+          qslot0 = qs;
+          if (++qs == p.qstages) {
+            qs = 0;
+            qph ^= 1u;
           }
           if (p.terms == 2) {
-            mbar_wait(full_bar(s), ph);
-            qa1 = stage_smem + (uint32_t)s * stage_bytes;
-            qslot1 = s;
-            if (++s == p.stages) {
-              s = 0;
-              ph ^= 1u;
+            mbar_wait(qring_full(qs), qph);
+            qa1 = q_smem + (uint32_t)qs * (uint32_t)cps * qblk;
+            qslot1 = qs;
+            if (++qs == p.qstages) {
+              qs = 0;
+              qph ^= 1u;
             }
           }
         }
@@ -401,8 +425,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
           }
         }
         if (!q_resident && lane == 0) {  // Q chunk(s) fully consumed by this k-chunk group
-          umma_commit(empty_bar(qslot0));
-          if (p.terms == 2) umma_commit(empty_bar(qslot1));
+          umma_commit(qring_empty(qslot0));
+          if (p.terms == 2) umma_commit(qring_empty(qslot1));
         }
       }
       __syncwarp();
@@ -794,7 +818,7 @@ cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dt
 
 template <int NACC, bool REGLIST, bool QRES>
 static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t stream) {
-  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, QRES);
+  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, QRES, p.qstages);
   auto kern = fused_search_kernel<NACC, REGLIST, QRES>;
   const int bytes = (int)map.total + 1024;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -803,8 +827,8 @@ static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t 
   return cudaGetLastError();
 }
 
-int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident) {
-  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0).total + 1024;
+int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages) {
+  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages).total + 1024;
 }
 int fused_reg_k() { return kRegK; }
 
