@@ -20,7 +20,7 @@ EXPORTS = (
     "rs_version", "rs_last_error", "rs_create", "rs_destroy", "rs_load_rows", "rs_fill_synthetic",
     "rs_finalize", "rs_search", "rs_search_device", "rs_merge_device", "rs_get_rows",
     "rs_get_norms", "rs_get_image", "rs_get_stats", "rs_get_kernel_times",
-    "rs_xchg_create", "rs_xchg_export", "rs_xchg_import", "rs_xchg_destroy", "rs_search_exchange",
+    "rs_debug_plan", "rs_xchg_create", "rs_xchg_export", "rs_xchg_import", "rs_xchg_destroy", "rs_search_exchange",
 )
 
 
@@ -79,6 +79,7 @@ def load() -> C.CDLL:
         "rs_search_device": [vp, vp, i32, i32, i32, i32, vp, vp, vp],
         "rs_merge_device": [i32, vp, vp, i32, i32, i32, i32, i64, i64, vp, vp, vp],
         "rs_get_kernel_times": [vp, vp, i32],
+        "rs_debug_plan": [i32, i32, i32, i32, i32, vp],
         "rs_xchg_create": [i32, i32, i32, i32, i32, C.POINTER(vp)],
         "rs_xchg_export": [vp, vp],
         "rs_xchg_import": [vp, i32, vp],
@@ -216,6 +217,13 @@ class Exchange:
             self.h = None
 
     __del__ = close
+
+
+def debug_plan(dim: int, dtype: str, B: int, k: int, query_terms: int = 1) -> dict:
+    out = (C.c_int32 * 9)()
+    check(load().rs_debug_plan(dim, DTYPES[dtype], B, k, query_terms, out), "rs_debug_plan")
+    keys = ("passes", "per_pass", "bpad", "stages", "q_resident", "sub", "nbuf", "mma_m", "cps")
+    return dict(zip(keys, list(out)))
 
 
 def merge_device(device: int, scores_ptr: int, idx_ptr: int, n_lists: int, B: int, kc: int, k: int,

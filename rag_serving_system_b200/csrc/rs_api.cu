@@ -116,74 +116,54 @@ int max_cap_rows(int kc, int terms, int k, int min_stages, int cps, int q_reside
 }
 
 // Small batches keep the query operand resident in shared memory (one tile per accumulator,
-// double-buffered TMEM).  Larger batches stream Q k-chunks through the ring and amortise each
-// chunk over `sub` document tiles that accumulate side by side in TMEM.
+// double-buffered TMEM).  Larger batches stream Q k-chunks through a private ring and amortise each
+// chunk over `sub` document tiles that accumulate side by side in TMEM.  Measured on B200: what
+// limits the stream is the number of barrier round trips per byte, so the planner prefers, in
+// order: fewest passes, resident Q, the largest ring stage (cps k-chunks of 16 KiB), the largest sub.
 int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
   const int nacc = (terms == 2 || ix->planes == 2) ? 2 : 1;
-  // two k-chunks (32 KiB) per ring stage halve the barrier round trips per byte
-  int cps = env_int("RS_CPS", ix->kc % 2 == 0 ? 2 : 1);
-  if ((cps != 1 && cps != 2 && cps != 4) || ix->kc % cps != 0) return fail(RS_E_INVALID, "RS_CPS=%d invalid for dim=%d", cps, ix->cfg.dim);
-  int kMinResidentStages = cps == 4 ? 2 : (cps == 2 ? 3 : 6);
-  int cap_res = max_cap_rows(ix->kc, terms, k, kMinResidentStages, cps, 1);
-  if (B > cap_res && cps >= 2 && B <= max_cap_rows(ix->kc, terms, k, 6, 1, 1)) {
-    cps = 1;  // the batch still fits next to a ring of six 16 KiB stages
-    kMinResidentStages = 6;
-    cap_res = max_cap_rows(ix->kc, terms, k, 6, 1, 1);
-  }
-  pl->cps = cps;
-  int resident = B <= cap_res ? 1 : 0;
-  resident = env_int("RS_QRESIDENT", resident);
-  int min_stages = kMinResidentStages;
-  int cap = cap_res;
-  if (resident) {
-    pl->sub = 1;
-    pl->nbuf = 2;
-  } else {
-    // one k-chunk group (terms Q items + planes*sub document items) must fit in the ring with a
-    // slot to spare; prefer the fewest passes, then the largest sub (least Q re-reading)
-    int best_passes = 1 << 30, best_sub = 0;
-    const int cps_hi = cps;
-    for (int c2 = cps_hi; c2 >= 1; --c2) {
-      for (int sub = (nacc == 1 ? 4 : 2); sub >= 1; sub >>= 1) {
-        const int need = ix->planes * sub + 1;   // one k-chunk group of document blocks + 1 (Q has its own ring)
-        const int c = max_cap_rows(ix->kc, terms, k, need, c2, 0);
-        if (c <= 0) continue;
-        const int passes = (B + c - 1) / c;
-        if (passes < best_passes || (passes == best_passes && sub > best_sub)) {
-          best_passes = passes;
-          best_sub = sub;
+  const int force_res = env_int("RS_QRESIDENT", -1), force_cps = env_int("RS_CPS", 0), force_sub = env_int("RS_SUB", 0);
+  long long best_cost = -1;
+  for (int resident = 1; resident >= 0; --resident) {
+    if (force_res >= 0 && resident != force_res) continue;
+    for (int cps = 4; cps >= 1; cps >>= 1) {
+      if (ix->kc % cps != 0 || (force_cps && cps != force_cps)) continue;
+      if (!resident && cps == 4) continue;
+      for (int sub = resident ? (force_sub ? force_sub : 1) : (nacc == 1 ? 4 : 2); sub >= 1; sub >>= 1) {
+        if (force_sub && sub != force_sub) continue;
+        // ring depth: at least 64 KiB in flight, and in streamed mode one whole k-chunk group + 1
+        int need = std::max(2, (4 + cps - 1) / cps);
+        if (!resident) need = std::max(need, ix->planes * sub + 1);
+        const int cap = max_cap_rows(ix->kc, terms, k, need, cps, resident);
+        if (cap <= 0) continue;
+        const int passes = (B + cap - 1) / cap;
+        const long long cost = ((long long)passes << 32) | ((long long)(1 - resident) << 24) | ((long long)(4 - cps) << 16) |
+                               (long long)(8 - sub);
+        if (best_cost < 0 || cost < best_cost) {
+          best_cost = cost;
+          pl->q_resident = resident;
+          pl->cps = cps;
           pl->sub = sub;
-          pl->cps = cps = c2;
-          cap = c;
-          min_stages = need;
+          pl->passes = passes;
+          pl->stages = need;
         }
       }
     }
-    if (best_passes == (1 << 30)) cap = 0;
-    pl->nbuf = pl->sub * nacc <= 2 ? 2 : 1;  // double-buffer the accumulators whenever TMEM has room
   }
-  if (cap <= 0) return fail(RS_E_UNSUPPORTED, "k=%d with dim=%d does not fit in shared memory", k, ix->cfg.dim);
-  pl->q_resident = resident;
-  pl->passes = (B + cap - 1) / cap;
+  if (best_cost < 0) return fail(RS_E_UNSUPPORTED, "B=%d k=%d dim=%d does not fit in shared memory", B, k, ix->cfg.dim);
   pl->per_pass = (B + pl->passes - 1) / pl->passes;
   pl->bpad = (pl->per_pass + 7) / 8 * 8;
   pl->mma_m = env_int("RS_MMA_M", pl->bpad <= 64 ? 64 : 128);
   if (pl->mma_m != 128 && !(pl->mma_m == 64 && pl->bpad <= 64)) return fail(RS_E_INVALID, "RS_MMA_M=%d invalid for bpad=%d", pl->mma_m, pl->bpad);
-  if (getenv("RS_SUB")) {
-    pl->sub = env_int("RS_SUB", pl->sub);
-    min_stages = resident ? kMinResidentStages : ix->planes * pl->sub + 1;
-  }
-  pl->nbuf = env_int("RS_NBUF", pl->nbuf);
+  pl->nbuf = env_int("RS_NBUF", pl->sub * nacc <= 2 ? 2 : 1);  // double-buffer the accumulators whenever TMEM has room
   const int cols = pl->sub * pl->nbuf * nacc;
-  if (pl->sub < 1 || pl->nbuf < 1 || pl->nbuf > 2 || (cols != 1 && cols != 2 && cols != 4))
+  if (pl->nbuf < 1 || pl->nbuf > 2 || (cols != 1 && cols != 2 && cols != 4))
     return fail(RS_E_INVALID, "sub=%d nbuf=%d nacc=%d does not map onto 128/256/512 TMEM columns", pl->sub, pl->nbuf, nacc);
-  int stages = min_stages;
-  while (stages < kMaxStages &&
-         rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages + 1, cps, k, resident, 2 * terms) <= kMaxSmem)
-    ++stages;
-  if (rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages, cps, k, resident, 2 * terms) > kMaxSmem)
+  while (pl->stages < kMaxStages && rs::fused_smem_bytes(pl->bpad, ix->kc, terms, pl->stages + 1, pl->cps, k,
+                                                         pl->q_resident, 2 * terms) <= kMaxSmem)
+    ++pl->stages;
+  if (rs::fused_smem_bytes(pl->bpad, ix->kc, terms, pl->stages, pl->cps, k, pl->q_resident, 2 * terms) > kMaxSmem)
     return fail(RS_E_UNSUPPORTED, "B=%d k=%d does not fit in shared memory", B, k);
-  pl->stages = stages;
   return RS_OK;
 }
 
@@ -650,6 +630,22 @@ RS_API int rs_get_kernel_times(rs_index* ix, float* out_ms, int32_t n) {
     RS_CUDA(cudaEventSynchronize(ix->ev_end[slot]));
     RS_CUDA(cudaEventElapsedTime(&out_ms[i], ix->ev_beg[slot], ix->ev_end[slot]));
   }
+  return RS_OK;
+}
+
+RS_API int rs_debug_plan(int32_t dim, int32_t dtype, int32_t B, int32_t k, int32_t query_terms, int32_t* out9) {
+  if (!out9 || dim <= 0 || dim % 64 != 0) return fail(RS_E_INVALID, "bad argument");
+  rs_index tmp;
+  memset(&tmp.cfg, 0, sizeof(tmp.cfg));
+  tmp.cfg.dim = dim;
+  tmp.kc = dim / RS_KCHUNK_ELEMS;
+  tmp.planes = dtype == RS_DTYPE_FP32 ? 2 : 1;
+  if (tmp.planes == 2) query_terms = 2;
+  Plan pl;
+  int rc = make_plan(&tmp, B, k, query_terms, &pl);
+  if (rc != RS_OK) return rc;
+  const int v[9] = {pl.passes, pl.per_pass, pl.bpad, pl.stages, pl.q_resident, pl.sub, pl.nbuf, pl.mma_m, pl.cps};
+  memcpy(out9, v, sizeof(v));
   return RS_OK;
 }
 

@@ -134,8 +134,8 @@ __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, in
                          : (uint32_t)qstages * cps * bpad * RS_KCHUNK_BYTES;
   m.stage_off = m.q_bytes;  // multiple of 1024 because bpad % 8 == 0
   m.bar_off = m.stage_off + (uint32_t)stages * (uint32_t)cps * RS_BLOCK_BYTES;
-  m.dump_off = m.bar_off + 1024;                       // per epilogue warp: one 32x32 fp32 chunk
-  m.list_off = m.dump_off + kNumEpiWarps * 4096;
+  m.dump_off = m.bar_off + 1024;                       // rare-path chunk dump: 32 columns x live rows, fp32
+  m.list_off = m.dump_off + (uint32_t)((bpad + 15) / 16 * 16) * 128u;
   m.total = m.list_off + (reglist ? 0u : (uint32_t)(k + kBufC) * (uint32_t)bpad * 8u);
   return m;
 }
@@ -460,7 +460,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       float* Bs = reinterpret_cast<float*>(Li + (size_t)k * lstride);
       int* Bi = reinterpret_cast<int*>(Bs + (size_t)kBufC * lstride);
       int cnt = 0;
-      float* dump = reinterpret_cast<float*>(smem + map.dump_off) + (size_t)quarter * 1024;  // 32 x 32 floats per warp
+      // per warp: [32 columns][rows_per_warp lanes] floats
+      float* dump = reinterpret_cast<float*>(smem + map.dump_off) + (size_t)quarter * 32 * rows_per_warp;
       if (REGLIST) {
 #pragma unroll
         for (int j = 0; j < kRegK; ++j) {
@@ -524,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 pm |= (v[j] > thr_raw) ? (1u << j) : 0u;
-                dump[j * 32 + lane] = v[j];
+                if (lane < rows_per_warp) dump[j * rows_per_warp + lane] = v[j];
               }
               if (tile_row0 + c0 + 32 > p.n_rows) {  // ragged last tile: mask padded rows
                 const int valid = p.n_rows - (tile_row0 + c0);
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
                 if (pm != 0u) {
                   const int j = __ffs(pm) - 1;
                   pm &= pm - 1;
-                  const float s = dump[j * 32 + lane];
+                  const float s = dump[j * rows_per_warp + lane];
                   const int idx = tile_row0 + c0 + j;
                   float x = s;  // dot metric: compare and store raw units (exact power-of-two scale)
                   if (cosine) {

@@ -13,14 +13,17 @@ g = torch.Generator().manual_seed(0)
 q = torch.randn(256, 1024, generator=g); q = (q / q.norm(dim=1, keepdim=True)).bfloat16().float().cuda()
 out = []
 for rep in range(2):
-    for env in ({"RS_CPS": 2}, {"RS_CPS": 4}):
+    for env in ({}, {"RS_CPS": 2}):
         run(ix, q, 32, 10, "dot", 1, steps, env, "B32", out)
-run(ix, q, 16, 10, "dot", 1, steps, {"RS_CPS": 4}, "B16", out)
-run(ix, q, 16, 10, "dot", 1, steps, {"RS_CPS": 2}, "B16", out)
-for B in (64, 128):
-    for env in ({}, {"RS_SUB": 2, "RS_NBUF": 2}, {"RS_SUB": 4, "RS_NBUF": 1}, {"RS_SUB": 2, "RS_NBUF": 1, "RS_CPS": 1}):
-        run(ix, q, B, 10, "dot", 1, steps, env, f"B{B}", out)
+for B in (1, 16):
+    run(ix, q, B, 10, "dot", 1, steps, {}, f"B{B}", out)
+for env in ({}, {"RS_QRESIDENT": 0}, {"RS_QRESIDENT": 0, "RS_SUB": 2}):
+    run(ix, q, 64, 10, "dot", 1, steps, env, "B64", out)
+for env in ({}, {"RS_SUB": 4}, {"RS_SUB": 1}, {"RS_CPS": 1, "RS_SUB": 4}):
+    run(ix, q, 128, 10, "dot", 1, steps, env, "B128", out)
 run(ix, q, 32, 10, "dot", 2, steps, {}, "B32 terms2", out)
+run(ix, q, 32, 10, "dot", 2, steps, {"RS_QRESIDENT": 0}, "B32 terms2", out)
 run(ix, q, 32, 10, "cosine", 1, steps, {}, "B32 cosine", out)
 run(ix, q, 32, 100, "dot", 1, steps // 2, {}, "B32 k100", out)
 run(ix, q, 128, 100, "dot", 1, steps // 2, {}, "B128 k100", out)
+run(ix, q, 256, 10, "dot", 1, steps // 2, {}, "B256", out)
