@@ -135,7 +135,7 @@ __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, in
   m.stage_off = m.q_bytes;  // multiple of 1024 because bpad % 8 == 0
   m.bar_off = m.stage_off + (uint32_t)stages * (uint32_t)cps * RS_BLOCK_BYTES;
   m.dump_off = m.bar_off + 1024;                       // rare-path chunk dump: 32 columns x live rows, fp32
-  m.list_off = m.dump_off + (uint32_t)((bpad + 15) / 16 * 16) * 128u;
+  m.list_off = m.dump_off + (uint32_t)((bpad + 31) / 32 * 32) * 128u;   // whole warps of 32 (M=128) or 2x16 (M=64) rows
   m.total = m.list_off + (reglist ? 0u : (uint32_t)(k + kBufC) * (uint32_t)bpad * 8u);
   return m;
 }
