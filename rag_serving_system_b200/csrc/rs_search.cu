@@ -659,8 +659,10 @@ __device__ __forceinline__ void st_volatile_u32(unsigned int* p, unsigned int v)
 // GPU of the box, reached through peer pointers - and the last warp to finish raises this
 // rank's flag on every peer.  That makes "local merge + candidate exchange" ONE kernel whose
 // stores travel over NVLink while other queries are still being merged.
+constexpr int kMergeThreads = 128;  // four warps stage one query's candidates; warp 0 runs the k rounds
+
 template <typename IdxT, bool STAGED>
-__global__ void __launch_bounds__(32) merge_topk_kernel(const float* __restrict__ cand_score,
+__global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const float* __restrict__ cand_score,
                                                         const IdxT* __restrict__ cand_idx, int n_lists,
                                                         int n_queries, int kc, int k, long long idx_offset,
                                                         long long score_list_stride, long long idx_list_stride,
@@ -668,7 +670,7 @@ __global__ void __launch_bounds__(32) merge_topk_kernel(const float* __restrict_
                                                         long long* __restrict__ out_idx, const MergeXchg x) {
   extern __shared__ __align__(16) uint8_t merge_smem[];
   const int q = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const int total = n_lists * kc;
   long long* res_i = reinterpret_cast<long long*>(merge_smem);
   float* res_s = reinterpret_cast<float*>(res_i + k);
@@ -676,24 +678,24 @@ __global__ void __launch_bounds__(32) merge_topk_kernel(const float* __restrict_
   IdxT* s_idx = reinterpret_cast<IdxT*>(stage);
   float* s_score = reinterpret_cast<float*>(stage + (size_t)total * sizeof(IdxT));
   if (x.n_wait > 0) {
-    if (lane < x.n_wait) {
+    if (threadIdx.x < x.n_wait) {
       long long spins = 0;
-      while ((int)(ld_volatile_u32(x.wait_flags + lane) - x.epoch) < 0 && ++spins < (1ll << 28)) {
+      while ((int)(ld_volatile_u32(x.wait_flags + threadIdx.x) - x.epoch) < 0 && ++spins < (1ll << 28)) {
       }
     }
     __threadfence_system();
-    __syncwarp();
+    __syncthreads();
   }
   const size_t qoff = (size_t)q * query_stride;
   if (STAGED) {
     // element (list l, slot j) of this query sits at l*list_stride + q*query_stride + j; issue the
     // loads four deep so the L2 round trips overlap
-    for (int e0 = lane; e0 < total; e0 += 128) {
+    for (int e0 = threadIdx.x; e0 < total; e0 += 4 * kMergeThreads) {
       IdxT ti[4];
       float ts[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int e = e0 + 32 * u;
+        const int e = e0 + kMergeThreads * u;
         if (e < total) {
           const int l = e / kc, j = e - l * kc;
           ti[u] = __ldcg(cand_idx + (size_t)l * idx_list_stride + qoff + j);
@@ -702,15 +704,16 @@ __global__ void __launch_bounds__(32) merge_topk_kernel(const float* __restrict_
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int e = e0 + 32 * u;
+        const int e = e0 + kMergeThreads * u;
         if (e < total) {
           s_idx[e] = ti[u];
           s_score[e] = ts[u];
         }
       }
     }
-    __syncwarp();
+    __syncthreads();
   }
+  if (threadIdx.x >= 32) return;  // the selection rounds are a single-warp job
   auto load = [&](int l, int j, float& s, long long& id) {
     if (STAGED) {
       s = s_score[l * kc + j];
@@ -864,10 +867,10 @@ static cudaError_t launch_merge_t(const float* cand_score, const IdxT* cand_idx,
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
       if (e != cudaSuccess) return e;
     }
-    kern<<<n_queries, 32, bytes, stream>>>(cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset,
+    kern<<<n_queries, kMergeThreads, bytes, stream>>>(cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset,
                                            score_list_stride, idx_list_stride, query_stride, out_score, out_idx, x);
   } else {
-    merge_topk_kernel<IdxT, false><<<n_queries, 32, res_bytes, stream>>>(
+    merge_topk_kernel<IdxT, false><<<n_queries, kMergeThreads, res_bytes, stream>>>(
         cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, score_list_stride, idx_list_stride, query_stride,
         out_score, out_idx, x);
   }
