@@ -723,63 +723,66 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const float* 
       s = __ldcg(cand_score + (size_t)l * score_list_stride + qoff + j);
     }
   };
+  // Every list head is kept as a sortable pair: ks = order-preserving image of the score (0 =
+  // padding / exhausted), ki = ~index (larger = lower index).  The warp's best head is found with
+  // three redux.sync steps (score, index high word, index low word) instead of shuffle trees.
+  unsigned int ks[kMergeMaxOwn];
+  unsigned long long ki[kMergeMaxOwn];
   int head[kMergeMaxOwn];
-#pragma unroll
-  for (int i = 0; i < kMergeMaxOwn; ++i) head[i] = 0;
-  float bs = -CUDART_INF_F;
-  long long bi = -1;
-  int bown = -1;
-  auto rescan = [&]() {  // best head among the lists this lane owns
-    bs = -CUDART_INF_F;
-    bi = -1;
-    bown = -1;
-#pragma unroll
-    for (int i = 0; i < kMergeMaxOwn; ++i) {
-      const int l = lane + 32 * i;
-      if (l < n_lists && head[i] < kc) {
-        float s;
-        long long id;
-        load(l, head[i], s, id);
-        if (id >= 0 && (bi < 0 || s > bs || (s == bs && id < bi))) {
-          bs = s;
-          bi = id;
-          bown = i;
-        }
+  auto read_head = [&](int i) {
+    const int l = lane + 32 * i;
+    ks[i] = 0u;
+    ki[i] = 0ull;
+    if (l < n_lists && head[i] < kc) {
+      float sc;
+      long long id;
+      load(l, head[i], sc, id);
+      if (id >= 0) {
+        unsigned int u = __float_as_uint(sc);
+        ks[i] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        ki[i] = ~(unsigned long long)id;
       }
     }
   };
-  rescan();
+#pragma unroll
+  for (int i = 0; i < kMergeMaxOwn; ++i) {
+    head[i] = 0;
+    read_head(i);
+  }
   int r = 0;
   for (; r < k; ++r) {
-    // warp arg-best on (score desc, idx asc); padding (index < 0) always loses
-    float ws = bs;
-    long long wi = bi;
-    int wl = lane;
+    unsigned int bs = 0u;  // this lane's best head
+    unsigned long long bi = 0ull;
+    int bown = 0;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, ws, off);
-      const long long oi = __shfl_xor_sync(0xffffffffu, wi, off);
-      const int ol = __shfl_xor_sync(0xffffffffu, wl, off);
-      const bool take = (oi >= 0) && (wi < 0 || os > ws || (os == ws && oi < wi));
-      if (take) {
-        ws = os;
-        wi = oi;
-        wl = ol;
+    for (int i = 0; i < kMergeMaxOwn; ++i)
+      if (ks[i] > bs || (ks[i] == bs && ki[i] > bi)) {
+        bs = ks[i];
+        bi = ki[i];
+        bown = i;
       }
-    }
-    if (wi < 0) break;  // every list exhausted: the rest is padding
-    if (lane == 0) {
-      res_s[r] = ws;
-      res_i[r] = wi + idx_offset;
-    }
-    if (lane == wl) {  // only the winning lane's state changed
+    const unsigned int m0 = __reduce_max_sync(0xffffffffu, bs);
+    if (m0 == 0u) break;  // every list exhausted: the rest is padding
+    bool mine = bs == m0;
+    const unsigned int m1 = __reduce_max_sync(0xffffffffu, mine ? (unsigned int)(bi >> 32) : 0u);
+    mine = mine && (unsigned int)(bi >> 32) == m1;
+    const unsigned int m2 = __reduce_max_sync(0xffffffffu, mine ? (unsigned int)bi : 0u);
+    mine = mine && (unsigned int)bi == m2;
+    if (mine) {  // exactly one lane when indices are unique
+      float sc;
+      long long id;
+      load(lane + 32 * bown, head[bown], sc, id);
+      res_s[r] = sc;
+      res_i[r] = id + idx_offset;
 #pragma unroll
       for (int i = 0; i < kMergeMaxOwn; ++i)
-        if (i == bown) ++head[i];
-      rescan();
+        if (i == bown) {
+          ++head[i];
+          read_head(i);
+        }
     }
-    __syncwarp();
   }
+  __syncwarp();
   for (int rr = r + lane; rr < k; rr += 32) {
     res_s[rr] = -CUDART_INF_F;
     res_i[rr] = -1;
