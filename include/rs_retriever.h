@@ -85,11 +85,14 @@ RS_API const char* rs_last_error(void);
 RS_API int rs_create(const rs_config* cfg, rs_index** out);
 RS_API int rs_destroy(rs_index* ix);
 
-/* Replaces cp.asarray(doc_embeddings) (retriever.py:582): chunked ingest of host rows
+/* Replaces cp.asarray(doc_embeddings) (retriever.py:582): chunked ingest of rows
  * [row0, row0+nrows) (local numbering), row-major, src_dtype = RS_DTYPE_FP32 (float) or
  * RS_DTYPE_BF16 / RS_DTYPE_FP16 (uint16 bit patterns).  Converts to the storage dtype, writes
  * the tiled image and the document norms (computed ONCE here; the reference recomputes them on
- * every call, retriever.py:603). */
+ * every call, retriever.py:603).  `host_rows` may be pageable host memory (e.g. an np.memmap
+ * slice; bounced through double-buffered pinned staging so the host copy of one chunk overlaps
+ * the DMA and tiling of the previous one), pinned host memory (DMA straight from it) or DEVICE
+ * memory (tiled in place, no copy) - detected with cudaPointerGetAttributes. */
 RS_API int rs_load_rows(rs_index* ix, const void* host_rows, int32_t src_dtype, int64_t row0, int64_t nrows);
 
 /* Fill the shard with the synthetic unit-normalised corpus (oracle: retrieval_oracle.synth_rows);

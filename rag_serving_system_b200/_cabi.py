@@ -133,10 +133,16 @@ class Index:
                 src_dtype = "fp32"
             elif rows.dtype == np.float16:
                 src_dtype = "fp16"
+            elif rows.dtype.itemsize == 2 and rows.dtype.kind == "V":
+                src_dtype = "bf16"          # ml_dtypes' bfloat16 round-trips through .npy as '<V2'
             else:
                 raise RsError(f"load_rows: pass float32/float16 rows or uint16 bits with src_dtype (got {rows.dtype})")
         assert rows.ndim == 2 and rows.shape[1] == self.dim
         check(self.lib.rs_load_rows(self.h, rows.ctypes.data, DTYPES[src_dtype], row0, rows.shape[0]), "rs_load_rows")
+
+    def load_rows_ptr(self, ptr: int, nrows: int, src_dtype: str, row0: int = 0):
+        """Rows behind a raw pointer: pageable / pinned host memory or DEVICE memory (tiled in place)."""
+        check(self.lib.rs_load_rows(self.h, ptr, DTYPES[src_dtype], row0, nrows), "rs_load_rows")
 
     def fill_synthetic(self, seed: int, global_row0: int | None = None):
         g0 = self.row_offset if global_row0 is None else global_row0

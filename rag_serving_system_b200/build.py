@@ -20,7 +20,7 @@ HEADERS = ["rs_kernels.h", "rs_layout.h", "rs_ptx.cuh", os.path.join("..", "..",
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # plain sm_100 rejects tcgen05.*
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-pthread",
     "-shared",
 ]
 

@@ -22,6 +22,7 @@ import json
 import logging
 import math
 import threading
+from operator import itemgetter
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -63,25 +64,28 @@ class B200Retriever:
 
     def __init__(self, doc_embeddings: np.ndarray, documents: Sequence[str], *, dtype: str = "fp32",
                  metric: str = "cosine", devices: Optional[Sequence[int]] = None, max_batch: int = 256,
-                 max_k: int = 128, query_terms: Optional[int] = None):
+                 max_k: int = 128, query_terms: Optional[int] = None, source_dtype: Optional[str] = None):
         if not isinstance(doc_embeddings, np.ndarray) or doc_embeddings.ndim != 2:
             raise ValueError("doc_embeddings must be a 2-D numpy array")
         if dtype not in _cabi.DTYPES or metric not in _cabi.METRICS:
             raise ValueError(f"dtype in {list(_cabi.DTYPES)}, metric in {list(_cabi.METRICS)}")
-        if doc_embeddings.dtype not in (np.float32, np.float16):     # retriever.py:576-578
+        src_dtype = _source_dtype(doc_embeddings.dtype, source_dtype)
+        if src_dtype is None:                                         # retriever.py:576-578
             doc_embeddings = doc_embeddings.astype(np.float32)
+            src_dtype = "fp32"
         self._setup(doc_embeddings.shape[0], doc_embeddings.shape[1], documents, dtype, metric, devices,
                     max_batch, max_k, query_terms)
         scale_exp = 0
         if dtype == "fp32":
-            scale_exp = _fp32_scale_exp(float(np.abs(doc_embeddings).max()) if doc_embeddings.size else 0.0)
+            scale_exp = _fp32_scale_exp(_max_abs_chunked(doc_embeddings, src_dtype))
         self._create_shards(scale_exp)
         try:
             for ix in self._shards:                                   # retriever.py:582 (H2D of the corpus)
                 lo = ix.row_offset
+                # chunk by chunk: works for np.memmap inputs far larger than host RAM
                 for r in range(0, ix.n_rows, _INGEST_ROWS):
                     n = min(_INGEST_ROWS, ix.n_rows - r)
-                    ix.load_rows(doc_embeddings[lo + r: lo + r + n], r)
+                    ix.load_rows(np.ascontiguousarray(doc_embeddings[lo + r: lo + r + n]), r, src_dtype)
                 ix.finalize()
         except Exception:
             log.error("Failed to move document embeddings to the device", exc_info=True)   # retriever.py:584-586
@@ -93,10 +97,31 @@ class B200Retriever:
     # ------------------------------------------------------------------ alternative constructors
     @classmethod
     def from_npy(cls, embeddings_path: str, contexts_path: Optional[str] = None, **kw) -> "B200Retriever":
-        """main.py:20-23: a JSON list of strings + an .npy of embeddings (memory-mapped here)."""
+        """main.py:20-23: a JSON list of strings + an .npy of embeddings.  The array is memory-mapped
+        and ingested chunk by chunk (never materialised on the host).  fp32 / fp16 files load as
+        they are; bf16 has no NumPy dtype - ml_dtypes writes it as '<V2' and a uint16 file needs
+        ``source_dtype="bf16"``."""
         emb = np.load(embeddings_path, mmap_mode="r")
-        docs = json.load(open(contexts_path)) if contexts_path else [str(i) for i in range(emb.shape[0])]
-        return cls(np.asarray(emb), docs, **kw)
+        docs = json.load(open(contexts_path)) if contexts_path else _LazyDocs(emb.shape[0])
+        return cls(emb, docs, **kw)
+
+    @classmethod
+    def from_device_tensor(cls, emb, documents: Sequence[str], **kw) -> "B200Retriever":
+        """Corpus already on a GPU (a torch CUDA tensor, fp32 / fp16 / bf16, contiguous): tiled in
+        place by the ingest kernel, no host round trip.  Single device."""
+        import torch
+        assert emb.is_cuda and emb.dim() == 2 and emb.is_contiguous()
+        src = {torch.float32: "fp32", torch.float16: "fp16", torch.bfloat16: "bf16"}[emb.dtype]
+        self = cls.__new__(cls)
+        dtype = kw.pop("dtype", "bf16" if src == "bf16" else ("fp16" if src == "fp16" else "fp32"))
+        self._setup(emb.shape[0], emb.shape[1], documents, dtype, kw.pop("metric", "cosine"), [emb.device.index],
+                    kw.pop("max_batch", 256), kw.pop("max_k", 128), kw.pop("query_terms", None))
+        scale = _fp32_scale_exp(float(emb.abs().max())) if dtype == "fp32" else 0
+        self._create_shards(scale)
+        torch.cuda.synchronize(emb.device)
+        self._shards[0].load_rows_ptr(emb.data_ptr(), emb.shape[0], src)
+        self._shards[0].finalize()
+        return self
 
     @classmethod
     def from_synthetic(cls, n_rows: int, dim: int = 1024, seed: int = 1234, documents=None, **kw) -> "B200Retriever":
@@ -186,11 +211,36 @@ class B200Retriever:
                            os_.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
         return oi.cpu().numpy(), os_.cpu().numpy()
 
+    def search_tensor(self, queries, k: int, metric: Optional[str] = None, query_terms: Optional[int] = None):
+        """Zero-copy hand-off from the embedder: ``queries`` is a float32 CUDA tensor
+        [B, D] on the index's device; the search is enqueued on torch's current stream and the
+        results come back as CUDA tensors (indices int64[B,k], scores float32[B,k]) without any
+        host synchronisation.  batch_processor.py:91-92 could pass ``mean(dim=1)`` directly."""
+        import torch
+        if len(self._shards) != 1:
+            raise ValueError("search_tensor drives a single-device index; use sharded.ShardedSearcher across GPUs")
+        ix = self._shards[0]
+        q = queries
+        if q.dim() == 1:
+            q = q[None, :]
+        if not q.is_cuda or q.device.index != ix.device or q.shape[1] != self.D:
+            raise ValueError(f"queries must be a CUDA tensor [B, {self.D}] on cuda:{ix.device}")
+        q = q.contiguous().float()
+        B = q.shape[0]
+        if B > self._max_batch or k > self._max_k or k <= 0:
+            raise ValueError("B / k outside the limits given at construction")
+        terms = query_terms or self._query_terms or (2 if self._dtype == "fp32" else 1)
+        oi = torch.empty((B, k), dtype=torch.int64, device=q.device)
+        os_ = torch.empty((B, k), dtype=torch.float32, device=q.device)
+        with self._lock:
+            ix.search_device(q.data_ptr(), B, k, oi.data_ptr(), os_.data_ptr(), metric or self._metric, terms,
+                             torch.cuda.current_stream(q.device).cuda_stream)
+        return oi, os_
+
     def retrieve_with_scores(self, queries: np.ndarray, k: int):
         """north_star triple: (indices, scores, contexts)."""
         idx, sc = self.search(queries, k)
-        ctx = [[self.documents[j] for j in row if j >= 0] for row in idx]
-        return idx, sc, ctx
+        return idx, sc, [_gather(self.documents, row[row >= 0]) for row in idx]
 
     # ------------------------------------------------------------------ reference surface
     def retrieve(self, query_emb: np.ndarray, k: int = 2) -> List[str]:
@@ -213,7 +263,7 @@ class B200Retriever:
                 log.warning("Requested k=%s results in actual_k=%s. Returning empty list.", k, actual_k)
                 return []
             idx, _ = self.search(query_emb.reshape(1, self.D), actual_k)
-            return [self.documents[i] for i in idx[0] if i >= 0]          # :675
+            return _gather(self.documents, idx[0][idx[0] >= 0])           # :675
         except Exception as e:                                            # :681-683
             log.error("Error during retrieve: %s", e, exc_info=True)
             return []
@@ -259,7 +309,7 @@ class B200Retriever:
                     out.append([])
                     continue
                 row = idx[i]
-                out.append([docs[j] for j in row[row >= 0][:k_i]])
+                out.append(_gather(docs, row[row >= 0][:k_i]))
             return out
         except Exception as e:                                            # :796-799
             log.error("Error during batch_retrieve: %s", e, exc_info=True)
@@ -267,6 +317,46 @@ class B200Retriever:
 
     def stats(self) -> List[dict]:
         return [ix.stats() for ix in self._shards]
+
+
+def _gather(documents, idx) -> List[str]:
+    """documents[i] for i in idx (retriever.py:789).  ``itemgetter`` does the B*k lookups in C, which
+    matters at k=100, B=256 (25 600 per call); the result is a fresh list."""
+    n = len(idx)
+    if n == 0:
+        return []
+    if n == 1 or not isinstance(documents, list):
+        return [documents[int(i)] for i in idx]
+    return list(itemgetter(*idx.tolist())(documents))
+
+
+def _source_dtype(np_dtype, override: Optional[str]) -> Optional[str]:
+    """Source element type the ingest kernel can read directly, or None (convert to fp32 first)."""
+    if override is not None:
+        if override not in _cabi.DTYPES:
+            raise ValueError(f"source_dtype in {list(_cabi.DTYPES)}")
+        want = 4 if override == "fp32" else 2
+        if np_dtype.itemsize != want:
+            raise ValueError(f"source_dtype={override} needs {want}-byte elements, array has {np_dtype}")
+        return override
+    if np_dtype == np.float32:
+        return "fp32"
+    if np_dtype == np.float16:
+        return "fp16"
+    if np_dtype.kind == "V" and np_dtype.itemsize == 2:
+        return "bf16"
+    return None
+
+
+def _max_abs_chunked(emb: np.ndarray, src_dtype: str) -> float:
+    m = 0.0
+    for r in range(0, emb.shape[0], _INGEST_ROWS):
+        c = np.asarray(emb[r:r + _INGEST_ROWS])
+        if src_dtype == "bf16":
+            c = (c.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+        if c.size:
+            m = max(m, float(np.abs(c).max()))
+    return m
 
 
 class _LazyDocs:

@@ -88,6 +88,74 @@ def test_bf16_source_rows_load_bit_exact(squad):
         ix.close()
 
 
+def test_from_npy_memmap_sources(tmp_path, squad):
+    """.npy corpora are memory-mapped and ingested chunk by chunk; fp32 / fp16 files
+    load directly, bf16 arrives as a uint16 file (+ source_dtype) or as ml_dtypes' '<V2'."""
+    E, Q, k = squad.E, squad.Q, 10
+    np.save(tmp_path / "f32.npy", E)
+    np.save(tmp_path / "f16.npy", E.astype(np.float16))
+    np.save(tmp_path / "bf16_u16.npy", o.bf16_bits(E))
+    cases = [("f32.npy", {"dtype": "fp32"}, E), ("f16.npy", {"dtype": "fp16"}, E.astype(np.float16).astype(np.float32)),
+             ("bf16_u16.npy", {"dtype": "bf16", "source_dtype": "bf16"}, o.round_to_bf16(E))]
+    try:
+        import ml_dtypes
+        np.save(tmp_path / "bf16_v2.npy", E.astype(ml_dtypes.bfloat16))
+        cases.append(("bf16_v2.npy", {"dtype": "bf16"}, o.round_to_bf16(E)))
+    except ImportError:
+        pass
+    for name, kw, stored in cases:
+        r = B200Retriever.from_npy(str(tmp_path / name), metric="dot", **kw)
+        assert r.N_A == len(E) and r.documents[3] == "doc-3"
+        idx, sc = r.search(Q, k)
+        S = o.scores_dot(Q.astype(np.float64), stored.astype(np.float64), np.float64)
+        o.check_topk(idx, sc, S, k, rtol=RTOL[kw["dtype"]], atol=1e-6)
+        r.close()
+
+
+def test_device_tensor_corpus_and_query_handoff(squad):
+    """corpus and queries that already live on the GPU never touch the host."""
+    import torch
+    E, Q, k = squad.E, squad.Q, 10
+    for tdt, name in ((torch.float32, "fp32"), (torch.bfloat16, "bf16"), (torch.float16, "fp16")):
+        emb = torch.from_numpy(E).cuda().to(tdt)
+        r = B200Retriever.from_device_tensor(emb, squad.contexts, metric="dot")
+        stored = emb.float().cpu().numpy()
+        qd = torch.from_numpy(Q).cuda()
+        oi, os_ = r.search_tensor(qd, k)
+        torch.cuda.synchronize()
+        idx, sc = oi.cpu().numpy(), os_.cpu().numpy()
+        terms = 2 if name == "fp32" else 1
+        Qv = Q if terms == 2 else o.round_to_dtype(Q, DT[name])
+        S = o.scores_dot(Qv.astype(np.float64), stored.astype(np.float64), np.float64)
+        o.check_topk(idx, sc, S, k, rtol=RTOL[name], atol=1e-6)
+        hidx, hsc = r.search(Q, k, query_terms=terms)
+        assert np.array_equal(hidx, idx) and np.array_equal(hsc, sc)
+        r.close()
+    # pinned host source: DMA straight from the caller's buffer
+    pin = torch.from_numpy(E).pin_memory()
+    ix = _cabi.Index(len(E), 1024, "bf16")
+    try:
+        ix.load_rows_ptr(pin.data_ptr(), len(E), "fp32")
+        ix.finalize()
+        assert np.array_equal(ix.get_rows(0, len(E)), o.round_to_bf16(E))
+    finally:
+        ix.close()
+
+
+def test_large_ingest_double_buffered():
+    """Several staging chunks (> 32 MiB each way) through the double-buffered pageable path."""
+    N, D = 40_000, 1024
+    E = o.synth_rows(3, np.arange(N), D)
+    ix = _cabi.Index(N, D, "fp32", scale_exp=4)
+    try:
+        ix.load_rows(E)                                    # 160 MB in one call: 5 chunks
+        ix.finalize()
+        got = np.concatenate([ix.get_rows(r, min(10_000, N - r)) for r in range(0, N, 10_000)])
+        assert np.array_equal(got, o.stored_values(E, o.DTYPE_FP32, 4).astype(np.float32))
+    finally:
+        ix.close()
+
+
 # ---------------------------------------------------------------- golden fixtures (reference outputs)
 def test_fp32_dot_equals_reference_golden(golden):
     idx, sc, _ = run_case(golden.E, golden.Q, golden.k, "fp32", "dot", 2, scale_exp=4)

@@ -83,6 +83,50 @@ def test_retrieve_with_scores_triple_and_multi_shard(fake_backend, squad):
         r.search(g.Q[:, :3], 1)
 
 
+def test_gather_and_source_dtype_helpers():
+    docs = [f"d{i}" for i in range(50)]
+    assert retriever._gather(docs, np.array([4, 0, 49])) == ["d4", "d0", "d49"]
+    assert retriever._gather(docs, np.array([7])) == ["d7"] and retriever._gather(docs, np.array([], np.int64)) == []
+    lazy = retriever._LazyDocs(10)
+    assert retriever._gather(lazy, np.array([2, 9])) == ["doc-2", "doc-9"] and len(lazy) == 10
+    with pytest.raises(IndexError):
+        lazy[10]
+    assert retriever._source_dtype(np.dtype(np.float32), None) == "fp32"
+    assert retriever._source_dtype(np.dtype(np.float16), None) == "fp16"
+    assert retriever._source_dtype(np.dtype("V2"), None) == "bf16"
+    assert retriever._source_dtype(np.dtype(np.float64), None) is None
+    assert retriever._source_dtype(np.dtype(np.uint16), "bf16") == "bf16"
+    with pytest.raises(ValueError):
+        retriever._source_dtype(np.dtype(np.float32), "bf16")
+    x = (np.arange(12, dtype=np.float32).reshape(3, 4) - 5) * 0.25
+    assert retriever._max_abs_chunked(x, "fp32") == 1.5
+    assert retriever._max_abs_chunked(o.bf16_bits(x), "bf16") == 1.5
+
+
+def test_launch_planner_is_consistent():
+    """rs_debug_plan (host only): every plan fits the TMEM / shared-memory budget the kernel assumes."""
+    for dim in (64, 128, 1024, 2048, 4096):
+        for dtype, terms in (("bf16", 1), ("bf16", 2), ("fp16", 1), ("fp32", 2)):
+            for B in (1, 8, 31, 32, 33, 64, 65, 100, 128, 129, 256):
+                for k in (1, 10, 16, 17, 100, 128):
+                    try:
+                        pl = _cabi.debug_plan(dim, dtype, B, k, terms)
+                    except _cabi.RsError:
+                        assert dim >= 2048 or k > 16, (dim, dtype, B, k)      # only big shapes may be refused
+                        continue
+                    nacc = 2 if (terms == 2 or dtype == "fp32") else 1
+                    assert pl["passes"] * pl["per_pass"] >= B and pl["bpad"] % 8 == 0 and pl["bpad"] <= 128
+                    assert pl["bpad"] >= pl["per_pass"] and pl["stages"] >= 2
+                    assert pl["sub"] * pl["nbuf"] * nacc in (1, 2, 4)
+                    assert pl["mma_m"] == (64 if pl["bpad"] <= 64 else 128)
+                    assert (dim // 64) % pl["cps"] == 0
+                    if pl["q_resident"]:
+                        assert pl["sub"] == 1 and pl["nbuf"] == 2
+    hl = _cabi.debug_plan(1024, "bf16", 32, 10, 1)                            # the headline config
+    assert hl == {"passes": 1, "per_pass": 32, "bpad": 32, "stages": 2, "q_resident": 1, "sub": 1, "nbuf": 2,
+                  "mma_m": 64, "cps": 4}
+
+
 def test_auto_query_terms():
     q = np.random.default_rng(0).standard_normal((4, 64)).astype(np.float32)
     assert retriever._auto_query_terms(q, "bf16") == 2
