@@ -12,6 +12,7 @@
 #include <mutex>
 #include <new>
 #include <thread>
+#include <vector>
 
 #include "../../include/rs_retriever.h"
 #include "rs_kernels.h"
@@ -87,6 +88,14 @@ struct rs_index {
   static constexpr int kEventRing = 256;
   cudaEvent_t ev_beg[kEventRing] = {}, ev_end[kEventRing] = {};
   cudaEvent_t ingest_done[2] = {};
+  // host-buffer searches replay a captured CUDA graph per (B, k, metric, terms): one launch instead
+  // of six stream operations - what a small (launch-bound) corpus feels
+  struct GraphEntry {
+    int B, k, metric, terms, uses;
+    cudaGraphExec_t exec;
+  };
+  std::vector<GraphEntry> graphs;
+  bool record_events = true;
   long long ev_count = 0;
   rs_stats stats;
   std::mutex mu;
@@ -184,6 +193,8 @@ void free_all(rs_index* ix) {
   cudaFree(ix->out_score_dev);
   cudaFree(ix->ingest_dev);
   if (ix->pinned) cudaFreeHost(ix->pinned);
+  for (auto& g : ix->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (int i = 0; i < 2; ++i)
     if (ix->ingest_done[i]) cudaEventDestroy(ix->ingest_done[i]);
   for (int i = 0; i < rs_index::kEventRing; ++i) {
@@ -258,7 +269,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.mma_m = pl.mma_m;
     p.debug_flags = env_int("RS_DEBUG_FLAGS", 0);
     p.lo_coef = ix->plane_dtype == RS_DTYPE_FP16 ? ldexpf(1.0f, -RS_FP16_SPLIT_SHIFT) : 1.0f;
-    if (env_int("RS_NO_EVENTS", 0)) {
+    if (!ix->record_events || env_int("RS_NO_EVENTS", 0)) {
       RS_CUDA(rs::launch_fused_search(p, grid, stream));
     } else {
       const int slot = (int)(ix->ev_count % rs_index::kEventRing);
@@ -533,12 +544,47 @@ RS_API int rs_search(rs_index* ix, const float* q_host, int32_t B, int32_t k, in
   char* pin = static_cast<char*>(ix->pinned);
   long long* pin_idx = reinterpret_cast<long long*>(pin + ((q_bytes + 255) & ~size_t(255)));
   float* pin_score = reinterpret_cast<float*>(pin_idx + n_out);
+  if (ix->planes == 2) query_terms = 2;
+  auto enqueue = [&]() -> int {  // H2D -> prep -> fused -> merge -> D2H, all on ix->stream
+    RS_CUDA(cudaMemcpyAsync(ix->q_dev, pin, q_bytes, cudaMemcpyHostToDevice, ix->stream));
+    int rc = search_device_locked(ix, ix->q_dev, B, k, metric, query_terms, ix->out_idx_dev, ix->out_score_dev, ix->stream);
+    if (rc != RS_OK) return rc;
+    RS_CUDA(cudaMemcpyAsync(pin_idx, ix->out_idx_dev, n_out * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
+    RS_CUDA(cudaMemcpyAsync(pin_score, ix->out_score_dev, n_out * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+    return RS_OK;
+  };
   memcpy(pin, q_host, q_bytes);
-  RS_CUDA(cudaMemcpyAsync(ix->q_dev, pin, q_bytes, cudaMemcpyHostToDevice, ix->stream));
-  int rc = search_device_locked(ix, ix->q_dev, B, k, metric, query_terms, ix->out_idx_dev, ix->out_score_dev, ix->stream);
-  if (rc != RS_OK) return rc;
-  RS_CUDA(cudaMemcpyAsync(pin_idx, ix->out_idx_dev, n_out * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
-  RS_CUDA(cudaMemcpyAsync(pin_score, ix->out_score_dev, n_out * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+  rs_index::GraphEntry* ge = nullptr;
+  if (env_int("RS_GRAPH", 1)) {
+    for (auto& g : ix->graphs)
+      if (g.B == B && g.k == k && g.metric == metric && g.terms == query_terms) ge = &g;
+    if (!ge && ix->graphs.size() < 64) {
+      ix->graphs.push_back({B, k, metric, query_terms, 0, nullptr});
+      ge = &ix->graphs.back();
+    }
+  }
+  if (ge && !ge->exec && ge->uses >= 1) {
+    // second call with this shape: capture the sequence (the first, eager call set the kernels'
+    // shared-memory attributes and validated the arguments)
+    ix->record_events = false;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(ix->stream, cudaStreamCaptureModeThreadLocal);
+    int rc = ce == cudaSuccess ? enqueue() : RS_E_CUDA;
+    cudaError_t ee = cudaStreamEndCapture(ix->stream, &graph);
+    ix->record_events = true;
+    if (rc == RS_OK && ee == cudaSuccess && graph && cudaGraphInstantiate(&ge->exec, graph, 0) != cudaSuccess) ge->exec = nullptr;
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (!ge->exec) ge->uses = -1000000;  // capture not possible here: stay on the eager path
+  }
+  if (ge && ge->exec) {
+    RS_CUDA(cudaGraphLaunch(ge->exec, ix->stream));
+    ix->stats.total_launches += ix->stats.launches;
+  } else {
+    int rc = enqueue();
+    if (rc != RS_OK) return rc;
+    if (ge) ++ge->uses;
+  }
   RS_CUDA(cudaStreamSynchronize(ix->stream));
   memcpy(out_idx, pin_idx, n_out * sizeof(long long));
   memcpy(out_score, pin_score, n_out * sizeof(float));

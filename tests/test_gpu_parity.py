@@ -408,6 +408,27 @@ def test_device_buffer_entry_point(squad):
         ix.close()
 
 
+def test_graph_replay_uses_fresh_queries(squad, monkeypatch):
+    """Host-buffer searches replay a captured CUDA graph from the third call of a shape on; every
+    replay must see that call's queries and a changed shape must not reuse the wrong graph."""
+    ix = make_index(squad.E, "bf16")
+    try:
+        rng = np.random.default_rng(4)
+        for it in range(6):
+            B, k = (32, 10) if it != 3 else (7, 5)
+            Q = o.round_to_bf16(squad.E[rng.integers(0, 1000, B)] + 0.05 * rng.standard_normal((B, 1024)).astype(np.float32))
+            idx, sc = ix.search(Q, k, "dot", 1)
+            S = o.scores_dot(Q.astype(np.float64), o.round_to_bf16(squad.E).astype(np.float64), np.float64)
+            o.check_topk(idx, sc, S, k, rtol=2e-3, atol=1e-6)
+            eidx, _ = o.topk_rows(S, k)
+            assert (idx[:, 0] == eidx[:, 0]).all()
+        monkeypatch.setenv("RS_GRAPH", "0")
+        i2, s2 = ix.search(Q, k, "dot", 1)                  # eager path gives the same answer
+        assert np.array_equal(i2, idx) and np.array_equal(s2, sc)
+    finally:
+        ix.close()
+
+
 def test_errors_are_loud(squad):
     ix = _cabi.Index(100, 1024, "bf16", max_batch=8, max_k=4)
     try:
