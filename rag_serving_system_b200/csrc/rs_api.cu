@@ -106,16 +106,14 @@ struct rs_index {
 struct rs_xchg {
   int device = 0, world = 1, rank = 0, max_batch = 0, max_k = 0;
   size_t slot_bytes = 0, parity_bytes = 0, total_bytes = 0;
-  uint8_t* local = nullptr;              // [flags 2 x 8 x u32 | pad to 256 B][parity 0: world slots][parity 1]
+  size_t header_bytes = 0;               // flags[2 parities][8 ranks][max_batch] u32, padded to 256 B
+  uint8_t* local = nullptr;              // [flags][parity 0: world slots][parity 1: world slots]
   uint8_t* peer[rs::kMaxPeers] = {};     // peer[g] = GPU g's buffer mapped into this process (peer[rank] = local)
   bool opened[rs::kMaxPeers] = {};
-  unsigned int* done_counter = nullptr;
   unsigned int epoch = 0;
 };
 
 namespace {
-
-constexpr size_t kXchgHeader = 256;
 
 int max_cap_rows(int kc, int terms, int k, int min_stages, int cps, int q_resident) {
   // largest bpad (multiple of 8, <= 128) that leaves at least min_stages ring slots
@@ -166,9 +164,11 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
   pl->bpad = (pl->per_pass + 7) / 8 * 8;
   pl->mma_m = env_int("RS_MMA_M", pl->bpad <= 64 ? 64 : 128);
   if (pl->mma_m != 128 && !(pl->mma_m == 64 && pl->bpad <= 64)) return fail(RS_E_INVALID, "RS_MMA_M=%d invalid for bpad=%d", pl->mma_m, pl->bpad);
-  pl->nbuf = env_int("RS_NBUF", pl->sub * nacc <= 2 ? 2 : 1);  // double-buffer the accumulators whenever TMEM has room
+  // as many accumulator buffers as the 512 TMEM columns hold: the epilogue's start-up burst (every
+  // score beats an empty list) then stalls the MMA/TMA pipeline less
+  pl->nbuf = env_int("RS_NBUF", std::max(1, 4 / (pl->sub * nacc)));
   const int cols = pl->sub * pl->nbuf * nacc;
-  if (pl->nbuf < 1 || pl->nbuf > 2 || (cols != 1 && cols != 2 && cols != 4))
+  if (pl->nbuf < 1 || pl->nbuf > 4 || (cols != 1 && cols != 2 && cols != 4))
     return fail(RS_E_INVALID, "sub=%d nbuf=%d nacc=%d does not map onto 128/256/512 TMEM columns", pl->sub, pl->nbuf, nacc);
   while (pl->stages < kMaxStages && rs::fused_smem_bytes(pl->bpad, ix->kc, terms, pl->stages + 1, pl->cps, k,
                                                          pl->q_resident, 2 * terms) <= kMaxSmem)
@@ -280,40 +280,33 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     }
     if (!xg) {
       RS_CUDA(rs::launch_merge_i32(ix->cand_score, ix->cand_idx, grid, nb, k, k, ix->cfg.row_offset,
-                                   out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, nullptr, stream));
+                                   out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, stream));
     } else {
-      // local merge + exchange in one kernel: rows go straight into every GPU's buffer
-      rs::MergeXchg mx;
-      memset(&mx, 0, sizeof(mx));
-      mx.n_dest = xg->world;
+      // local merge + exchange + final merge in one kernel: rows go straight into every GPU's buffer
+      rs::ExchangeArgs ea;
+      memset(&ea, 0, sizeof(ea));
+      ea.world = xg->world;
+      ea.q0 = b0;
+      ea.epoch = epoch;
       for (int g = 0; g < xg->world; ++g) {
-        uint8_t* slot = xg->peer[g] + kXchgHeader + parity * xg->parity_bytes + (size_t)xg->rank * xg->slot_bytes;
-        mx.dest_idx[g] = reinterpret_cast<long long*>(slot) + (size_t)b0 * k;
-        mx.dest_score[g] = reinterpret_cast<float*>(slot + (size_t)B * k * 8) + (size_t)b0 * k;
-        mx.dest_flag[g] = reinterpret_cast<unsigned int*>(xg->peer[g]) + parity * rs::kMaxPeers + xg->rank;
+        uint8_t* slot = xg->peer[g] + xg->header_bytes + parity * xg->parity_bytes + (size_t)xg->rank * xg->slot_bytes;
+        ea.dest_idx[g] = reinterpret_cast<long long*>(slot);
+        ea.dest_score[g] = reinterpret_cast<float*>(slot + (size_t)B * k * 8);
+        ea.dest_flag[g] = reinterpret_cast<unsigned int*>(xg->peer[g]) +
+                          ((size_t)parity * rs::kMaxPeers + xg->rank) * xg->max_batch;
       }
-      mx.done_counter = xg->done_counter;
-      mx.done_target = (unsigned int)B;
-      mx.epoch = epoch;
-      RS_CUDA(rs::launch_merge_i32(ix->cand_score, ix->cand_idx, grid, nb, k, k, ix->cfg.row_offset, nullptr, nullptr,
-                                   &mx, stream));
+      ea.wait_flags = reinterpret_cast<const unsigned int*>(xg->local) + (size_t)parity * rs::kMaxPeers * xg->max_batch;
+      ea.flag_stride = xg->max_batch;
+      const uint8_t* base = xg->local + xg->header_bytes + parity * xg->parity_bytes;
+      ea.local_idx = reinterpret_cast<const long long*>(base);
+      ea.local_score = reinterpret_cast<const float*>(base + (size_t)B * k * 8);
+      ea.idx_list_stride = (long long)(xg->slot_bytes / 8);
+      ea.score_list_stride = (long long)(xg->slot_bytes / 4);
+      RS_CUDA(rs::launch_exchange_merge(ix->cand_score, ix->cand_idx, grid, nb, k, ix->cfg.row_offset,
+                                        out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, ea, stream));
     }
     ix->stats.launches += 3;
     ix->stats.bytes_streamed += (int64_t)ix->corpus_bytes;
-  }
-  if (xg) {
-    // final merge: wait for every rank's flag of this epoch, then merge the world lists
-    rs::MergeXchg mw;
-    memset(&mw, 0, sizeof(mw));
-    mw.n_wait = xg->world;
-    mw.wait_flags = reinterpret_cast<const unsigned int*>(xg->local) + parity * rs::kMaxPeers;
-    mw.epoch = epoch;
-    const uint8_t* base = xg->local + kXchgHeader + parity * xg->parity_bytes;
-    RS_CUDA(rs::launch_merge_i64(reinterpret_cast<const float*>(base + (size_t)B * k * 8),
-                                 reinterpret_cast<const long long*>(base), xg->world, B, k, k,
-                                 (long long)(xg->slot_bytes / 4), (long long)(xg->slot_bytes / 8), out_score, out_idx,
-                                 &mw, stream));
-    ix->stats.launches += 1;
   }
   ix->stats.total_launches += ix->stats.launches;
   return RS_OK;
@@ -602,7 +595,7 @@ RS_API int rs_merge_device(int32_t device, const float* scores_dev, const int64_
   if (idx_list_stride <= 0) idx_list_stride = (int64_t)B * kc;
   RS_CUDA(rs::launch_merge_i64(scores_dev, reinterpret_cast<const long long*>(idx_dev), n_lists, B, kc, k,
                                score_list_stride, idx_list_stride, out_score_dev, reinterpret_cast<long long*>(out_idx_dev),
-                               nullptr, static_cast<cudaStream_t>(stream)));
+                               static_cast<cudaStream_t>(stream)));
   return RS_OK;
 }
 
@@ -621,15 +614,13 @@ RS_API int rs_xchg_create(int32_t device, int32_t world, int32_t rank, int32_t m
   x->max_k = max_k;
   x->slot_bytes = (((size_t)max_batch * max_k * 12) + 255) & ~size_t(255);
   x->parity_bytes = x->slot_bytes * world;
-  x->total_bytes = kXchgHeader + 2 * x->parity_bytes;
+  x->header_bytes = (((size_t)2 * rs::kMaxPeers * max_batch * sizeof(unsigned int)) + 255) & ~size_t(255);
+  x->total_bytes = x->header_bytes + 2 * x->parity_bytes;
   cudaError_t e = cudaMalloc(&x->local, x->total_bytes);
   if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->total_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&x->done_counter, sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(x->done_counter, 0, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     cudaFree(x->local);
-    cudaFree(x->done_counter);
     delete x;
     return fail(RS_E_CUDA, "exchange buffer allocation failed: %s", cudaGetErrorString(e));
   }
@@ -669,7 +660,6 @@ RS_API int rs_xchg_destroy(rs_xchg* x) {
   for (int g = 0; g < x->world; ++g)
     if (x->opened[g]) cudaIpcCloseMemHandle(x->peer[g]);
   cudaFree(x->local);
-  cudaFree(x->done_counter);
   delete x;
   return RS_OK;
 }

@@ -35,18 +35,21 @@ struct SearchParams {
   float lo_coef;                     // weight of the low-order accumulator (2^-11 for fp16 terms, 1 for bf16)
 };
 
-// Optional exchange hooks of the merge kernel (multi-GPU candidate exchange over peer memory).
+// Arguments of the fused merge + exchange kernel (multi-GPU candidate exchange over peer memory).
 constexpr int kMaxPeers = 8;
-struct MergeXchg {
-  int n_dest;                           // > 0: write the merged rows to these buffers instead of out_*
-  long long* dest_idx[kMaxPeers];       //   destination g: this rank's slot in GPU g's exchange buffer
-  float* dest_score[kMaxPeers];
-  unsigned int* dest_flag[kMaxPeers];   //   GPU g's flag word for (parity, this rank)
-  unsigned int* done_counter;           //   local counter of finished query warps
-  unsigned int done_target;             //   query warps per search (all passes)
-  int n_wait;                           // > 0: wait for wait_flags[0..n_wait) >= epoch before reading
-  const unsigned int* wait_flags;
-  unsigned int epoch;
+struct ExchangeArgs {
+  int world;                            // GPUs taking part
+  int q0;                               // first query of this pass inside the search's batch
+  unsigned int epoch;                   // search counter; flags carry it
+  long long* dest_idx[kMaxPeers];       // GPU g: this rank's slot in g's exchange buffer, idx block  [B][k]
+  float* dest_score[kMaxPeers];         //        ... score block [B][k]
+  unsigned int* dest_flag[kMaxPeers];   // GPU g: flags[parity][this rank][0..max_batch)
+  const unsigned int* wait_flags;       // local flags[parity][0][0]; rank stride = flag_stride
+  int flag_stride;                      // = max_batch
+  const long long* local_idx;           // local exchange buffer, slot of rank 0 (idx block)
+  const float* local_score;             //                                      (score block)
+  long long idx_list_stride;            // elements between consecutive ranks' slots
+  long long score_list_stride;
 };
 
 cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dtype, int terms, int corpus_scale_exp,
@@ -55,11 +58,13 @@ cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t st
 int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages);
 int fused_reg_k();
 cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int kc, int k,
-                             long long idx_offset, float* out_score, long long* out_idx, const MergeXchg* xc,
-                             cudaStream_t stream);
+                             long long idx_offset, float* out_score, long long* out_idx, cudaStream_t stream);
+cudaError_t launch_exchange_merge(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int k,
+                                  long long idx_offset, float* out_score, long long* out_idx, const ExchangeArgs& x,
+                                  cudaStream_t stream);
 cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx, int n_lists, int n_queries, int kc,
                              int k, long long score_list_stride, long long idx_list_stride, float* out_score,
-                             long long* out_idx, const MergeXchg* xc, cudaStream_t stream);
+                             long long* out_idx, cudaStream_t stream);
 
 // ingest (rs_ingest.cu)
 cudaError_t launch_tile_rows(const void* rows_dev, int src_dtype, long long row0, int nrows, int D, int dtype,

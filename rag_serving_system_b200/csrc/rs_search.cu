@@ -18,6 +18,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "rs_kernels.h"
 #include "rs_layout.h"
 #include "rs_ptx.cuh"
@@ -247,14 +249,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   const uint32_t q_smem = smem_base;
   const uint32_t stage_smem = smem_base + map.stage_off;
   const uint32_t bar_base = smem_base + map.bar_off;
-  // barrier slots (8 B each): full[s], empty[s], tfull[2], tempty[2], qfull
+  // barrier slots (8 B each): full[s], empty[s], tfull[4], tempty[4], qfull, qring_full[], qring_empty[]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
-  const uint32_t qfull_bar = bar_base + 8u * (2 * p.stages + 4);
-  auto qring_full = [&](int s) { return bar_base + 8u * (2 * p.stages + 5 + s); };              // streamed Q ring
-  auto qring_empty = [&](int s) { return bar_base + 8u * (2 * p.stages + 5 + p.qstages + s); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 4 + a); };
+  const uint32_t qfull_bar = bar_base + 8u * (2 * p.stages + 8);
+  auto qring_full = [&](int s) { return bar_base + 8u * (2 * p.stages + 9 + s); };              // streamed Q ring
+  auto qring_empty = [&](int s) { return bar_base + 8u * (2 * p.stages + 9 + p.qstages + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + map.bar_off + 1016);
 
   // M=128: query row r lives in TMEM lane r.  M=64 (half the tensor work, used when bpad <= 64):
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   const int rows_per_warp = p.mma_m == 64 ? 16 : 32;
   const int nact_warps = (p.bpad + rows_per_warp - 1) / rows_per_warp;
   const int S = p.sub;     // 128-document tiles per supertile
-  const int NB = p.nbuf;   // accumulator buffers in TMEM (2 = epilogue overlaps the next supertile's MMAs)
+  const int NB = p.nbuf;   // accumulator buffers in TMEM (>1: the epilogue overlaps the next supertiles' MMAs)
   const uint32_t tmem_cols = (uint32_t)(NB * S * NACC) * RS_TILE_ROWS;  // 128, 256 or 512
   const int n_super = (p.n_tiles + S - 1) / S;
   const uint32_t qblk = (uint32_t)p.bpad * RS_KCHUNK_BYTES;
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 4; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), nact_warps);
     }
@@ -653,79 +655,47 @@ __device__ __forceinline__ void st_volatile_u32(unsigned int* p, unsigned int v)
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// One warp per query.  With x.n_wait > 0 the warp first waits until every source rank has
-// published its candidates for this epoch (flags written by PEER GPUs over NVLink).  With
-// x.n_dest > 0 the merged row is written to n_dest destinations - the exchange buffers of every
-// GPU of the box, reached through peer pointers - and the last warp to finish raises this
-// rank's flag on every peer.  That makes "local merge + candidate exchange" ONE kernel whose
-// stores travel over NVLink while other queries are still being merged.
 constexpr int kMergeThreads = 128;  // four warps stage one query's candidates; warp 0 runs the k rounds
 
-template <typename IdxT, bool STAGED>
-__global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const float* __restrict__ cand_score,
-                                                        const IdxT* __restrict__ cand_idx, int n_lists,
-                                                        int n_queries, int kc, int k, long long idx_offset,
-                                                        long long score_list_stride, long long idx_list_stride,
-                                                        long long query_stride, float* __restrict__ out_score,
-                                                        long long* __restrict__ out_idx, const MergeXchg x) {
-  extern __shared__ __align__(16) uint8_t merge_smem[];
-  const int q = blockIdx.x;
-  const int lane = threadIdx.x & 31;
+// Copy one query's candidate lists into shared memory.  Element (list l, slot j) sits at
+// l*list_stride + qoff + j; the loads are issued four deep so the L2 round trips overlap.
+template <typename IdxT>
+__device__ __forceinline__ void stage_lists(const float* __restrict__ cand_score, const IdxT* __restrict__ cand_idx,
+                                            int n_lists, int kc, long long score_list_stride,
+                                            long long idx_list_stride, size_t qoff, IdxT* s_idx, float* s_score) {
   const int total = n_lists * kc;
-  long long* res_i = reinterpret_cast<long long*>(merge_smem);
-  float* res_s = reinterpret_cast<float*>(res_i + k);
-  uint8_t* stage = merge_smem + (((size_t)k * 12 + 15) & ~size_t(15));
-  IdxT* s_idx = reinterpret_cast<IdxT*>(stage);
-  float* s_score = reinterpret_cast<float*>(stage + (size_t)total * sizeof(IdxT));
-  if (x.n_wait > 0) {
-    if (threadIdx.x < x.n_wait) {
-      long long spins = 0;
-      while ((int)(ld_volatile_u32(x.wait_flags + threadIdx.x) - x.epoch) < 0 && ++spins < (1ll << 28)) {
-      }
-    }
-    __threadfence_system();
-    __syncthreads();
-  }
-  const size_t qoff = (size_t)q * query_stride;
-  if (STAGED) {
-    // element (list l, slot j) of this query sits at l*list_stride + q*query_stride + j; issue the
-    // loads four deep so the L2 round trips overlap
-    for (int e0 = threadIdx.x; e0 < total; e0 += 4 * kMergeThreads) {
-      IdxT ti[4];
-      float ts[4];
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * kMergeThreads) {
+    IdxT ti[4];
+    float ts[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + kMergeThreads * u;
-        if (e < total) {
-          const int l = e / kc, j = e - l * kc;
-          ti[u] = __ldcg(cand_idx + (size_t)l * idx_list_stride + qoff + j);
-          ts[u] = __ldcg(cand_score + (size_t)l * score_list_stride + qoff + j);
-        }
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + kMergeThreads * u;
+      if (e < total) {
+        const int l = e / kc, j = e - l * kc;
+        ti[u] = __ldcg(cand_idx + (size_t)l * idx_list_stride + qoff + j);
+        ts[u] = __ldcg(cand_score + (size_t)l * score_list_stride + qoff + j);
       }
+    }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + kMergeThreads * u;
-        if (e < total) {
-          s_idx[e] = ti[u];
-          s_score[e] = ts[u];
-        }
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + kMergeThreads * u;
+      if (e < total) {
+        s_idx[e] = ti[u];
+        s_score[e] = ts[u];
       }
     }
-    __syncthreads();
   }
-  if (threadIdx.x >= 32) return;  // the selection rounds are a single-warp job
-  auto load = [&](int l, int j, float& s, long long& id) {
-    if (STAGED) {
-      s = s_score[l * kc + j];
-      id = (long long)s_idx[l * kc + j];
-    } else {
-      id = (long long)__ldcg(cand_idx + (size_t)l * idx_list_stride + qoff + j);
-      s = __ldcg(cand_score + (size_t)l * score_list_stride + qoff + j);
-    }
-  };
-  // Every list head is kept as a sortable pair: ks = order-preserving image of the score (0 =
-  // padding / exhausted), ki = ~index (larger = lower index).  The warp's best head is found with
-  // three redux.sync steps (score, index high word, index low word) instead of shuffle trees.
+  __syncthreads();
+}
+
+// k selection rounds by ONE warp over n_lists sorted lists (score desc, index asc; index < 0 is
+// padding at the end of a list).  Every list head is kept as a sortable pair: ks = order-preserving
+// image of the score (0 = padding / exhausted), ki = ~index (larger = lower index).  The warp's best
+// head is found with three redux.sync steps (score, index high word, index low word).  `load(l, j,
+// score&, idx&)` reads element j of list l.  Writes k rows to res_* (padding: -1 / -inf).
+template <typename Load>
+__device__ __forceinline__ void select_rounds(Load load, int n_lists, int kc, int k, long long idx_offset,
+                                              float* res_s, long long* res_i, int lane) {
   unsigned int ks[kMergeMaxOwn];
   unsigned long long ki[kMergeMaxOwn];
   int head[kMergeMaxOwn];
@@ -788,26 +758,109 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const float* 
     res_i[rr] = -1;
   }
   __syncwarp();
-  if (x.n_dest == 0) {
-    for (int j = lane; j < k; j += 32) {
-      out_score[(size_t)q * k + j] = res_s[j];
-      out_idx[(size_t)q * k + j] = res_i[j];
+}
+
+// Plain merge: one CTA per query, lists -> out[q][0..k).
+template <typename IdxT, bool STAGED>
+__global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const float* __restrict__ cand_score,
+                                                                   const IdxT* __restrict__ cand_idx, int n_lists,
+                                                                   int n_queries, int kc, int k, long long idx_offset,
+                                                                   long long score_list_stride,
+                                                                   long long idx_list_stride, long long query_stride,
+                                                                   float* __restrict__ out_score,
+                                                                   long long* __restrict__ out_idx) {
+  extern __shared__ __align__(16) uint8_t merge_smem[];
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  long long* res_i = reinterpret_cast<long long*>(merge_smem);
+  float* res_s = reinterpret_cast<float*>(res_i + k);
+  uint8_t* stage = merge_smem + (((size_t)k * 12 + 15) & ~size_t(15));
+  IdxT* s_idx = reinterpret_cast<IdxT*>(stage);
+  float* s_score = reinterpret_cast<float*>(stage + (size_t)n_lists * kc * sizeof(IdxT));
+  const size_t qoff = (size_t)q * query_stride;
+  if (STAGED) stage_lists<IdxT>(cand_score, cand_idx, n_lists, kc, score_list_stride, idx_list_stride, qoff, s_idx, s_score);
+  if (threadIdx.x >= 32) return;  // the selection rounds are a single-warp job
+  auto load = [&](int l, int j, float& sc, long long& id) {
+    if (STAGED) {
+      sc = s_score[l * kc + j];
+      id = (long long)s_idx[l * kc + j];
+    } else {
+      id = (long long)__ldcg(cand_idx + (size_t)l * idx_list_stride + qoff + j);
+      sc = __ldcg(cand_score + (size_t)l * score_list_stride + qoff + j);
     }
-  } else {
-    // fan the row out to every GPU's exchange buffer (peer stores over NVLink)
-    for (int e = lane; e < k * x.n_dest; e += 32) {
-      const int g = e / k, j = e - g * k;
-      x.dest_score[g][(size_t)q * k + j] = res_s[j];
-      x.dest_idx[g][(size_t)q * k + j] = res_i[j];
+  };
+  select_rounds(load, n_lists, kc, k, idx_offset, res_s, res_i, lane);
+  for (int j = lane; j < k; j += 32) {
+    out_score[(size_t)q * k + j] = res_s[j];
+    out_idx[(size_t)q * k + j] = res_i[j];
+  }
+}
+
+// Multi-GPU: local merge + candidate exchange + final merge in ONE kernel (one CTA per query).
+//   1. merge this GPU's per-CTA lists of query q into its local top-k (global indices)
+//   2. store that row into every GPU's exchange buffer through peer pointers (NVLink) and raise
+//      this rank's per-query flag there with the search epoch
+//   3. wait until every rank's flag for query q shows this epoch (written by the PEER GPUs)
+//   4. merge the world lists of query q from the local exchange buffer into the final row
+// A CTA only ever waits for the CTAs of the same query on other GPUs, never for a CTA of its own
+// grid, so no co-residency is required.  Buffers are double-buffered by epoch parity.
+__global__ void __launch_bounds__(kMergeThreads) exchange_merge_kernel(const float* __restrict__ cand_score,
+                                                                       const int* __restrict__ cand_idx, int n_lists,
+                                                                       int kc, int k, long long idx_offset,
+                                                                       float* __restrict__ out_score,
+                                                                       long long* __restrict__ out_idx,
+                                                                       const ExchangeArgs x) {
+  extern __shared__ __align__(16) uint8_t merge_smem[];
+  const int q = blockIdx.x;  // query inside this pass
+  const int lane = threadIdx.x & 31;
+  long long* res_i = reinterpret_cast<long long*>(merge_smem);
+  float* res_s = reinterpret_cast<float*>(res_i + k);
+  uint8_t* stage = merge_smem + (((size_t)k * 12 + 15) & ~size_t(15));
+  {
+    int* s_idx = reinterpret_cast<int*>(stage);
+    float* s_score = reinterpret_cast<float*>(stage + (size_t)n_lists * kc * sizeof(int));
+    stage_lists<int>(cand_score, cand_idx, n_lists, kc, kc, kc, (size_t)q * n_lists * kc, s_idx, s_score);
+    if (threadIdx.x < 32) {
+      auto load = [&](int l, int j, float& sc, long long& id) {
+        sc = s_score[l * kc + j];
+        id = (long long)s_idx[l * kc + j];
+      };
+      select_rounds(load, n_lists, kc, k, idx_offset, res_s, res_i, lane);
+      // fan the row out to every GPU's exchange buffer (peer stores over NVLink), then publish
+      const size_t qg = (size_t)(x.q0 + q) * k;
+      for (int e = lane; e < k * x.world; e += 32) {
+        const int g = e / k, j = e - g * k;
+        x.dest_score[g][qg + j] = res_s[j];
+        x.dest_idx[g][qg + j] = res_i[j];
+      }
+      __threadfence_system();
+      __syncwarp();
+      if (lane < x.world) st_volatile_u32(x.dest_flag[lane] + x.q0 + q, x.epoch);
     }
-    __threadfence_system();
-    __syncwarp();
-    if (lane == 0) {
-      const unsigned int prev = atomicAdd(x.done_counter, 1u);
-      if (prev == x.done_target - 1u) {  // last query of this search: publish
-        *x.done_counter = 0u;
-        __threadfence_system();
-        for (int g = 0; g < x.n_dest; ++g) st_volatile_u32(x.dest_flag[g], x.epoch);
+  }
+  // wait for all ranks' rows of this query
+  if (threadIdx.x < x.world) {
+    long long spins = 0;
+    const unsigned int* f = x.wait_flags + (size_t)threadIdx.x * x.flag_stride + x.q0 + q;
+    while ((int)(ld_volatile_u32(f) - x.epoch) < 0 && ++spins < (1ll << 28)) {
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  {
+    long long* s_idx = reinterpret_cast<long long*>(stage);
+    float* s_score = reinterpret_cast<float*>(stage + (size_t)x.world * k * sizeof(long long));
+    stage_lists<long long>(x.local_score, x.local_idx, x.world, k, x.score_list_stride, x.idx_list_stride,
+                           (size_t)(x.q0 + q) * k, s_idx, s_score);
+    if (threadIdx.x < 32) {
+      auto load = [&](int l, int j, float& sc, long long& id) {
+        sc = s_score[l * k + j];
+        id = s_idx[l * k + j];
+      };
+      select_rounds(load, x.world, k, k, 0, res_s, res_i, lane);
+      for (int j = lane; j < k; j += 32) {
+        out_score[(size_t)q * k + j] = res_s[j];
+        out_idx[(size_t)q * k + j] = res_i[j];
       }
     }
   }
@@ -856,11 +909,8 @@ template <typename IdxT>
 static cudaError_t launch_merge_t(const float* cand_score, const IdxT* cand_idx, int n_lists, int n_queries, int kc,
                                   int k, long long idx_offset, long long score_list_stride,
                                   long long idx_list_stride, long long query_stride, float* out_score,
-                                  long long* out_idx, const MergeXchg* xc, cudaStream_t stream) {
+                                  long long* out_idx, cudaStream_t stream) {
   if (n_lists > 32 * kMergeMaxOwn) return cudaErrorInvalidValue;
-  MergeXchg x;
-  memset(&x, 0, sizeof(x));
-  if (xc) x = *xc;
   const size_t res_bytes = ((size_t)k * 12 + 15) & ~size_t(15);
   const size_t stage_bytes = (size_t)n_lists * kc * (sizeof(IdxT) + sizeof(float));
   if (res_bytes + stage_bytes <= 200 * 1024) {
@@ -871,27 +921,44 @@ static cudaError_t launch_merge_t(const float* cand_score, const IdxT* cand_idx,
       if (e != cudaSuccess) return e;
     }
     kern<<<n_queries, kMergeThreads, bytes, stream>>>(cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset,
-                                           score_list_stride, idx_list_stride, query_stride, out_score, out_idx, x);
+                                                      score_list_stride, idx_list_stride, query_stride, out_score,
+                                                      out_idx);
   } else {
     merge_topk_kernel<IdxT, false><<<n_queries, kMergeThreads, res_bytes, stream>>>(
         cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, score_list_stride, idx_list_stride, query_stride,
-        out_score, out_idx, x);
+        out_score, out_idx);
   }
   return cudaGetLastError();
 }
 
 cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int kc, int k,
-                             long long idx_offset, float* out_score, long long* out_idx, const MergeXchg* xc,
-                             cudaStream_t stream) {
+                             long long idx_offset, float* out_score, long long* out_idx, cudaStream_t stream) {
   // per-CTA candidates are stored [query][cta][k]: one query's lists are contiguous (coalesced staging)
   return launch_merge_t<int>(cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, (long long)kc,
-                             (long long)kc, (long long)n_lists * kc, out_score, out_idx, xc, stream);
+                             (long long)kc, (long long)n_lists * kc, out_score, out_idx, stream);
 }
 cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx, int n_lists, int n_queries, int kc,
                              int k, long long score_list_stride, long long idx_list_stride, float* out_score,
-                             long long* out_idx, const MergeXchg* xc, cudaStream_t stream) {
+                             long long* out_idx, cudaStream_t stream) {
   return launch_merge_t<long long>(cand_score, cand_idx, n_lists, n_queries, kc, k, 0, score_list_stride,
-                                   idx_list_stride, (long long)kc, out_score, out_idx, xc, stream);
+                                   idx_list_stride, (long long)kc, out_score, out_idx, stream);
+}
+
+cudaError_t launch_exchange_merge(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int k,
+                                  long long idx_offset, float* out_score, long long* out_idx, const ExchangeArgs& x,
+                                  cudaStream_t stream) {
+  if (n_lists > 32 * kMergeMaxOwn || x.world > kMaxPeers) return cudaErrorInvalidValue;
+  const size_t res_bytes = ((size_t)k * 12 + 15) & ~size_t(15);
+  const size_t stage_bytes = std::max((size_t)n_lists * k * 8, (size_t)x.world * k * 12);
+  const size_t bytes = res_bytes + stage_bytes;
+  if (bytes > 200 * 1024) return cudaErrorInvalidValue;
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+  }
+  exchange_merge_kernel<<<n_queries, kMergeThreads, bytes, stream>>>(cand_score, cand_idx, n_lists, k, k, idx_offset,
+                                                                     out_score, out_idx, x);
+  return cudaGetLastError();
 }
 
 }  // namespace rs

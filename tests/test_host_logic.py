@@ -121,9 +121,9 @@ def test_launch_planner_is_consistent():
                     assert pl["mma_m"] == (64 if pl["bpad"] <= 64 else 128)
                     assert (dim // 64) % pl["cps"] == 0
                     if pl["q_resident"]:
-                        assert pl["sub"] == 1 and pl["nbuf"] == 2
+                        assert pl["sub"] == 1 and pl["nbuf"] == 4 // nacc
     hl = _cabi.debug_plan(1024, "bf16", 32, 10, 1)                            # the headline config
-    assert hl == {"passes": 1, "per_pass": 32, "bpad": 32, "stages": 2, "q_resident": 1, "sub": 1, "nbuf": 2,
+    assert hl == {"passes": 1, "per_pass": 32, "bpad": 32, "stages": 2, "q_resident": 1, "sub": 1, "nbuf": 4,
                   "mma_m": 64, "cps": 4}
 
 
