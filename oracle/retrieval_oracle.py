@@ -7,13 +7,17 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 Every function restates, in NumPy, the arithmetic of the reference file
 ``rag_service/core/retriever.py`` (citations are ``retriever.py:<line>`` relative to
 ``/root/reference``).  The restatement is pinned against the *imported, unmodified*
-reference ``SimpleRetriever`` by ``oracle/make_golden.py`` (run in the build container, where
-``/root/reference`` exists); the vectors it wrote live in ``tests/golden/`` and are re-checked
-by ``tests/test_oracle.py`` on every run.  The reference ships no tests of its own
-(SURVEY.md §4), and its live GPU class ``CupyRetriever`` cannot be executed anywhere we can
-reach (CuPy is not installable), so for the cosine path the oracle follows the source text
-only: parity for ``metric="cosine"`` is pinned by construction on the NumPy shim of the CuPy
-logic (``CupyRetrieverPort``), not by reference-generated vectors.
+reference ``SimpleRetriever`` (raw dot) AND the imported, unmodified live class ``CupyRetriever``
+(cosine) by ``oracle/make_golden.py`` (run in the build container, where ``/root/reference``
+exists); the vectors it wrote live in ``tests/golden/`` and are re-checked by
+``tests/test_oracle.py`` on every run.  The reference ships no tests of its own.
+``CupyRetriever`` holds no arithmetic of its own - every operation is a call into CuPy, which is
+not vendored, not pinned (Dockerfile:12; ``#cupy==13.4.1`` at requirements.txt:84) and not
+installable here - so the generator runs the reference class with ``oracle/cupy_numpy_shim.py``
+registered as ``cupy``: the reference's own control flow and call sequence, NumPy's fp32
+implementation of each call.  That pins the cosine formula, its operation order, ``max_k``
+handling, slicing and string gather; what it cannot pin is cuBLAS' summation order inside SGEMM
+(covered by the 1e-5 relative score bar) and CuPy's tie order (goldens are tie-free).
 """
 from __future__ import annotations
 

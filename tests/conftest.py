@@ -45,6 +45,13 @@ class Golden:
         self.idx_var = g["idx_var"]
         self.self_top1 = g["self_top1"]
         self.texts = json.load(open(os.path.join(GOLD, f"{name}_golden_texts.json")))
+        # outputs of the unmodified reference CupyRetriever (cosine) with NumPy standing in for CuPy
+        c = np.load(os.path.join(GOLD, f"{name}_golden_cosine.npz"))
+        self.cos_Q = c["queries"]
+        self.cos_idx_fixed = c["idx_fixed"]
+        self.cos_scores_fixed = c["scores_fixed"]
+        self.cos_idx_var = c["idx_var"]
+        self.cos_texts = json.load(open(os.path.join(GOLD, f"{name}_golden_cosine_texts.json")))
 
 
 @pytest.fixture(scope="session", params=["short_facts", "squad"])

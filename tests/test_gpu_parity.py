@@ -183,6 +183,22 @@ def test_drop_in_classes_equal_reference_golden(golden):
     c.close()
 
 
+def test_cosine_equals_reference_cupy_class_golden(golden):
+    # the unmodified reference CupyRetriever (NumPy standing in for CuPy): indices identical,
+    # scores within 1e-5 relative, strings identical, variable k identical
+    Q, k = golden.cos_Q, golden.k
+    idx, sc, _ = run_case(golden.E, Q, k, "fp32", "cosine", 2, scale_exp=4)
+    assert (idx == golden.cos_idx_fixed).all()
+    assert np.allclose(sc, golden.cos_scores_fixed, rtol=1e-5, atol=0)
+    c = CupyRetriever(golden.E, golden.contexts)
+    assert c.batch_retrieve(Q, [k] * len(Q)) == golden.cos_texts
+    got = c.batch_retrieve(Q, golden.ks_var)
+    for row, exp in zip(got, golden.cos_idx_var):
+        assert row == [golden.contexts[i] for i in exp if i >= 0]
+    assert c.retrieve(Q[3], k) == golden.cos_texts[3]
+    c.close()
+
+
 def test_self_retrieval_kat_all_dtypes(golden):
     for dtype in ("bf16", "fp16", "fp32"):
         r = B200Retriever(golden.E, golden.contexts, dtype=dtype, metric="cosine")

@@ -46,6 +46,31 @@ def test_cosine_and_dot_rank_identically_on_unit_norm_corpora(golden):
     assert (np.abs(v_cos) <= 1.0).all()
 
 
+def test_cosine_oracle_matches_reference_cupy_class_golden(golden):
+    # goldens: the unmodified CupyRetriever (retriever.py:564-799) run with oracle/cupy_numpy_shim.py
+    idx, val = o.search(golden.cos_Q, golden.E, golden.k, "cosine")
+    assert (idx == golden.cos_idx_fixed).all()
+    assert np.array_equal(val, golden.cos_scores_fixed)        # same fp32 operations in the same order
+    assert not np.allclose(val, np.take_along_axis(golden.cos_Q @ golden.E.T, idx, axis=1), rtol=1e-2)
+    docs = [str(i) for i in range(len(golden.E))]
+    r = o.CupyRetrieverPort(golden.E, docs)
+    got = r.batch_retrieve(golden.cos_Q, golden.ks_var)
+    for row, exp in zip(got, golden.cos_idx_var):
+        assert [int(s) for s in row] == [int(x) for x in exp if x >= 0]
+    assert o.CupyRetrieverPort(golden.E, golden.contexts).batch_retrieve(
+        golden.cos_Q, [golden.k] * len(golden.cos_Q)) == golden.cos_texts
+
+
+def test_cupy_shim_runs_like_numpy():
+    from oracle import cupy_numpy_shim as cp
+    a = cp.asarray(np.array([[3.0, 1.0, 2.0]], dtype=np.float32))
+    assert isinstance(a @ a.T, cp.ndarray) and isinstance(a[0], cp.ndarray)
+    assert cp.argpartition(a[0], 1)[-2:].get().tolist() == [2, 0]       # full sort, like CuPy
+    assert cp.argsort(-a[0]).get().tolist() == [0, 2, 1]
+    assert type(cp.empty((2, 2), dtype=cp.int64).get()) is np.ndarray
+    assert float(cp.linalg.norm(a, axis=1, keepdims=True)[0, 0]) == pytest.approx(14 ** 0.5)
+
+
 def test_cupy_port_agrees_with_search(golden):
     docs = [str(i) for i in range(len(golden.E))]
     r = o.CupyRetrieverPort(golden.E, docs)
