@@ -155,6 +155,10 @@ RS_API int rs_get_stats(rs_index* ix, rs_stats* out);
 /* Launch plan the host would pick for a search (no device needed; used by the CPU tests):
  * out9 = {passes, queries_per_pass, bpad, ring_stages, q_resident, sub, nbuf, mma_m, chunks_per_stage}. */
 RS_API int rs_debug_plan(int32_t dim, int32_t dtype, int32_t B, int32_t k, int32_t query_terms, int32_t* out9);
+/* Timing experiments only: with RS_DEBUG_TS=1 in the environment the fused kernel stamps %globaltimer
+ * (ns) at 7 phase boundaries per CTA (entry, query prep done, first accumulator, last tile, arrival,
+ * all arrived, merged); out = uint64[n_ctas][8] of the last launch. */
+RS_API int rs_debug_timestamps(rs_index* ix, uint64_t* out, int32_t n_ctas);
 /* Durations (ms) of the last n fused score+select kernel launches, oldest first, from CUDA events
  * recorded on the launching stream around each launch (ring of 256); synchronises on them. */
 RS_API int rs_get_kernel_times(rs_index* ix, float* out_ms, int32_t n);

@@ -20,7 +20,7 @@ EXPORTS = (
     "rs_version", "rs_last_error", "rs_create", "rs_destroy", "rs_load_rows", "rs_fill_synthetic",
     "rs_finalize", "rs_search", "rs_search_device", "rs_merge_device", "rs_get_rows",
     "rs_get_norms", "rs_get_image", "rs_get_stats", "rs_get_kernel_times",
-    "rs_debug_plan", "rs_xchg_create", "rs_xchg_export", "rs_xchg_import", "rs_xchg_destroy", "rs_search_exchange",
+    "rs_debug_plan", "rs_debug_timestamps", "rs_xchg_create", "rs_xchg_export", "rs_xchg_import", "rs_xchg_destroy", "rs_search_exchange",
 )
 
 
@@ -80,6 +80,7 @@ def load() -> C.CDLL:
         "rs_merge_device": [i32, vp, vp, i32, i32, i32, i32, i64, i64, vp, vp, vp],
         "rs_get_kernel_times": [vp, vp, i32],
         "rs_debug_plan": [i32, i32, i32, i32, i32, vp],
+        "rs_debug_timestamps": [vp, vp, i32],
         "rs_xchg_create": [i32, i32, i32, i32, i32, C.POINTER(vp)],
         "rs_xchg_export": [vp, vp],
         "rs_xchg_import": [vp, i32, vp],
@@ -185,6 +186,12 @@ class Index:
     def kernel_times_ms(self, n: int) -> np.ndarray:
         out = np.empty(n, dtype=np.float32)
         check(self.lib.rs_get_kernel_times(self.h, out.ctypes.data, n), "rs_get_kernel_times")
+        return out
+
+    def debug_timestamps(self, n_ctas: int) -> np.ndarray:
+        """uint64[n_ctas, 8] %globaltimer stamps of the last fused launch (needs RS_DEBUG_TS=1)."""
+        out = np.zeros((n_ctas, 8), dtype=np.uint64)
+        check(self.lib.rs_debug_timestamps(self.h, out.ctypes.data, n_ctas), "rs_debug_timestamps")
         return out
 
     def stats(self) -> dict:

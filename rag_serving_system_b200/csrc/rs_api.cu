@@ -83,6 +83,9 @@ struct rs_index {
   void* pinned = nullptr;  // pinned host staging (queries in, results out, ingest chunks)
   size_t pinned_bytes = 0;
   cudaStream_t stream = nullptr;
+  unsigned int* sync = nullptr;      // device counters of the fused kernel's tail (arrivals, departures)
+  unsigned long long* debug_ts = nullptr;  // RS_DEBUG_TS=1: [grid][8] phase stamps of the last fused launch
+  unsigned int* err_flag = nullptr;  // mapped pinned word the kernel raises if its arrival wait times out
   // CUDA-event pairs around every fused-kernel launch (on the launching stream) so callers can
   // read the kernel's own duration without a profiler
   static constexpr int kEventRing = 256;
@@ -192,6 +195,9 @@ void free_all(rs_index* ix) {
   cudaFree(ix->out_idx_dev);
   cudaFree(ix->out_score_dev);
   cudaFree(ix->ingest_dev);
+  cudaFree(ix->sync);
+  cudaFree(ix->debug_ts);
+  if (ix->err_flag) cudaFreeHost(ix->err_flag);
   if (ix->pinned) cudaFreeHost(ix->pinned);
   for (auto& g : ix->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -216,7 +222,20 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   Plan pl;
   int rc = make_plan(ix, B, k, terms, &pl);
   if (rc != RS_OK) return rc;
-  const int grid = std::min(ix->sm_count, ix->n_tiles);
+  if (*reinterpret_cast<volatile unsigned int*>(ix->err_flag)) {
+    *ix->err_flag = 0;
+    cudaMemsetAsync(ix->sync, 0, 256, stream);
+    return fail(RS_E_CUDA, "a previous search timed out waiting for its own CTAs (device shared with another job?)");
+  }
+  const int n_work = std::min(ix->sm_count, ix->n_tiles);  // CTAs that own tiles = candidate lists per query
+  // single-launch search (default): query prep in the fused kernel's prologue (resident-Q plans) and the
+  // candidate merge (+ exchange) in its tail.  RS_INLINE_PREP=0 / RS_FUSED_TAIL=0 fall back to the
+  // separate query_prep_kernel / merge kernels.
+  const bool inline_prep = pl.q_resident && ix->cfg.dim <= 1024 && pl.bpad <= 32 && env_int("RS_INLINE_PREP", 1) != 0;
+  const int tail_cap = rs::fused_tail_smem_capacity(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms);
+  const bool fused_tail = env_int("RS_FUSED_TAIL", 1) != 0 &&
+                          rs::fused_tail_smem_bytes(n_work, k, xg ? xg->world : 1) <= (size_t)tail_cap;
+  const int grid = fused_tail ? std::max(n_work, std::min(pl.per_pass, ix->sm_count)) : n_work;
   ix->stats.grid = grid;
   ix->stats.stages = pl.stages;
   ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms);
@@ -239,9 +258,27 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   for (int pass = 0; pass < pl.passes; ++pass) {
     const int b0 = pass * pl.per_pass;
     const int nb = std::min(pl.per_pass, B - b0);
-    RS_CUDA(rs::launch_query_prep(q_dev + (size_t)b0 * ix->cfg.dim, nb, ix->cfg.dim, pl.bpad, ix->plane_dtype, terms,
-                                  ix->planes == 2 ? ix->cfg.scale_exp : 0, ix->qimg, ix->qnorm, ix->qscale, stream));
+    const int corpus_scale_exp = ix->planes == 2 ? ix->cfg.scale_exp : 0;
+    if (!inline_prep)
+      RS_CUDA(rs::launch_query_prep(q_dev + (size_t)b0 * ix->cfg.dim, nb, ix->cfg.dim, pl.bpad, ix->plane_dtype, terms,
+                                    corpus_scale_exp, ix->qimg, ix->qnorm, ix->qscale, stream));
     rs::SearchParams p;
+    memset(&p, 0, sizeof(p));
+    p.q_f32 = q_dev + (size_t)b0 * ix->cfg.dim;
+    p.inline_prep = inline_prep ? 1 : 0;
+    p.corpus_scale_exp = corpus_scale_exp;
+    p.n_work = n_work;
+    p.tail_mode = fused_tail ? (xg ? 2 : 1) : 0;
+    p.sync = ix->sync;
+    p.err_flag = ix->err_flag;
+    p.out_score = out_score + (size_t)b0 * k;
+    p.out_idx = out_idx + (size_t)b0 * k;
+    p.idx_offset = ix->cfg.row_offset;
+    if (env_int("RS_DEBUG_TS", 0)) {
+      if (!ix->debug_ts) RS_CUDA(cudaMalloc(&ix->debug_ts, (size_t)ix->sm_count * 8 * sizeof(unsigned long long)));
+      RS_CUDA(cudaMemsetAsync(ix->debug_ts, 0, (size_t)ix->sm_count * 8 * sizeof(unsigned long long), stream));
+      p.debug_ts = ix->debug_ts;
+    }
     p.corpus = ix->corpus;
     p.qimg = ix->qimg;
     p.qnorm = ix->qnorm;
@@ -269,22 +306,9 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.mma_m = pl.mma_m;
     p.debug_flags = env_int("RS_DEBUG_FLAGS", 0);
     p.lo_coef = ix->plane_dtype == RS_DTYPE_FP16 ? ldexpf(1.0f, -RS_FP16_SPLIT_SHIFT) : 1.0f;
-    if (!ix->record_events || env_int("RS_NO_EVENTS", 0)) {
-      RS_CUDA(rs::launch_fused_search(p, grid, stream));
-    } else {
-      const int slot = (int)(ix->ev_count % rs_index::kEventRing);
-      RS_CUDA(cudaEventRecord(ix->ev_beg[slot], stream));
-      RS_CUDA(rs::launch_fused_search(p, grid, stream));
-      RS_CUDA(cudaEventRecord(ix->ev_end[slot], stream));
-      ++ix->ev_count;
-    }
-    if (!xg) {
-      RS_CUDA(rs::launch_merge_i32(ix->cand_score, ix->cand_idx, grid, nb, k, k, ix->cfg.row_offset,
-                                   out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, stream));
-    } else {
-      // local merge + exchange + final merge in one kernel: rows go straight into every GPU's buffer
-      rs::ExchangeArgs ea;
-      memset(&ea, 0, sizeof(ea));
+    rs::ExchangeArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    if (xg) {
       ea.world = xg->world;
       ea.q0 = b0;
       ea.epoch = epoch;
@@ -302,10 +326,28 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
       ea.local_score = reinterpret_cast<const float*>(base + (size_t)B * k * 8);
       ea.idx_list_stride = (long long)(xg->slot_bytes / 8);
       ea.score_list_stride = (long long)(xg->slot_bytes / 4);
-      RS_CUDA(rs::launch_exchange_merge(ix->cand_score, ix->cand_idx, grid, nb, k, ix->cfg.row_offset,
-                                        out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, ea, stream));
     }
-    ix->stats.launches += 3;
+    p.x = ea;
+    if (!ix->record_events || env_int("RS_NO_EVENTS", 0)) {
+      RS_CUDA(rs::launch_fused_search(p, grid, stream));
+    } else {
+      const int slot = (int)(ix->ev_count % rs_index::kEventRing);
+      RS_CUDA(cudaEventRecord(ix->ev_beg[slot], stream));
+      RS_CUDA(rs::launch_fused_search(p, grid, stream));
+      RS_CUDA(cudaEventRecord(ix->ev_end[slot], stream));
+      ++ix->ev_count;
+    }
+    if (!fused_tail) {
+      if (!xg) {
+        RS_CUDA(rs::launch_merge_i32(ix->cand_score, ix->cand_idx, n_work, nb, k, k, ix->cfg.row_offset,
+                                     out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, stream));
+      } else {
+        // local merge + exchange + final merge in one kernel: rows go straight into every GPU's buffer
+        RS_CUDA(rs::launch_exchange_merge(ix->cand_score, ix->cand_idx, n_work, nb, k, ix->cfg.row_offset,
+                                          out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, ea, stream));
+      }
+    }
+    ix->stats.launches += 1 + (inline_prep ? 0 : 1) + (fused_tail ? 0 : 1);
     ix->stats.bytes_streamed += (int64_t)ix->corpus_bytes;
   }
   ix->stats.total_launches += ix->stats.launches;
@@ -395,6 +437,10 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   RS_ALLOC(cudaMalloc(&ix->out_score_dev, out_elems * sizeof(float)));
   RS_ALLOC(cudaMalloc(&ix->ingest_dev, kIngestChunkBytes));
   RS_ALLOC(cudaMallocHost(&ix->pinned, ix->pinned_bytes));
+  RS_ALLOC(cudaMalloc(&ix->sync, 256));
+  RS_ALLOC(cudaMemsetAsync(ix->sync, 0, 256, ix->stream));
+  RS_ALLOC(cudaHostAlloc(&ix->err_flag, 64, cudaHostAllocMapped));
+  *ix->err_flag = 0;
   for (int i = 0; i < 2; ++i) RS_ALLOC(cudaEventCreateWithFlags(&ix->ingest_done[i], cudaEventDisableTiming));
   for (int i = 0; i < rs_index::kEventRing; ++i) {
     RS_ALLOC(cudaEventCreate(&ix->ev_beg[i]));
@@ -722,6 +768,16 @@ RS_API int rs_get_kernel_times(rs_index* ix, float* out_ms, int32_t n) {
     RS_CUDA(cudaEventSynchronize(ix->ev_end[slot]));
     RS_CUDA(cudaEventElapsedTime(&out_ms[i], ix->ev_beg[slot], ix->ev_end[slot]));
   }
+  return RS_OK;
+}
+
+RS_API int rs_debug_timestamps(rs_index* ix, uint64_t* out, int32_t n_ctas) {
+  if (!ix || !out || n_ctas <= 0 || n_ctas > ix->sm_count) return fail(RS_E_INVALID, "bad argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  if (!ix->debug_ts) return fail(RS_E_STATE, "no stamps recorded: run a search with RS_DEBUG_TS=1 first");
+  RS_CUDA(cudaDeviceSynchronize());
+  RS_CUDA(cudaMemcpy(out, ix->debug_ts, (size_t)n_ctas * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return RS_OK;
 }
 

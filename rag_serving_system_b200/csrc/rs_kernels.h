@@ -5,6 +5,23 @@
 
 namespace rs {
 
+// Arguments of the fused merge + exchange kernel (multi-GPU candidate exchange over peer memory).
+constexpr int kMaxPeers = 8;
+struct ExchangeArgs {
+  int world;                            // GPUs taking part
+  int q0;                               // first query of this pass inside the search's batch
+  unsigned int epoch;                   // search counter; flags carry it
+  long long* dest_idx[kMaxPeers];       // GPU g: this rank's slot in g's exchange buffer, idx block  [B][k]
+  float* dest_score[kMaxPeers];         //        ... score block [B][k]
+  unsigned int* dest_flag[kMaxPeers];   // GPU g: flags[parity][this rank][0..max_batch)
+  const unsigned int* wait_flags;       // local flags[parity][0][0]; rank stride = flag_stride
+  int flag_stride;                      // = max_batch
+  const long long* local_idx;           // local exchange buffer, slot of rank 0 (idx block)
+  const float* local_score;             //                                      (score block)
+  long long idx_list_stride;            // elements between consecutive ranks' slots
+  long long score_list_stride;
+};
+
 struct SearchParams {
   const uint8_t* corpus;             // tiled corpus image (rs_layout.h)
   const uint8_t* qimg;               // Q image: terms x KC blocks of bpad rows
@@ -31,25 +48,21 @@ struct SearchParams {
   int sub;                           // 128-document tiles per supertile (share one Q k-chunk load)
   int mma_m;                         // 128, or 64 when bpad <= 64 (half the tensor work / operand reads)
   int nbuf;                          // TMEM accumulator buffers (1 or 2); nbuf*sub*NACC*128 <= 512 columns
-  int debug_flags;                   // timing experiments only (RS_DEBUG_FLAGS): 1 = skip MMAs, 2 = skip epilogue
+  int debug_flags;                   // timing experiments only (RS_DEBUG_FLAGS): 1 = skip MMAs, 2 = skip epilogue, 4 = skip tail merge, 8 = skip inline prep
   float lo_coef;                     // weight of the low-order accumulator (2^-11 for fp16 terms, 1 for bf16)
-};
-
-// Arguments of the fused merge + exchange kernel (multi-GPU candidate exchange over peer memory).
-constexpr int kMaxPeers = 8;
-struct ExchangeArgs {
-  int world;                            // GPUs taking part
-  int q0;                               // first query of this pass inside the search's batch
-  unsigned int epoch;                   // search counter; flags carry it
-  long long* dest_idx[kMaxPeers];       // GPU g: this rank's slot in g's exchange buffer, idx block  [B][k]
-  float* dest_score[kMaxPeers];         //        ... score block [B][k]
-  unsigned int* dest_flag[kMaxPeers];   // GPU g: flags[parity][this rank][0..max_batch)
-  const unsigned int* wait_flags;       // local flags[parity][0][0]; rank stride = flag_stride
-  int flag_stride;                      // = max_batch
-  const long long* local_idx;           // local exchange buffer, slot of rank 0 (idx block)
-  const float* local_score;             //                                      (score block)
-  long long idx_list_stride;            // elements between consecutive ranks' slots
-  long long score_list_stride;
+  // ---- single-launch search: query prep in the prologue, candidate merge (+ exchange) in the tail
+  const float* q_f32;                // fp32 queries [n_queries][D]; read when inline_prep
+  int inline_prep;                   // 1: the CTA builds its own resident Q image (no query_prep_kernel launch)
+  int corpus_scale_exp;              // power-of-two pre-scale of an fp32 corpus (folded into qscale)
+  int n_work;                        // CTAs that own tiles and write candidate lists (= lists per query)
+  int tail_mode;                     // 0: candidates only; 1: + in-kernel merge; 2: + peer exchange and final merge
+  unsigned int* sync;                // [0] arrivals of worker CTAs, [1] departures of merging CTAs
+  unsigned int* err_flag;            // mapped host word, set to 1 if the arrival wait timed out
+  float* out_score;                  // tail_mode != 0: final [n_queries][k]
+  long long* out_idx;
+  long long idx_offset;              // global index of this shard's row 0
+  ExchangeArgs x;                    // tail_mode == 2
+  unsigned long long* debug_ts;      // null, or [grid][8] globaltimer stamps of the kernel's phases (RS_DEBUG_TS=1)
 };
 
 cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dtype, int terms, int corpus_scale_exp,
@@ -57,6 +70,8 @@ cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dt
 cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t stream);
 int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages);
 int fused_reg_k();
+size_t fused_tail_smem_bytes(int n_lists, int k, int world);
+int fused_tail_smem_capacity(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages);
 cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int kc, int k,
                              long long idx_offset, float* out_score, long long* out_idx, cudaStream_t stream);
 cudaError_t launch_exchange_merge(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int k,

@@ -38,6 +38,45 @@ __device__ __forceinline__ float bf16_to_f32(uint16_t b) { return __uint_as_floa
 __device__ __forceinline__ uint16_t f32_to_f16_rn(float x) { return __half_as_ushort(__float2half_rn(x)); }
 __device__ __forceinline__ float f16_to_f32(uint16_t b) { return __half2float(__ushort_as_half(b)); }
 
+// Per-query power-of-two pre-scale: brings max|q| into [1,2) so the fp16 terms stay in range.  Exact
+// (a power of two), so it never changes a result; exponents are clamped to what a normal float holds.
+struct QScale {
+  float up, down;  // 2^e, 2^-e
+  int e;
+};
+__device__ __forceinline__ QScale q_scale_from_max(float mx) {
+  QScale s;
+  s.e = 0;
+  if (mx > 0.f && mx < CUDART_INF_F) s.e = max(-126, min(126, 127 - (int)((__float_as_uint(mx) >> 23) & 0xffu)));
+  s.up = __uint_as_float((uint32_t)(127 + s.e) << 23);
+  s.down = __uint_as_float((uint32_t)(127 - s.e) << 23);
+  return s;
+}
+// One query element -> its tensor-core term(s) in the storage type + the value they represent.
+__device__ __forceinline__ void q_convert(float x, const QScale& sc, int dtype, int terms, uint16_t& t0, uint16_t& t1,
+                                          float& rep) {
+  const float xs = x * sc.up;
+  t1 = 0;
+  if (dtype == RS_DTYPE_BF16) {
+    t0 = f32_to_bf16_rn(xs);
+    const float h = bf16_to_f32(t0);
+    rep = h;
+    if (terms == 2) {
+      t1 = f32_to_bf16_rn(xs - h);
+      rep = h + bf16_to_f32(t1);
+    }
+  } else {
+    t0 = f32_to_f16_rn(xs);
+    const float h = f16_to_f32(t0);
+    rep = h;
+    if (terms == 2) {
+      t1 = f32_to_f16_rn((xs - h) * (float)(1 << RS_FP16_SPLIT_SHIFT));
+      rep = h + f16_to_f32(t1) * (1.0f / (float)(1 << RS_FP16_SPLIT_SHIFT));
+    }
+  }
+  rep *= sc.down;
+}
+
 // One CTA per (padded) query row.  Writes terms x KC blocks of the Q image, the L2 norm of the
 // represented query (retriever.py:602) and the power-of-two factor that undoes the scaling.
 __global__ void __launch_bounds__(256) query_prep_kernel(const float* __restrict__ q, int B, int D, int bpad,
@@ -47,7 +86,6 @@ __global__ void __launch_bounds__(256) query_prep_kernel(const float* __restrict
   const int row = blockIdx.x;
   const int kc_count = D / RS_KCHUNK_ELEMS;
   __shared__ float red[256];
-  __shared__ int s_exp;
   const bool live = row < B;
   // 1. max |q| -> per-query power-of-two scale (keeps fp16 terms in range; exact)
   float mx = 0.f;
@@ -59,39 +97,15 @@ __global__ void __launch_bounds__(256) query_prep_kernel(const float* __restrict
     if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    float m = red[0];
-    int e = 0;
-    if (m > 0.f && m < CUDART_INF_F) e = -ilogbf(m);  // scaled max in [1,2)
-    s_exp = e;
-  }
+  const QScale qsc = q_scale_from_max(red[0]);
   __syncthreads();
-  const int e = s_exp;
   // 2. split into terms, write swizzled, accumulate the norm of the represented value
   float ss = 0.f;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float x = live ? q[(size_t)row * D + c] : 0.f;
-    float xs = ldexpf(x, e);
-    uint16_t t0, t1 = 0;
+    const float x = live ? q[(size_t)row * D + c] : 0.f;
+    uint16_t t0, t1;
     float rep;
-    if (dtype == RS_DTYPE_BF16) {
-      t0 = f32_to_bf16_rn(xs);
-      float h = bf16_to_f32(t0);
-      rep = h;
-      if (terms == 2) {
-        t1 = f32_to_bf16_rn(xs - h);
-        rep = h + bf16_to_f32(t1);
-      }
-    } else {
-      t0 = f32_to_f16_rn(xs);
-      float h = f16_to_f32(t0);
-      rep = h;
-      if (terms == 2) {
-        t1 = f32_to_f16_rn(ldexpf(xs - h, RS_FP16_SPLIT_SHIFT));
-        rep = h + ldexpf(f16_to_f32(t1), -RS_FP16_SPLIT_SHIFT);
-      }
-    }
-    rep = ldexpf(rep, -e);
+    q_convert(x, qsc, dtype, terms, t0, t1, rep);
     ss += rep * rep;
     const int kc = c >> 6;
     const uint32_t off = rs_block_offset((uint32_t)row, (uint32_t)(c & 63));
@@ -107,7 +121,158 @@ __global__ void __launch_bounds__(256) query_prep_kernel(const float* __restrict
   }
   if (threadIdx.x == 0) {
     qnorm[row] = sqrtf(red[0]);
-    qscale[row] = ldexpf(1.0f, -(e + corpus_scale_exp));
+    qscale[row] = ldexpf(1.0f, -(qsc.e + corpus_scale_exp));
+  }
+}
+
+// ---- in-kernel query prep (resident-Q mode) ------------------------------------------------------
+// Four consecutive query elements -> packed 16-bit terms (hardware cvt.rn, same round-to-nearest-even as
+// f32_to_bf16_rn / __float2half_rn for finite values) + the sum of squares of the represented values.
+// Compile-time dtype/terms keep this run-once code compact (it executes from a cold instruction cache).
+template <bool BF16, bool TWO>
+__device__ __forceinline__ void q_convert4(const float4 x, const float up, const float down, uint2& t0, uint2& t1,
+                                           float& ss) {
+  const float xs[4] = {x.x * up, x.y * up, x.z * up, x.w * up};
+  uint32_t p[2], l[2] = {0u, 0u};
+  float h[4], rep[4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (BF16) {
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p[j]) : "f"(xs[2 * j + 1]), "f"(xs[2 * j]));
+      h[2 * j] = __uint_as_float(p[j] << 16);
+      h[2 * j + 1] = __uint_as_float(p[j] & 0xffff0000u);
+    } else {
+      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p[j]) : "f"(xs[2 * j + 1]), "f"(xs[2 * j]));
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&p[j]));
+      h[2 * j] = f.x;
+      h[2 * j + 1] = f.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) rep[j] = h[j];
+  if (TWO) {
+    constexpr float kUp = (float)(1 << RS_FP16_SPLIT_SHIFT), kDown = 1.0f / (float)(1 << RS_FP16_SPLIT_SHIFT);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float d0 = xs[2 * j] - h[2 * j], d1 = xs[2 * j + 1] - h[2 * j + 1];
+      if (BF16) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l[j]) : "f"(d1), "f"(d0));
+        rep[2 * j] += __uint_as_float(l[j] << 16);
+        rep[2 * j + 1] += __uint_as_float(l[j] & 0xffff0000u);
+      } else {
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l[j]) : "f"(d1 * kUp), "f"(d0 * kUp));
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&l[j]));
+        rep[2 * j] += f.x * kDown;
+        rep[2 * j + 1] += f.y * kDown;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float r = rep[j] * down;
+    ss = fmaf(r, r, ss);
+  }
+  t0 = make_uint2(p[0], p[1]);
+  t1 = make_uint2(l[0], l[1]);
+}
+
+// One warp preps the query rows wid, wid+4, ... (at most 8: bpad <= 32) of the resident Q image.
+// The work is K-MAJOR: columns are processed in groups of 256 (4 k-chunks) across all of the warp's
+// rows, and the warp arrives on the group's mbarrier as soon as its part of the group is in shared
+// memory, so the MMA issuer starts on the first tile's leading k-chunks while later groups are still
+// being converted - the document stream (already running) is never stalled behind the whole prep.
+// bf16 terms need no range pre-scale (bf16 has fp32's exponent range and a power-of-two scale does not
+// change the represented value), so that type converts in a single pass over global memory; fp16
+// terms first take each row's max |q| (pass A) for the power-of-two scale.  Writes the L2 norm of the
+// represented query (retriever.py:602) and the factor that undoes the scaling; values are identical
+// to query_prep_kernel's.  Rows >= n_queries are zero-filled.
+constexpr int kPrepGroupCols = 256;  // columns per readiness group = 4 k-chunks
+template <bool BF16, bool TWO>
+__device__ __noinline__ void prep_queries_warp(const float* __restrict__ q, int wid, int n_queries, int D, int bpad,
+                                               int corpus_scale_exp, uint8_t* qimg_smem, float* s_qnorm,
+                                               float* s_qscale, uint32_t group_bar0, int lane) {
+  const uint32_t blk = (uint32_t)bpad * RS_KCHUNK_BYTES;
+  const uint32_t term1 = (uint32_t)(D / RS_KCHUNK_ELEMS) * blk;
+  float up[8], down[8];
+  int e[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    up[i] = down[i] = 1.f;
+    e[i] = 0;
+  }
+  if (!BF16) {
+    // pass A: row maxima, two rows' loads in flight together
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      float m[2] = {0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int row = wid + 4 * (i + r);
+        if (row < n_queries) {
+#pragma unroll 8
+          for (int c = lane * 4; c < D; c += 128) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(q + (size_t)row * D + c));
+            m[r] = fmaxf(m[r], fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const QScale sc = q_scale_from_max(__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m[r]))));
+        up[i + r] = sc.up;
+        down[i + r] = sc.down;
+        e[i + r] = sc.e;
+      }
+    }
+  }
+  float ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int n_groups = (D + kPrepGroupCols - 1) / kPrepGroupCols;
+  // float4 f = lane + 32*j (j = 0,1) of a group covers columns g*256 + 4f: k-chunk 4g + lane/16 + 2j, and
+  // 8 contiguous bytes inside the block at a lane-constant offset
+  const uint32_t lane_col = (uint32_t)((lane * 4) & 63);
+#pragma unroll 1
+  for (int g = 0; g < n_groups; ++g) {
+    float4 v[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = wid + 4 * i;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = g * kPrepGroupCols + 4 * (lane + 32 * j);
+        v[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < n_queries && c < D) v[i][j] = __ldg(reinterpret_cast<const float4*>(q + (size_t)row * D + c));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = wid + 4 * i;
+      if (row < bpad) {
+        const uint32_t off = rs_block_offset((uint32_t)row, lane_col) + (uint32_t)(lane >> 4) * blk;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (g * kPrepGroupCols + 4 * (lane + 32 * j) < D) {
+            uint2 t0, t1;
+            q_convert4<BF16, TWO>(v[i][j], up[i], down[i], t0, t1, ss[i]);
+            uint8_t* dst = qimg_smem + off + (uint32_t)(4 * g + 2 * j) * blk;
+            *reinterpret_cast<uint2*>(dst) = t0;
+            if (TWO) *reinterpret_cast<uint2*>(dst + term1) = t1;
+          }
+        }
+      }
+    }
+    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+    __syncwarp();
+    if (lane == 0) mbar_arrive(group_bar0 + 8u * (uint32_t)g);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], o);
+    const int row = wid + 4 * i;
+    if (lane == 0 && row < bpad) {
+      s_qnorm[row] = sqrtf(ss[i]);
+      s_qscale[row] = ldexpf(1.0f, -(e[i] + corpus_scale_exp));
+    }
   }
 }
 
@@ -136,7 +301,8 @@ __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, in
                          : (uint32_t)qstages * cps * bpad * RS_KCHUNK_BYTES;
   m.stage_off = m.q_bytes;  // multiple of 1024 because bpad % 8 == 0
   m.bar_off = m.stage_off + (uint32_t)stages * (uint32_t)cps * RS_BLOCK_BYTES;
-  m.dump_off = m.bar_off + 1024;                       // rare-path chunk dump: 32 columns x live rows, fp32
+  m.dump_off = m.bar_off + 2048;                       // [bar_off, +1 KiB) barriers, then qnorm[128], qscale[128];
+                                                       // dump = rare-path chunk: 32 columns x live rows, fp32
   m.list_off = m.dump_off + (uint32_t)((bpad + 31) / 32 * 32) * 128u;   // whole warps of 32 (M=128) or 2x16 (M=64) rows
   m.total = m.list_off + (reglist ? 0u : (uint32_t)(k + kBufC) * (uint32_t)bpad * 8u);
   return m;
@@ -233,6 +399,350 @@ __device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs,
   return Ls[(k - 1) * stride + qrow];
 }
 
+// ------------------------------------------------------------------------------------------
+// merge of sorted candidate lists: one warp per query, each lane walks lists lane, lane+32, ...
+// Ordering everywhere is (score desc, index asc); index < 0 is padding and only occurs at the end
+// of a list.  STAGED: the query's candidates are first copied (coalesced) into shared memory so
+// the k selection rounds run at shared-memory latency instead of k dependent global round trips.
+// ------------------------------------------------------------------------------------------
+constexpr int kMergeMaxOwn = 8;  // up to 256 lists
+
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int kMergeThreads = 128;  // four warps stage one query's candidates; warp 0 runs the k rounds
+
+// Copy one query's candidate lists into shared memory.  Element (list l, slot j) sits at
+// l*list_stride + qoff + j; the loads are issued four deep so the L2 round trips overlap.
+template <typename IdxT>
+__device__ __forceinline__ void stage_lists(const float* __restrict__ cand_score, const IdxT* __restrict__ cand_idx,
+                                            int n_lists, int kc, long long score_list_stride,
+                                            long long idx_list_stride, size_t qoff, IdxT* s_idx, float* s_score,
+                                            const int nthr) {
+  const int total = n_lists * kc;
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * nthr) {
+    IdxT ti[4];
+    float ts[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + nthr * u;
+      if (e < total) {
+        const int l = e / kc, j = e - l * kc;
+        ti[u] = __ldcg(cand_idx + (size_t)l * idx_list_stride + qoff + j);
+        ts[u] = __ldcg(cand_score + (size_t)l * score_list_stride + qoff + j);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + nthr * u;
+      if (e < total) {
+        s_idx[e] = ti[u];
+        s_score[e] = ts[u];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// k selection rounds by ONE warp over n_lists sorted lists (score desc, index asc; index < 0 is
+// padding at the end of a list).  Every list head is kept as a sortable pair: ks = order-preserving
+// image of the score (0 = padding / exhausted), ki = ~index (larger = lower index).  The warp's best
+// head is found with three redux.sync steps (score, index high word, index low word).  `load(l, j,
+// score&, idx&)` reads element j of list l.  Writes k rows to res_* (padding: -1 / -inf).
+template <typename Load>
+__device__ __forceinline__ void select_rounds(Load load, int n_lists, int kc, int k, long long idx_offset,
+                                              float* res_s, long long* res_i, int lane) {
+  unsigned int ks[kMergeMaxOwn];
+  unsigned long long ki[kMergeMaxOwn];
+  int head[kMergeMaxOwn];
+  auto read_head = [&](int i) {
+    const int l = lane + 32 * i;
+    ks[i] = 0u;
+    ki[i] = 0ull;
+    if (l < n_lists && head[i] < kc) {
+      float sc;
+      long long id;
+      load(l, head[i], sc, id);
+      if (id >= 0) {
+        unsigned int u = __float_as_uint(sc);
+        ks[i] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        ki[i] = ~(unsigned long long)id;
+      }
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < kMergeMaxOwn; ++i) {
+    head[i] = 0;
+    read_head(i);
+  }
+  int r = 0;
+  for (; r < k; ++r) {
+    unsigned int bs = 0u;  // this lane's best head
+    unsigned long long bi = 0ull;
+    int bown = 0;
+#pragma unroll
+    for (int i = 0; i < kMergeMaxOwn; ++i)
+      if (ks[i] > bs || (ks[i] == bs && ki[i] > bi)) {
+        bs = ks[i];
+        bi = ki[i];
+        bown = i;
+      }
+    const unsigned int m0 = __reduce_max_sync(0xffffffffu, bs);
+    if (m0 == 0u) break;  // every list exhausted: the rest is padding
+    bool mine = bs == m0;
+    const unsigned int m1 = __reduce_max_sync(0xffffffffu, mine ? (unsigned int)(bi >> 32) : 0u);
+    mine = mine && (unsigned int)(bi >> 32) == m1;
+    const unsigned int m2 = __reduce_max_sync(0xffffffffu, mine ? (unsigned int)bi : 0u);
+    mine = mine && (unsigned int)bi == m2;
+    if (mine) {  // exactly one lane when indices are unique
+      float sc;
+      long long id;
+      load(lane + 32 * bown, head[bown], sc, id);
+      res_s[r] = sc;
+      res_i[r] = id + idx_offset;
+#pragma unroll
+      for (int i = 0; i < kMergeMaxOwn; ++i)
+        if (i == bown) {
+          ++head[i];
+          read_head(i);
+        }
+    }
+  }
+  __syncwarp();
+  for (int rr = r + lane; rr < k; rr += 32) {
+    res_s[rr] = -CUDART_INF_F;
+    res_i[rr] = -1;
+  }
+  __syncwarp();
+}
+
+
+__device__ __forceinline__ void stamp(unsigned long long* ts, int slot) {
+  if (ts) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    ts[(size_t)blockIdx.x * 8 + slot] = t;
+  }
+}
+// Per-query shared-memory workspace of a merge: result row (k indices + k scores) then the staged lists.
+struct MergeSmem {
+  long long* res_i;
+  float* res_s;
+  int* slot;  // parallel selection: the (at most k) lists whose heads rank among the k best heads
+  uint8_t* stage;
+};
+__host__ __device__ inline size_t merge_res_bytes(int k) {  // k results (8 + 4 B) + max(k, kMaxPeers) list slots
+  return ((size_t)k * 12 + (size_t)(k > kMaxPeers ? k : kMaxPeers) * 4 + 15) & ~size_t(15);
+}
+__device__ __forceinline__ MergeSmem merge_smem_at(uint8_t* base, int k) {
+  MergeSmem m;
+  m.res_i = reinterpret_cast<long long*>(base);
+  m.res_s = reinterpret_cast<float*>(m.res_i + k);
+  m.slot = reinterpret_cast<int*>(m.res_s + k);
+  m.stage = base + merge_res_bytes(k);
+  return m;
+}
+
+// ---- parallel selection for k <= 16 (every thread of the CTA takes part; no sequential rounds) -------
+// The global top-k of sorted lists can only come from the lists whose HEAD is among the k best heads.
+//   1. one thread per list ranks its head among all heads (brute force over n_lists <= 256 keys)
+//      and the k best lists are written to slot[rank]
+//   2. one thread per element of those <= k lists computes its final rank = position in its own list
+//      + number of better elements in each other active list (linear scan, stops once rank >= k)
+//      and writes itself to res[rank].
+// Keys are unique (every document sits in exactly one list), so ranks never collide.
+constexpr int kParMaxK = 16;
+
+// sortable 64-bit key of a (score, local row id >= 0) pair: larger = better (score desc, id asc); 0 = padding
+__device__ __forceinline__ unsigned long long pack_key(float sc, int id) {
+  const unsigned int u = __float_as_uint(sc);
+  const unsigned int ks = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)ks << 32) | (unsigned int)(0x7fffffff - id);
+}
+__device__ __forceinline__ void unpack_key(unsigned long long key, float& sc, int& id) {
+  const unsigned int ks = (unsigned int)(key >> 32);
+  sc = __uint_as_float((ks & 0x80000000u) ? (ks & 0x7fffffffu) : ~ks);
+  id = 0x7fffffff - (int)(unsigned int)key;
+}
+
+// stage one query's per-CTA lists (contiguous [list][kc] scores / int32 ids at qoff) as packed keys
+__device__ __forceinline__ void stage_keys(const float* __restrict__ cand_score, const int* __restrict__ cand_idx,
+                                           int total, size_t qoff, unsigned long long* s_key, const int nthr) {
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * nthr) {
+    int ti[4];
+    float ts[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + nthr * u;
+      if (e < total) {
+        ti[u] = __ldcg(cand_idx + qoff + e);
+        ts[u] = __ldcg(cand_score + qoff + e);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + nthr * u;
+      if (e < total) s_key[e] = ti[u] < 0 ? 0ull : pack_key(ts[u], ti[u]);
+    }
+  }
+  __syncthreads();
+}
+
+// step 2 of the parallel selection over the lists named in slot[0..n_slots) (-1 = unused slot).
+// valid(pos), better(pos_a, pos_b), emit(rank, pos) work on staged element positions l*kc + j.
+template <typename Valid, typename Better, typename Emit>
+__device__ __forceinline__ void rank_active_lists(const int* slot, int n_slots, int kc, int k, Valid valid, Better better,
+                                                  Emit emit, const int nthr) {
+  for (int e = threadIdx.x; e < n_slots * kc; e += nthr) {
+    const int a = e / kc, j = e - a * kc;
+    const int l = slot[a];
+    if (l < 0) continue;
+    const int pe = l * kc + j;
+    if (!valid(pe)) continue;
+    int rank = j;
+    for (int b = 0; b < n_slots && rank < k; ++b) {
+      const int lb = slot[b];
+      if (lb < 0 || b == a) continue;
+      int c = 0;
+      while (c < kc && rank + c < k && valid(lb * kc + c) && better(lb * kc + c, pe)) ++c;
+      rank += c;
+    }
+    if (rank < k) emit(rank, pe);
+  }
+}
+
+// local merge of packed keys: n_lists lists of kc keys -> res (k rows, padded with -1 / -inf)
+__device__ __forceinline__ void select_parallel_keys(const unsigned long long* s_key, int n_lists, int kc, int k,
+                                                     long long idx_offset, const MergeSmem& m, const int nthr) {
+  for (int j = threadIdx.x; j < k; j += nthr) {
+    m.res_s[j] = -CUDART_INF_F;
+    m.res_i[j] = -1;
+    m.slot[j] = -1;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_lists; t += nthr) {
+    const unsigned long long mine = s_key[t * kc];
+    if (mine != 0ull) {
+      int rank = 0;
+#pragma unroll 4
+      for (int u = 0; u < n_lists; ++u) rank += s_key[u * kc] > mine ? 1 : 0;
+      if (rank < k) m.slot[rank] = t;
+    }
+  }
+  __syncthreads();
+  rank_active_lists(
+      m.slot, k, kc, k, [&](int pos) { return s_key[pos] != 0ull; },
+      [&](int a, int b) { return s_key[a] > s_key[b]; },
+      [&](int rank, int pos) {
+        float sc;
+        int id;
+        unpack_key(s_key[pos], sc, id);
+        m.res_s[rank] = sc;
+        m.res_i[rank] = (long long)id + idx_offset;
+      },
+      nthr);
+  __syncthreads();
+}
+
+// Local merge of one query: this GPU's per-CTA lists ([query][cta][k] layout, local int32 row ids)
+// -> m.res_* (global indices).  Called by the whole CTA; warp 0 runs the rounds.  Ends with a barrier.
+__device__ __forceinline__ void merge_query_local(const float* __restrict__ cand_score, const int* __restrict__ cand_idx,
+                                                  int n_lists, int k, long long idx_offset, int q, const MergeSmem& m,
+                                                  int nthr, unsigned long long* ts = nullptr) {
+  if (k <= kParMaxK) {
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(m.stage);
+    stage_keys(cand_score, cand_idx, n_lists * k, (size_t)q * n_lists * k, s_key, nthr);
+    if (threadIdx.x == 0) stamp(ts, 2);  // lists staged
+    select_parallel_keys(s_key, n_lists, k, k, idx_offset, m, nthr);
+    if (threadIdx.x == 0) stamp(ts, 3);  // selected
+    return;
+  }
+  int* s_idx = reinterpret_cast<int*>(m.stage);
+  float* s_score = reinterpret_cast<float*>(m.stage + (size_t)n_lists * k * sizeof(int));
+  stage_lists<int>(cand_score, cand_idx, n_lists, k, k, k, (size_t)q * n_lists * k, s_idx, s_score, nthr);
+  if (threadIdx.x == 0) stamp(ts, 2);  // lists staged
+  if (threadIdx.x < 32) {
+    auto load = [&](int l, int j, float& sc, long long& id) {
+      sc = s_score[l * k + j];
+      id = (long long)s_idx[l * k + j];
+    };
+    select_rounds(load, n_lists, k, k, idx_offset, m.res_s, m.res_i, threadIdx.x & 31);
+  }
+  if (threadIdx.x == 0) stamp(ts, 3);  // rounds done
+  __syncthreads();
+}
+
+// Candidate exchange + final merge of one query (multi-GPU): store the local row (m.res_*) into every
+// GPU's exchange buffer through peer pointers (NVLink), raise this rank's per-query flag there with
+// the search epoch, wait until every rank's flag for this query shows the epoch, then merge the
+// world lists from the local exchange buffer back into m.res_*.  A CTA only ever waits for the CTAs
+// of the same query on other GPUs.  Buffers are double-buffered by epoch parity (host side).
+__device__ __forceinline__ void exchange_query(const ExchangeArgs& x, int q, int k, const MergeSmem& m, int nthr) {
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    const size_t qg = (size_t)(x.q0 + q) * k;
+    for (int e = lane; e < k * x.world; e += 32) {
+      const int g = e / k, j = e - g * k;
+      x.dest_score[g][qg + j] = m.res_s[j];
+      x.dest_idx[g][qg + j] = m.res_i[j];
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane < x.world) st_volatile_u32(x.dest_flag[lane] + x.q0 + q, x.epoch);
+  }
+  if (threadIdx.x < x.world) {
+    long long spins = 0;
+    const unsigned int* f = x.wait_flags + (size_t)threadIdx.x * x.flag_stride + x.q0 + q;
+    while ((int)(ld_volatile_u32(f) - x.epoch) < 0 && ++spins < (1ll << 28)) {
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  long long* s_idx = reinterpret_cast<long long*>(m.stage);
+  float* s_score = reinterpret_cast<float*>(m.stage + (size_t)x.world * k * sizeof(long long));
+  stage_lists<long long>(x.local_score, x.local_idx, x.world, k, x.score_list_stride, x.idx_list_stride,
+                         (size_t)(x.q0 + q) * k, s_idx, s_score, nthr);
+  if (k <= kParMaxK) {
+    // the local row was consumed by the fan-out above (same warp 0 lanes) before the flags were raised
+    for (int j = threadIdx.x; j < k; j += nthr) {
+      m.res_s[j] = -CUDART_INF_F;
+      m.res_i[j] = -1;
+    }
+    for (int g = threadIdx.x; g < kMaxPeers; g += nthr) m.slot[g] = g < x.world ? g : -1;
+    __syncthreads();
+    rank_active_lists(
+        m.slot, x.world, k, k, [&](int pos) { return s_idx[pos] >= 0; },
+        [&](int a, int b) { return s_score[a] > s_score[b] || (s_score[a] == s_score[b] && s_idx[a] < s_idx[b]); },
+        [&](int rank, int pos) {
+          m.res_s[rank] = s_score[pos];
+          m.res_i[rank] = s_idx[pos];
+        },
+        nthr);
+    __syncthreads();
+    return;
+  }
+  if (threadIdx.x < 32) {
+    auto load = [&](int l, int j, float& sc, long long& id) {
+      sc = s_score[l * k + j];
+      id = s_idx[l * k + j];
+    };
+    select_rounds(load, x.world, k, k, 0, m.res_s, m.res_i, lane);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // One CTA walks "supertiles" of p.sub consecutive 128-document tiles.  Per supertile the K loop
 // is outermost: for every 64-element k-chunk the (optional) Q blocks arrive once and are reused
 // by the MMAs of all p.sub document blocks, each accumulating into its own TMEM columns.
@@ -268,8 +778,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   const uint32_t tmem_cols = (uint32_t)(NB * S * NACC) * RS_TILE_ROWS;  // 128, 256 or 512
   const int n_super = (p.n_tiles + S - 1) / S;
   const uint32_t qblk = (uint32_t)p.bpad * RS_KCHUNK_BYTES;
+  // CTAs >= n_work own no tiles: they exist only so that every query has a CTA for the tail merge
+  const bool worker = (int)blockIdx.x < p.n_work;
+  const bool inline_prep = QRES && p.inline_prep != 0;
+  float* s_qnorm = reinterpret_cast<float*>(smem + map.bar_off + 1024);
+  float* s_qscale = s_qnorm + 128;
 
   if (threadIdx.x == 0) {
+    stamp(p.debug_ts, 0);  // kernel entry
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -278,12 +794,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), nact_warps);
     }
-    mbar_init(qfull_bar, 1);
+    mbar_init(qfull_bar, inline_prep ? kNumEpiWarps : 1);
     if (!q_resident)
       for (int s = 0; s < p.qstages; ++s) {
         mbar_init(qring_full(s), 1);
         mbar_init(qring_empty(s), 1);
       }
+    if (inline_prep)  // readiness of each 256-column group of the Q image (reuses the streamed-Q slots)
+      for (int g = 0; g < 4; ++g) mbar_init(qring_full(g), kNumEpiWarps);
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -308,7 +826,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
     // ===================== bulk-copy producer =====================
     const uint64_t pol_stream = l2_policy_evict_first();
     const uint64_t pol_keep = l2_policy_evict_last();
-    if (q_resident && lane == 0) {
+    if (q_resident && !inline_prep && worker && lane == 0) {
       mbar_arrive_expect_tx(qfull_bar, map.q_bytes);
       for (uint32_t off = 0; off < map.q_bytes; off += 32768u) {
         uint32_t n = min(32768u, map.q_bytes - off);
@@ -355,7 +873,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (lane 0 issues) =====================
     const uint32_t idesc = umma_idesc_f16(p.dtype == RS_DTYPE_BF16, p.mma_m, RS_TILE_ROWS);
-    if (q_resident) mbar_wait(qfull_bar, 0);
+    if (q_resident && !inline_prep && worker) {
+      mbar_wait(qfull_bar, 0);
+      tc_fence_after();
+    }
+    bool q_pending = inline_prep;  // first tile: wait for each k-chunk group of the Q image as it is needed
     int s = 0;
     uint32_t ph = 0;
     int acc = 0;
@@ -381,6 +903,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
         uint32_t qa0, qa1 = 0;
         int qslot0 = 0, qslot1 = 0;
         if (q_resident) {
+          if (q_pending) {
+            mbar_wait(qring_full(kc >> 2), 0);
+            tc_fence_after();
+          }
           qa0 = q_smem + (uint32_t)kc * qblk;
           qa1 = q_smem + (uint32_t)(p.kc + kc) * qblk;
         } else {
@@ -431,6 +957,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
           if (p.terms == 2) umma_commit(qring_empty(qslot1));
         }
       }
+      q_pending = false;
       __syncwarp();
       if (lane == 0) umma_commit(tfull_bar(acc));  // accumulators complete -> epilogue
       if (++acc == NB) {
@@ -441,15 +968,34 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   } else {
     // ===================== epilogue: one thread per query row =====================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
+    if (inline_prep && worker) {
+      // single-launch search: the four epilogue warps (idle until the first accumulator is ready)
+      // build the resident Q image while the producer warp already streams document tiles
+      static_assert(kNumEpiWarps == 4, "prep_queries_warp strides rows by 4 warps");
+      const int D = p.kc * RS_KCHUNK_ELEMS, wid = warp - kFirstEpiWarp;
+      const bool bf = p.dtype == RS_DTYPE_BF16;
+      const uint32_t gb = qring_full(0);
+      if (p.terms == 2) {
+        if (bf) prep_queries_warp<true, true>(p.q_f32, wid, p.n_queries, D, p.bpad, p.corpus_scale_exp, smem, s_qnorm, s_qscale, gb, lane);
+        else prep_queries_warp<false, true>(p.q_f32, wid, p.n_queries, D, p.bpad, p.corpus_scale_exp, smem, s_qnorm, s_qscale, gb, lane);
+      } else {
+        if (bf) prep_queries_warp<true, false>(p.q_f32, wid, p.n_queries, D, p.bpad, p.corpus_scale_exp, smem, s_qnorm, s_qscale, gb, lane);
+        else prep_queries_warp<false, false>(p.q_f32, wid, p.n_queries, D, p.bpad, p.corpus_scale_exp, smem, s_qnorm, s_qscale, gb, lane);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qfull_bar);  // this warp's norms / scales are in shared memory
+      if (threadIdx.x == kFirstEpiWarp * 32) stamp(p.debug_ts, 1);  // query prep done
+    }
     if (quarter < nact_warps) {
       const int row = quarter * rows_per_warp + lane;
       const bool live = lane < rows_per_warp && row < p.n_queries;
       const int k = p.k;
       const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
       const bool cosine = p.metric == RS_METRIC_COSINE;
-      const float qs = live ? p.qscale[row] : 1.f;  // raw accumulator -> dot product (power of two)
+      if (inline_prep && worker) mbar_wait(qfull_bar, 0);  // all four warps' rows (and norms) are in place
+      const float qs = live ? (inline_prep ? s_qscale[row] : p.qscale[row]) : 1.f;  // raw accumulator -> dot (2^n)
       const float inv_qs = 1.0f / qs;
-      const float nq = live ? p.qnorm[row] : 0.f;
+      const float nq = live ? (inline_prep ? s_qnorm[row] : p.qnorm[row]) : 0.f;
       const float lo_coef = p.lo_coef;
 
       // running top-k.  k <= kRegK: registers, ascending, slot 0 is the current k-th best (the
@@ -606,9 +1152,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
         }
       }
       // per-CTA candidates, best first; dot scores leave raw units here
-      if (live) {
-        float* cs = p.cand_score + ((size_t)row * gridDim.x + blockIdx.x) * k;   // [query][cta][k]
-        int* ci = p.cand_idx + ((size_t)row * gridDim.x + blockIdx.x) * k;
+      if (live && worker) {
+        float* cs = p.cand_score + ((size_t)row * p.n_work + blockIdx.x) * k;   // [query][cta][k]
+        int* ci = p.cand_idx + ((size_t)row * p.n_work + blockIdx.x) * k;
         if (REGLIST) {
 #pragma unroll
           for (int j = 0; j < kRegK; ++j) {
@@ -630,134 +1176,68 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
     }
   }
 
+  if (p.tail_mode != 0) __threadfence();  // this thread's candidate stores are visible GPU-wide before the arrival
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
-}
 
-// ------------------------------------------------------------------------------------------
-// merge of sorted candidate lists: one warp per query, each lane walks lists lane, lane+32, ...
-// Ordering everywhere is (score desc, index asc); index < 0 is padding and only occurs at the end
-// of a list.  STAGED: the query's candidates are first copied (coalesced) into shared memory so
-// the k selection rounds run at shared-memory latency instead of k dependent global round trips.
-// ------------------------------------------------------------------------------------------
-constexpr int kMergeMaxOwn = 8;  // up to 256 lists
-
-__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_volatile_u32(unsigned int* p, unsigned int v) {
-  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-constexpr int kMergeThreads = 128;  // four warps stage one query's candidates; warp 0 runs the k rounds
-
-// Copy one query's candidate lists into shared memory.  Element (list l, slot j) sits at
-// l*list_stride + qoff + j; the loads are issued four deep so the L2 round trips overlap.
-template <typename IdxT>
-__device__ __forceinline__ void stage_lists(const float* __restrict__ cand_score, const IdxT* __restrict__ cand_idx,
-                                            int n_lists, int kc, long long score_list_stride,
-                                            long long idx_list_stride, size_t qoff, IdxT* s_idx, float* s_score) {
-  const int total = n_lists * kc;
-  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * kMergeThreads) {
-    IdxT ti[4];
-    float ts[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = e0 + kMergeThreads * u;
-      if (e < total) {
-        const int l = e / kc, j = e - l * kc;
-        ti[u] = __ldcg(cand_idx + (size_t)l * idx_list_stride + qoff + j);
-        ts[u] = __ldcg(cand_score + (size_t)l * score_list_stride + qoff + j);
-      }
+  // ===================== tail: candidate merge (+ multi-GPU exchange) inside the same launch ============
+  // Worker CTAs publish their lists and arrive on a device counter; CTA q (q < n_queries) waits for all
+  // n_work arrivals, merges query q's lists out of L2 (ring/Q shared memory is free by now) and - multi-GPU
+  // - exchanges the row with the peer GPUs and merges the world lists.  Every CTA of the grid is resident
+  // (grid <= SM count, one CTA per SM), so the wait cannot starve a CTA that has not started.  The last
+  // merging CTA to leave resets the counters for the next launch (launches on one index are stream-ordered).
+  if (p.tail_mode != 0) {
+    if (threadIdx.x == 0 && worker) {
+      __threadfence();
+      atomicAdd(p.sync, 1u);
+      stamp(p.debug_ts, 4);  // candidates published, arrived
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = e0 + kMergeThreads * u;
-      if (e < total) {
-        s_idx[e] = ti[u];
-        s_score[e] = ts[u];
-      }
-    }
-  }
-  __syncthreads();
-}
-
-// k selection rounds by ONE warp over n_lists sorted lists (score desc, index asc; index < 0 is
-// padding at the end of a list).  Every list head is kept as a sortable pair: ks = order-preserving
-// image of the score (0 = padding / exhausted), ki = ~index (larger = lower index).  The warp's best
-// head is found with three redux.sync steps (score, index high word, index low word).  `load(l, j,
-// score&, idx&)` reads element j of list l.  Writes k rows to res_* (padding: -1 / -inf).
-template <typename Load>
-__device__ __forceinline__ void select_rounds(Load load, int n_lists, int kc, int k, long long idx_offset,
-                                              float* res_s, long long* res_i, int lane) {
-  unsigned int ks[kMergeMaxOwn];
-  unsigned long long ki[kMergeMaxOwn];
-  int head[kMergeMaxOwn];
-  auto read_head = [&](int i) {
-    const int l = lane + 32 * i;
-    ks[i] = 0u;
-    ki[i] = 0ull;
-    if (l < n_lists && head[i] < kc) {
-      float sc;
-      long long id;
-      load(l, head[i], sc, id);
-      if (id >= 0) {
-        unsigned int u = __float_as_uint(sc);
-        ks[i] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-        ki[i] = ~(unsigned long long)id;
-      }
-    }
-  };
-#pragma unroll
-  for (int i = 0; i < kMergeMaxOwn; ++i) {
-    head[i] = 0;
-    read_head(i);
-  }
-  int r = 0;
-  for (; r < k; ++r) {
-    unsigned int bs = 0u;  // this lane's best head
-    unsigned long long bi = 0ull;
-    int bown = 0;
-#pragma unroll
-    for (int i = 0; i < kMergeMaxOwn; ++i)
-      if (ks[i] > bs || (ks[i] == bs && ki[i] > bi)) {
-        bs = ks[i];
-        bi = ki[i];
-        bown = i;
-      }
-    const unsigned int m0 = __reduce_max_sync(0xffffffffu, bs);
-    if (m0 == 0u) break;  // every list exhausted: the rest is padding
-    bool mine = bs == m0;
-    const unsigned int m1 = __reduce_max_sync(0xffffffffu, mine ? (unsigned int)(bi >> 32) : 0u);
-    mine = mine && (unsigned int)(bi >> 32) == m1;
-    const unsigned int m2 = __reduce_max_sync(0xffffffffu, mine ? (unsigned int)bi : 0u);
-    mine = mine && (unsigned int)bi == m2;
-    if (mine) {  // exactly one lane when indices are unique
-      float sc;
-      long long id;
-      load(lane + 32 * bown, head[bown], sc, id);
-      res_s[r] = sc;
-      res_i[r] = id + idx_offset;
-#pragma unroll
-      for (int i = 0; i < kMergeMaxOwn; ++i)
-        if (i == bown) {
-          ++head[i];
-          read_head(i);
+    if ((int)blockIdx.x < p.n_queries) {
+      if (threadIdx.x == 0) {
+        long long spins = 0;
+        while (ld_acquire_gpu_u32(p.sync) < (unsigned int)p.n_work) {
+          __nanosleep(40);
+          if (++spins > (1ll << 24)) {  // ~1 s: a CTA of this grid never ran; flag it instead of hanging the GPU
+            *reinterpret_cast<volatile unsigned int*>(p.err_flag) = 1u;  // mapped host memory
+            break;
+          }
         }
+        __threadfence();
+        stamp(p.debug_ts, 5);  // every worker CTA has arrived
+      }
+      __syncthreads();
+      const MergeSmem m = merge_smem_at(smem, p.k);
+      for (int q = blockIdx.x; q < ((p.debug_flags & 4) ? 0 : p.n_queries); q += gridDim.x) {
+        merge_query_local(p.cand_score, p.cand_idx, p.n_work, p.k, p.idx_offset, q, m, kThreads, p.debug_ts);
+        if (p.tail_mode == 2) exchange_query(p.x, q, p.k, m, kThreads);
+        for (int j = threadIdx.x; j < p.k; j += kThreads) {
+          p.out_score[(size_t)q * p.k + j] = m.res_s[j];
+          p.out_idx[(size_t)q * p.k + j] = m.res_i[j];
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {
+        stamp(p.debug_ts, 6);  // this CTA's queries merged and written
+        const unsigned int mergers = (unsigned int)min((int)gridDim.x, p.n_queries);
+        if (atomicAdd(p.sync + 1, 1u) == mergers - 1u) {
+          atomicExch(p.sync, 0u);
+          atomicExch(p.sync + 1, 0u);
+        }
+      }
     }
   }
-  __syncwarp();
-  for (int rr = r + lane; rr < k; rr += 32) {
-    res_s[rr] = -CUDART_INF_F;
-    res_i[rr] = -1;
-  }
-  __syncwarp();
+}
+
+// smem bytes the tail needs at offset 0 (result row + staged lists of one query)
+size_t fused_tail_smem_bytes(int n_lists, int k, int world) {
+  return merge_res_bytes(k) + std::max((size_t)n_lists * k * 8, (size_t)world * k * 12);
+}
+int fused_tail_smem_capacity(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages) {
+  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages).bar_off;
 }
 
 // Plain merge: one CTA per query, lists -> out[q][0..k).
@@ -774,11 +1254,13 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const float* 
   const int lane = threadIdx.x & 31;
   long long* res_i = reinterpret_cast<long long*>(merge_smem);
   float* res_s = reinterpret_cast<float*>(res_i + k);
-  uint8_t* stage = merge_smem + (((size_t)k * 12 + 15) & ~size_t(15));
+  uint8_t* stage = merge_smem + merge_res_bytes(k);
   IdxT* s_idx = reinterpret_cast<IdxT*>(stage);
   float* s_score = reinterpret_cast<float*>(stage + (size_t)n_lists * kc * sizeof(IdxT));
   const size_t qoff = (size_t)q * query_stride;
-  if (STAGED) stage_lists<IdxT>(cand_score, cand_idx, n_lists, kc, score_list_stride, idx_list_stride, qoff, s_idx, s_score);
+  if (STAGED)
+    stage_lists<IdxT>(cand_score, cand_idx, n_lists, kc, score_list_stride, idx_list_stride, qoff, s_idx, s_score,
+                      kMergeThreads);
   if (threadIdx.x >= 32) return;  // the selection rounds are a single-warp job
   auto load = [&](int l, int j, float& sc, long long& id) {
     if (STAGED) {
@@ -796,6 +1278,21 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const float* 
   }
 }
 
+// Stand-alone local merge (RS_FUSED_TAIL=0 fallback): one CTA per query over the per-CTA lists.
+__global__ void __launch_bounds__(kMergeThreads) merge_local_kernel(const float* __restrict__ cand_score,
+                                                                    const int* __restrict__ cand_idx, int n_lists, int k,
+                                                                    long long idx_offset, float* __restrict__ out_score,
+                                                                    long long* __restrict__ out_idx) {
+  extern __shared__ __align__(16) uint8_t merge_smem[];
+  const int q = blockIdx.x;
+  const MergeSmem m = merge_smem_at(merge_smem, k);
+  merge_query_local(cand_score, cand_idx, n_lists, k, idx_offset, q, m, kMergeThreads);
+  for (int j = threadIdx.x; j < k; j += kMergeThreads) {
+    out_score[(size_t)q * k + j] = m.res_s[j];
+    out_idx[(size_t)q * k + j] = m.res_i[j];
+  }
+}
+
 // Multi-GPU: local merge + candidate exchange + final merge in ONE kernel (one CTA per query).
 //   1. merge this GPU's per-CTA lists of query q into its local top-k (global indices)
 //   2. store that row into every GPU's exchange buffer through peer pointers (NVLink) and raise
@@ -806,63 +1303,18 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const float* 
 // grid, so no co-residency is required.  Buffers are double-buffered by epoch parity.
 __global__ void __launch_bounds__(kMergeThreads) exchange_merge_kernel(const float* __restrict__ cand_score,
                                                                        const int* __restrict__ cand_idx, int n_lists,
-                                                                       int kc, int k, long long idx_offset,
+                                                                       int k, long long idx_offset,
                                                                        float* __restrict__ out_score,
                                                                        long long* __restrict__ out_idx,
                                                                        const ExchangeArgs x) {
   extern __shared__ __align__(16) uint8_t merge_smem[];
   const int q = blockIdx.x;  // query inside this pass
-  const int lane = threadIdx.x & 31;
-  long long* res_i = reinterpret_cast<long long*>(merge_smem);
-  float* res_s = reinterpret_cast<float*>(res_i + k);
-  uint8_t* stage = merge_smem + (((size_t)k * 12 + 15) & ~size_t(15));
-  {
-    int* s_idx = reinterpret_cast<int*>(stage);
-    float* s_score = reinterpret_cast<float*>(stage + (size_t)n_lists * kc * sizeof(int));
-    stage_lists<int>(cand_score, cand_idx, n_lists, kc, kc, kc, (size_t)q * n_lists * kc, s_idx, s_score);
-    if (threadIdx.x < 32) {
-      auto load = [&](int l, int j, float& sc, long long& id) {
-        sc = s_score[l * kc + j];
-        id = (long long)s_idx[l * kc + j];
-      };
-      select_rounds(load, n_lists, kc, k, idx_offset, res_s, res_i, lane);
-      // fan the row out to every GPU's exchange buffer (peer stores over NVLink), then publish
-      const size_t qg = (size_t)(x.q0 + q) * k;
-      for (int e = lane; e < k * x.world; e += 32) {
-        const int g = e / k, j = e - g * k;
-        x.dest_score[g][qg + j] = res_s[j];
-        x.dest_idx[g][qg + j] = res_i[j];
-      }
-      __threadfence_system();
-      __syncwarp();
-      if (lane < x.world) st_volatile_u32(x.dest_flag[lane] + x.q0 + q, x.epoch);
-    }
-  }
-  // wait for all ranks' rows of this query
-  if (threadIdx.x < x.world) {
-    long long spins = 0;
-    const unsigned int* f = x.wait_flags + (size_t)threadIdx.x * x.flag_stride + x.q0 + q;
-    while ((int)(ld_volatile_u32(f) - x.epoch) < 0 && ++spins < (1ll << 28)) {
-    }
-  }
-  __threadfence_system();
-  __syncthreads();
-  {
-    long long* s_idx = reinterpret_cast<long long*>(stage);
-    float* s_score = reinterpret_cast<float*>(stage + (size_t)x.world * k * sizeof(long long));
-    stage_lists<long long>(x.local_score, x.local_idx, x.world, k, x.score_list_stride, x.idx_list_stride,
-                           (size_t)(x.q0 + q) * k, s_idx, s_score);
-    if (threadIdx.x < 32) {
-      auto load = [&](int l, int j, float& sc, long long& id) {
-        sc = s_score[l * k + j];
-        id = s_idx[l * k + j];
-      };
-      select_rounds(load, x.world, k, k, 0, res_s, res_i, lane);
-      for (int j = lane; j < k; j += 32) {
-        out_score[(size_t)q * k + j] = res_s[j];
-        out_idx[(size_t)q * k + j] = res_i[j];
-      }
-    }
+  const MergeSmem m = merge_smem_at(merge_smem, k);
+  merge_query_local(cand_score, cand_idx, n_lists, k, idx_offset, q, m, kMergeThreads);
+  exchange_query(x, q, k, m, kMergeThreads);
+  for (int j = threadIdx.x; j < k; j += kMergeThreads) {
+    out_score[(size_t)q * k + j] = m.res_s[j];
+    out_idx[(size_t)q * k + j] = m.res_i[j];
   }
 }
 
@@ -911,7 +1363,7 @@ static cudaError_t launch_merge_t(const float* cand_score, const IdxT* cand_idx,
                                   long long idx_list_stride, long long query_stride, float* out_score,
                                   long long* out_idx, cudaStream_t stream) {
   if (n_lists > 32 * kMergeMaxOwn) return cudaErrorInvalidValue;
-  const size_t res_bytes = ((size_t)k * 12 + 15) & ~size_t(15);
+  const size_t res_bytes = merge_res_bytes(k);
   const size_t stage_bytes = (size_t)n_lists * kc * (sizeof(IdxT) + sizeof(float));
   if (res_bytes + stage_bytes <= 200 * 1024) {
     auto kern = merge_topk_kernel<IdxT, true>;
@@ -934,8 +1386,16 @@ static cudaError_t launch_merge_t(const float* cand_score, const IdxT* cand_idx,
 cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int kc, int k,
                              long long idx_offset, float* out_score, long long* out_idx, cudaStream_t stream) {
   // per-CTA candidates are stored [query][cta][k]: one query's lists are contiguous (coalesced staging)
-  return launch_merge_t<int>(cand_score, cand_idx, n_lists, n_queries, kc, k, idx_offset, (long long)kc,
-                             (long long)kc, (long long)n_lists * kc, out_score, out_idx, stream);
+  if (kc != k || n_lists > 32 * kMergeMaxOwn) return cudaErrorInvalidValue;
+  const size_t bytes = merge_res_bytes(k) + (size_t)n_lists * k * 8;
+  if (bytes > 200 * 1024) return cudaErrorInvalidValue;
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(merge_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+  }
+  merge_local_kernel<<<n_queries, kMergeThreads, bytes, stream>>>(cand_score, cand_idx, n_lists, k, idx_offset, out_score,
+                                                                  out_idx);
+  return cudaGetLastError();
 }
 cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx, int n_lists, int n_queries, int kc,
                              int k, long long score_list_stride, long long idx_list_stride, float* out_score,
@@ -948,7 +1408,7 @@ cudaError_t launch_exchange_merge(const float* cand_score, const int* cand_idx, 
                                   long long idx_offset, float* out_score, long long* out_idx, const ExchangeArgs& x,
                                   cudaStream_t stream) {
   if (n_lists > 32 * kMergeMaxOwn || x.world > kMaxPeers) return cudaErrorInvalidValue;
-  const size_t res_bytes = ((size_t)k * 12 + 15) & ~size_t(15);
+  const size_t res_bytes = merge_res_bytes(k);
   const size_t stage_bytes = std::max((size_t)n_lists * k * 8, (size_t)x.world * k * 12);
   const size_t bytes = res_bytes + stage_bytes;
   if (bytes > 200 * 1024) return cudaErrorInvalidValue;
@@ -956,7 +1416,7 @@ cudaError_t launch_exchange_merge(const float* cand_score, const int* cand_idx, 
     cudaError_t e = cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
   }
-  exchange_merge_kernel<<<n_queries, kMergeThreads, bytes, stream>>>(cand_score, cand_idx, n_lists, k, k, idx_offset,
+  exchange_merge_kernel<<<n_queries, kMergeThreads, bytes, stream>>>(cand_score, cand_idx, n_lists, k, idx_offset,
                                                                      out_score, out_idx, x);
   return cudaGetLastError();
 }

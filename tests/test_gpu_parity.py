@@ -270,6 +270,8 @@ MODES = [
     {"RS_QRESIDENT": "0", "RS_SUB": "1", "RS_NBUF": "2"}, {"RS_QRESIDENT": "0", "RS_SUB": "2", "RS_NBUF": "2"},
     {"RS_QRESIDENT": "0", "RS_SUB": "4", "RS_NBUF": "1"}, {"RS_QRESIDENT": "0", "RS_SUB": "2", "RS_NBUF": "1", "RS_MMA_M": "128"},
     {"RS_QRESIDENT": "1", "RS_SUB": "2", "RS_NBUF": "2"},
+    # the multi-launch fallbacks of the single-launch search: separate query_prep_kernel / merge kernel
+    {"RS_INLINE_PREP": "0"}, {"RS_FUSED_TAIL": "0"}, {"RS_INLINE_PREP": "0", "RS_FUSED_TAIL": "0"},
 ]
 
 
@@ -293,6 +295,24 @@ def test_kernel_modes(monkeypatch, squad, mode):
             monkeypatch.setenv(k_, v)
         run_case(squad.E, squad.Q, 10, "fp32", "dot", 2, scale_exp=4)
         run_case(E[:40_000], Q, 10, "fp16", "cosine", 2)
+
+
+def test_single_launch_search_counts_and_small_grids(squad):
+    """One fused launch per search by default; extra merge-only CTAs when the corpus has fewer tiles than
+    the batch has queries (grid >= B so every query owns a tail CTA)."""
+    for n, B in ((100, 32), (128, 64), (300, 17), (1000, 32), (1000, 5)):
+        ix = make_index(squad.E[:n], "bf16", max_batch=64, max_k=16)
+        try:
+            Q = squad.Q[np.arange(B) % len(squad.Q)] * (1 + 0.01 * np.arange(B)[:, None]).astype(np.float32)
+            for _ in range(3):                               # repeated launches reuse the reset counters
+                idx, sc = ix.search(Q, 10, "dot", 1)
+            st = ix.stats()
+            assert st["launches"] == (1 if B <= 32 else 2), st      # B > 32: query_prep_kernel stays separate
+            assert st["grid"] == max(min(148, -(-n // 128)), min(B, 148))
+            S = exact_scores(Q, squad.E[:n], "bf16", "dot", 1)
+            o.check_topk(idx, sc, S, 10, rtol=2e-3, atol=1e-6)
+        finally:
+            ix.close()
 
 
 @pytest.mark.parametrize("B,dtype,terms", [(96, "bf16", 1), (128, "bf16", 1), (128, "fp32", 2), (128, "fp16", 2),
