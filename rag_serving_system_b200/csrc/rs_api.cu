@@ -51,6 +51,7 @@ struct Plan {
   int nbuf;        // TMEM accumulator buffers
   int mma_m;       // MMA M: 64 when the padded batch fits, else 128
   int cps;         // k-chunks per ring stage
+  int bufc;        // k > 16: candidate-buffer entries per query (32; 16 when that saves a pass)
 };
 
 int env_int(const char* name, int dflt) {
@@ -118,11 +119,11 @@ struct rs_xchg {
 
 namespace {
 
-int max_cap_rows(int kc, int terms, int k, int min_stages, int cps, int q_resident) {
+int max_cap_rows(int kc, int terms, int k, int min_stages, int cps, int q_resident, int bufc = 32) {
   // largest bpad (multiple of 8, <= 128) that leaves at least min_stages ring slots
   int best = 0;
   for (int bpad = 8; bpad <= 128; bpad += 8) {
-    if (rs::fused_smem_bytes(bpad, kc, terms, min_stages, cps, k, q_resident, 2 * terms) <= kMaxSmem) best = bpad;
+    if (rs::fused_smem_bytes(bpad, kc, terms, min_stages, cps, k, q_resident, 2 * terms, bufc) <= kMaxSmem) best = bpad;
   }
   return best;
 }
@@ -135,6 +136,8 @@ int max_cap_rows(int kc, int terms, int k, int min_stages, int cps, int q_reside
 int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
   const int nacc = (terms == 2 || ix->planes == 2) ? 2 : 1;
   const int force_res = env_int("RS_QRESIDENT", -1), force_cps = env_int("RS_CPS", 0), force_sub = env_int("RS_SUB", 0);
+  const int force_bufc = env_int("RS_BUFC", 0), force_lean = env_int("RS_LEAN", -1);
+  const bool lists_in_smem = k > rs::fused_reg_k();
   long long best_cost = -1;
   for (int resident = 1; resident >= 0; --resident) {
     if (force_res >= 0 && resident != force_res) continue;
@@ -143,21 +146,32 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
       if (!resident && cps == 4) continue;
       for (int sub = resident ? (force_sub ? force_sub : 1) : (nacc == 1 ? 4 : 2); sub >= 1; sub >>= 1) {
         if (force_sub && sub != force_sub) continue;
-        // ring depth: at least 64 KiB in flight, and in streamed mode one whole k-chunk group + 1
-        int need = std::max(2, (4 + cps - 1) / cps);
-        if (!resident) need = std::max(need, ix->planes * sub + 1);
-        const int cap = max_cap_rows(ix->kc, terms, k, need, cps, resident);
-        if (cap <= 0) continue;
-        const int passes = (B + cap - 1) / cap;
-        const long long cost = ((long long)passes << 32) | ((long long)(1 - resident) << 24) | ((long long)(4 - cps) << 16) |
-                               (long long)(8 - sub);
-        if (best_cost < 0 || cost < best_cost) {
-          best_cost = cost;
-          pl->q_resident = resident;
-          pl->cps = cps;
-          pl->sub = sub;
-          pl->passes = passes;
-          pl->stages = need;
+        // k > 16 only: a 16-entry candidate buffer (twice the flushes) and a 48 KiB ring are accepted
+        // when they save a whole pass over the shard
+        for (int bufc = 32; bufc >= (lists_in_smem ? 16 : 32); bufc >>= 1) {
+          if (force_bufc && bufc != force_bufc) continue;
+          for (int lean = 0; lean <= (lists_in_smem ? 1 : 0); ++lean) {
+            if (force_lean >= 0 && lean != force_lean) continue;
+            // ring depth: at least 64 KiB in flight (48 KiB when lean), and in streamed mode one whole
+            // k-chunk group + 1
+            int need = std::max(2, ((lean ? 3 : 4) + cps - 1) / cps);
+            if (!resident) need = std::max(need, ix->planes * sub + 1);
+            const int cap = max_cap_rows(ix->kc, terms, k, need, cps, resident, bufc);
+            if (cap <= 0) continue;
+            const int passes = (B + cap - 1) / cap;
+            const long long cost = ((long long)passes << 32) | ((long long)(1 - resident) << 28) |
+                                   ((long long)(bufc == 32 ? 0 : 1) << 24) | ((long long)lean << 20) |
+                                   ((long long)(4 - cps) << 16) | (long long)(8 - sub);
+            if (best_cost < 0 || cost < best_cost) {
+              best_cost = cost;
+              pl->q_resident = resident;
+              pl->cps = cps;
+              pl->sub = sub;
+              pl->passes = passes;
+              pl->stages = need;
+              pl->bufc = bufc;
+            }
+          }
         }
       }
     }
@@ -173,11 +187,11 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
   const int cols = pl->sub * pl->nbuf * nacc;
   if (pl->nbuf < 1 || pl->nbuf > 4 || (cols != 1 && cols != 2 && cols != 4))
     return fail(RS_E_INVALID, "sub=%d nbuf=%d nacc=%d does not map onto 128/256/512 TMEM columns", pl->sub, pl->nbuf, nacc);
-  while (pl->stages < kMaxStages && rs::fused_smem_bytes(pl->bpad, ix->kc, terms, pl->stages + 1, pl->cps, k,
-                                                         pl->q_resident, 2 * terms) <= kMaxSmem)
-    ++pl->stages;
-  if (rs::fused_smem_bytes(pl->bpad, ix->kc, terms, pl->stages, pl->cps, k, pl->q_resident, 2 * terms) > kMaxSmem)
-    return fail(RS_E_UNSUPPORTED, "B=%d k=%d does not fit in shared memory", B, k);
+  auto bytes = [&](int stages) {
+    return rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages, pl->cps, k, pl->q_resident, 2 * terms, pl->bufc);
+  };
+  while (pl->stages < kMaxStages && bytes(pl->stages + 1) <= kMaxSmem) ++pl->stages;
+  if (bytes(pl->stages) > kMaxSmem) return fail(RS_E_UNSUPPORTED, "B=%d k=%d does not fit in shared memory", B, k);
   return RS_OK;
 }
 
@@ -238,7 +252,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   const int grid = fused_tail ? std::max(n_work, std::min(pl.per_pass, ix->sm_count)) : n_work;
   ix->stats.grid = grid;
   ix->stats.stages = pl.stages;
-  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms);
+  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms, pl.bufc);
   ix->stats.q_resident = pl.q_resident;
   ix->stats.sub = pl.sub;
   ix->stats.nbuf = pl.nbuf;
@@ -270,6 +284,8 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.n_work = n_work;
     p.tail_mode = fused_tail ? (xg ? 2 : 1) : 0;
     p.sync = ix->sync;
+    p.dyn_sched = env_int("RS_DYN_SCHED", 1) != 0 ? 1 : 0;
+    if (p.dyn_sched && !fused_tail) RS_CUDA(cudaMemsetAsync(ix->sync + 4, 0, sizeof(unsigned int), stream));  // the tail resets it otherwise
     p.err_flag = ix->err_flag;
     p.out_score = out_score + (size_t)b0 * k;
     p.out_idx = out_idx + (size_t)b0 * k;
@@ -299,6 +315,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.dtype = ix->plane_dtype;
     p.stages = pl.stages;
     p.cps = pl.cps;
+    p.bufc = pl.bufc;
     p.qstages = 2 * terms;
     p.q_resident = pl.q_resident;
     p.sub = pl.sub;

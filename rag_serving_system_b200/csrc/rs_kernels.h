@@ -48,6 +48,7 @@ struct SearchParams {
   int sub;                           // 128-document tiles per supertile (share one Q k-chunk load)
   int mma_m;                         // 128, or 64 when bpad <= 64 (half the tensor work / operand reads)
   int nbuf;                          // TMEM accumulator buffers (1 or 2); nbuf*sub*NACC*128 <= 512 columns
+  int bufc;                          // k > 16: candidate-buffer entries per query before a flush (32, or 16 to save smem)
   int debug_flags;                   // timing experiments only (RS_DEBUG_FLAGS): 1 = skip MMAs, 2 = skip epilogue, 4 = skip tail merge, 8 = skip inline prep
   float lo_coef;                     // weight of the low-order accumulator (2^-11 for fp16 terms, 1 for bf16)
   // ---- single-launch search: query prep in the prologue, candidate merge (+ exchange) in the tail
@@ -56,7 +57,8 @@ struct SearchParams {
   int corpus_scale_exp;              // power-of-two pre-scale of an fp32 corpus (folded into qscale)
   int n_work;                        // CTAs that own tiles and write candidate lists (= lists per query)
   int tail_mode;                     // 0: candidates only; 1: + in-kernel merge; 2: + peer exchange and final merge
-  unsigned int* sync;                // [0] arrivals of worker CTAs, [1] departures of merging CTAs
+  unsigned int* sync;                // [0] arrivals of worker CTAs, [1] departures of merging CTAs, [4] next tile (dynamic scheduler)
+  int dyn_sched;                     // 1: supertiles after the first come from sync[4] (work stealing); 0: static round-robin
   unsigned int* err_flag;            // mapped host word, set to 1 if the arrival wait timed out
   float* out_score;                  // tail_mode != 0: final [n_queries][k]
   long long* out_idx;
@@ -68,7 +70,7 @@ struct SearchParams {
 cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dtype, int terms, int corpus_scale_exp,
                               uint8_t* qimg, float* qnorm, float* qscale, cudaStream_t stream);
 cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t stream);
-int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages);
+int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages, int bufc);
 int fused_reg_k();
 size_t fused_tail_smem_bytes(int n_lists, int k, int world);
 int fused_tail_smem_capacity(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages);

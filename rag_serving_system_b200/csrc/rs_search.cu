@@ -285,8 +285,11 @@ constexpr int kFirstEpiWarp = 2;
 constexpr int kNumEpiWarps = 4;
 constexpr int kThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;  // 192
 constexpr int kRegK = 16;                                       // register-resident list capacity
-constexpr int kBufC = 32;                                       // k > kRegK: unsorted candidate buffer per query
+constexpr int kBufC = 32;                                       // k > kRegK: unsorted candidate buffer per query (p.bufc <= 32)
 constexpr int kMaxListK = 128;                                  // k > kRegK: sorted list in smem, <= 4 slots per lane
+
+// words per query of the k > kRegK selection state (odd: see the epilogue)
+__host__ __device__ inline int list_row_words(int k, int bufc) { return (2 * (k + bufc)) | 1; }
 
 struct SmemMap {
   uint32_t q_bytes, stage_off, bar_off, dump_off, list_off, total;
@@ -294,7 +297,7 @@ struct SmemMap {
 // q_resident: the whole Q image lives in shared memory for the kernel's lifetime (small batches);
 // otherwise Q k-chunks travel through the ring next to the document blocks (large batches).
 __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, int stages, int cps, int k,
-                                                 bool reglist, bool q_resident, int qstages) {
+                                                 bool reglist, bool q_resident, int qstages, int bufc = kBufC) {
   SmemMap m;
   // resident: the whole Q image; streamed: a private ring of qstages slots of cps k-chunks each
   m.q_bytes = q_resident ? (uint32_t)terms * kc * bpad * RS_KCHUNK_BYTES
@@ -304,7 +307,7 @@ __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, in
   m.dump_off = m.bar_off + 2048;                       // [bar_off, +1 KiB) barriers, then qnorm[128], qscale[128];
                                                        // dump = rare-path chunk: 32 columns x live rows, fp32
   m.list_off = m.dump_off + (uint32_t)((bpad + 31) / 32 * 32) * 128u;   // whole warps of 32 (M=128) or 2x16 (M=64) rows
-  m.total = m.list_off + (reglist ? 0u : (uint32_t)(k + kBufC) * (uint32_t)bpad * 8u);
+  m.total = m.list_off + (reglist ? 0u : (uint32_t)list_row_words(k, bufc) * (uint32_t)bpad * 4u);
   return m;
 }
 
@@ -329,17 +332,18 @@ __device__ __forceinline__ float cosine_raw_bound(float thr_cos, float nq, float
   return thr_cos * (nq * ndmax + 1e-8f) * inv_qs * (1.0f + 1e-6f);
 }
 
-// k > kRegK selection state (per query, in shared memory, [slot][row] so rows are bank-parallel):
-// a sorted top-k list (best first) plus an unsorted buffer of kBufC candidates that passed the
-// (stale) threshold.  When a buffer fills, the whole warp merges it into the list: bitonic-sort the
+// k > kRegK selection state (per query one shared-memory row of list_row_words() words, odd stride):
+// a sorted top-k list (best first) plus an unsorted buffer of bufc (16 or 32) candidates that passed
+// the (stale) threshold.  The sorted candidates are parked in Bs[0..32): with bufc == 16 that runs
+// over the (already consumed) id half of the buffer, which is exactly 16 more words.  When a buffer fills, the whole warp merges it into the list: bitonic-sort the
 // 32 candidates across lanes, then every element computes its rank in the merged order by binary
 // search in the other sequence and is written straight to that position.  Ties: list elements were
 // seen earlier (lower index) so they win; candidates order by (score desc, index asc).
 // Must be called by the full, converged warp.  Returns the new k-th best score.
 __device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs, int* Bi, int stride, int qrow, int n,
                                                   int k, int lane) {
-  float cs = lane < n ? Bs[lane * stride + qrow] : -CUDART_INF_F;
-  int ci = lane < n ? Bi[lane * stride + qrow] : 0x7fffffff;
+  float cs = lane < n ? Bs[(lane) + qrow * stride] : -CUDART_INF_F;
+  int ci = lane < n ? Bi[(lane) + qrow * stride] : 0x7fffffff;
 #pragma unroll
   for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
@@ -356,7 +360,7 @@ __device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs,
       }
     }
   }
-  Bs[lane * stride + qrow] = cs;  // now sorted, best first
+  Bs[(lane) + qrow * stride] = cs;  // now sorted, best first
   __syncwarp();
   float es[kMaxListK / 32];
   int ei[kMaxListK / 32], er[kMaxListK / 32];
@@ -365,38 +369,38 @@ __device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs,
     const int pos = lane + 32 * g;
     er[g] = k;
     if (pos < k) {
-      es[g] = Ls[pos * stride + qrow];
-      ei[g] = Li[pos * stride + qrow];
+      es[g] = Ls[(pos) + qrow * stride];
+      ei[g] = Li[(pos) + qrow * stride];
       // candidates strictly better than this list element: fixed-trip binary search (count in
       // [0,32]) so the four independent searches of a lane interleave their shared-memory loads
       int c = 0;
 #pragma unroll
       for (int step = 16; step > 0; step >>= 1)
-        if (Bs[(c + step - 1) * stride + qrow] > es[g]) c += step;
-      if (c == 31 && Bs[31 * stride + qrow] > es[g]) c = 32;
+        if (Bs[((c + step - 1)) + qrow * stride] > es[g]) c += step;
+      if (c == 31 && Bs[(31) + qrow * stride] > es[g]) c = 32;
       er[g] = pos + c;
     }
   }
   int lo = 0, hi = k;  // list elements at least as good as this candidate
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (Ls[mid * stride + qrow] >= cs) lo = mid + 1; else hi = mid;
+    if (Ls[(mid) + qrow * stride] >= cs) lo = mid + 1; else hi = mid;
   }
   const int cr = lane + lo;
   __syncwarp();
 #pragma unroll
   for (int g = 0; g < kMaxListK / 32; ++g) {
     if (er[g] < k) {
-      Ls[er[g] * stride + qrow] = es[g];
-      Li[er[g] * stride + qrow] = ei[g];
+      Ls[er[g] + qrow * stride] = es[g];
+      Li[er[g] + qrow * stride] = ei[g];
     }
   }
   if (lane < n && cr < k) {
-    Ls[cr * stride + qrow] = cs;
-    Li[cr * stride + qrow] = ci;
+    Ls[(cr) + qrow * stride] = cs;
+    Li[(cr) + qrow * stride] = ci;
   }
   __syncwarp();
-  return Ls[(k - 1) * stride + qrow];
+  return Ls[((k - 1)) + qrow * stride];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -754,7 +758,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr bool q_resident = QRES;
-  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, q_resident, p.qstages);
+  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, q_resident, p.qstages, p.bufc);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t q_smem = smem_base;
   const uint32_t stage_smem = smem_base + map.stage_off;
@@ -767,6 +771,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   const uint32_t qfull_bar = bar_base + 8u * (2 * p.stages + 8);
   auto qring_full = [&](int s) { return bar_base + 8u * (2 * p.stages + 9 + s); };              // streamed Q ring
   auto qring_empty = [&](int s) { return bar_base + 8u * (2 * p.stages + 9 + p.qstages + s); };
+  // tile scheduler queue: the producer warp publishes the supertile ids this CTA works on (-1 = done)
+  constexpr int kSched = 8;
+  auto sched_full = [&](int s) { return bar_base + 8u * (2 * p.stages + 9 + 2 * p.qstages + s); };
+  auto sched_empty = [&](int s) { return bar_base + 8u * (2 * p.stages + 9 + 2 * p.qstages + kSched + s); };
+  volatile int* tile_u = reinterpret_cast<volatile int*>(smem + map.bar_off + 1016 - 4 * kSched);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + map.bar_off + 1016);
 
   // M=128: query row r lives in TMEM lane r.  M=64 (half the tensor work, used when bpad <= 64):
@@ -802,6 +811,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       }
     if (inline_prep)  // readiness of each 256-column group of the Q image (reuses the streamed-Q slots)
       for (int g = 0; g < 4; ++g) mbar_init(qring_full(g), kNumEpiWarps);
+    for (int s = 0; s < kSched; ++s) {
+      mbar_init(sched_full(s), 1);
+      mbar_init(sched_empty(s), 1 + nact_warps);  // read by the MMA warp and every active epilogue warp
+    }
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -859,7 +872,26 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
         qph ^= 1u;
       }
     };
-    for (int u = blockIdx.x; u < n_super; u += gridDim.x) {
+    // Supertiles are handed out dynamically: the first one is static (blockIdx.x), every further one comes
+    // from a device-wide counter, so CTAs that stream faster take more tiles and all CTAs finish within
+    // one tile time of each other.  The counter only grows, so a CTA still sees ascending document
+    // indices (the tie rule relies on that).  RS_DYN_SCHED=0: static round-robin.
+    int sslot = 0;
+    uint32_t sph = 0;
+    int u = (worker && (int)blockIdx.x < n_super) ? (int)blockIdx.x : -1;
+    while (true) {
+      mbar_wait(sched_empty(sslot), sph ^ 1u);
+      if (lane == 0) {
+        tile_u[sslot] = u;
+        mbar_arrive(sched_full(sslot));
+      }
+      if (++sslot == kSched) {
+        sslot = 0;
+        sph ^= 1u;
+      }
+      if (u < 0) break;
+      int nxt = u + (int)gridDim.x;
+      if (p.dyn_sched && lane == 0) nxt = (int)atomicAdd(p.sync + 4, 1u) + (int)gridDim.x;  // consumed after the pushes
       const int nsub = min(S, p.n_tiles - u * S);
       const uint8_t* src = p.corpus + (size_t)u * S * tile_bytes;
       for (int kc = 0; kc < p.kc; kc += cps) {
@@ -869,6 +901,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
           for (int sub = 0; sub < nsub; ++sub)
             push(src + (size_t)sub * tile_bytes + (size_t)(pl * p.kc + kc) * RS_BLOCK_BYTES, stage_bytes, pol_stream);
       }
+      nxt = __shfl_sync(0xffffffffu, nxt, 0);
+      u = nxt < n_super ? nxt : -1;
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (lane 0 issues) =====================
@@ -894,7 +928,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
           umma_f16(d, a + 2u * ks, b + 2u * ks, idesc, (fresh && ks == 0) ? 0u : 1u);
       }
     };
-    for (int u = blockIdx.x; u < n_super; u += gridDim.x) {
+    int sslot = 0;
+    uint32_t sph = 0;
+    while (true) {
+      mbar_wait(sched_full(sslot), sph);
+      const int u = tile_u[sslot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sched_empty(sslot));
+      if (++sslot == kSched) {
+        sslot = 0;
+        sph ^= 1u;
+      }
+      if (u < 0) break;
       const int nsub = min(S, p.n_tiles - u * S);
       mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
       tc_fence_after();
@@ -1002,11 +1047,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       // threshold).  Larger k: sorted list + candidate buffer in shared memory (flush_candidates).
       float ls[REGLIST ? kRegK : 1];
       int li[REGLIST ? kRegK : 1];
-      const int lstride = p.bpad;
+      // per query one contiguous row [list scores k][list ids k][buffer scores bufc][buffer ids bufc] with an
+      // ODD word stride: lanes that walk one query's slots (flush) and lanes that touch the same slot of
+      // 32 different queries (append) both spread over all shared-memory banks
+      const int lstride = list_row_words(k, p.bufc);
       float* Ls = reinterpret_cast<float*>(smem + map.list_off);
-      int* Li = reinterpret_cast<int*>(Ls + (size_t)k * lstride);
-      float* Bs = reinterpret_cast<float*>(Li + (size_t)k * lstride);
-      int* Bi = reinterpret_cast<int*>(Bs + (size_t)kBufC * lstride);
+      int* Li = reinterpret_cast<int*>(Ls + k);
+      float* Bs = Ls + 2 * k;
+      int* Bi = reinterpret_cast<int*>(Ls + 2 * k + p.bufc);
       int cnt = 0;
       // per warp: [32 columns][rows_per_warp lanes] floats
       float* dump = reinterpret_cast<float*>(smem + map.dump_off) + (size_t)quarter * 32 * rows_per_warp;
@@ -1019,8 +1067,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       } else {
         if (live) {
           for (int j = 0; j < k; ++j) {
-            Ls[j * lstride + row] = -CUDART_INF_F;
-            Li[j * lstride + row] = -1;
+            Ls[(j) + row * lstride] = -CUDART_INF_F;
+            Li[(j) + row * lstride] = -1;
           }
         }
         __syncwarp();
@@ -1030,7 +1078,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
 
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (int u = blockIdx.x; u < n_super; u += gridDim.x) {
+      int sslot = 0;
+      uint32_t sph = 0;
+      while (true) {
+        mbar_wait(sched_full(sslot), sph);
+        const int u = tile_u[sslot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sched_empty(sslot));
+        if (++sslot == kSched) {
+          sslot = 0;
+          sph ^= 1u;
+        }
+        if (u < 0) break;
         const int nsub = min(S, p.n_tiles - u * S);
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
@@ -1108,18 +1167,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
                       thr = ls[0];
                       thr_raw = cosine ? cosine_raw_bound(thr, nq, inv_qs, ndmin, ndmax) : thr;
                     } else {
-                      Bs[cnt * lstride + row] = x;  // O(1) append; threshold stays stale until the flush
-                      Bi[cnt * lstride + row] = idx;
+                      Bs[(cnt) + row * lstride] = x;  // O(1) append; threshold stays stale until the flush
+                      Bi[(cnt) + row * lstride] = idx;
                       ++cnt;
                     }
                   }
                 }
                 if (!REGLIST) {
-                  uint32_t full = __ballot_sync(0xffffffffu, cnt == kBufC);
+                  uint32_t full = __ballot_sync(0xffffffffu, cnt == p.bufc);
                   while (full) {
                     const int ql = __ffs(full) - 1;
                     full &= full - 1;
-                    const float nt = flush_candidates(Ls, Li, Bs, Bi, lstride, quarter * rows_per_warp + ql, kBufC, k, lane);
+                    const float nt = flush_candidates(Ls, Li, Bs, Bi, lstride, quarter * rows_per_warp + ql, p.bufc, k, lane);
                     if (lane == ql) {
                       thr = nt;
                       cnt = 0;
@@ -1166,8 +1225,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
           }
         } else {
           for (int j = 0; j < k; ++j) {
-            const float raw = Ls[j * lstride + row];
-            const int id = Li[j * lstride + row];
+            const float raw = Ls[(j) + row * lstride];
+            const int id = Li[(j) + row * lstride];
             cs[j] = id < 0 ? -CUDART_INF_F : (cosine ? raw : raw * qs);
             ci[j] = id;
           }
@@ -1226,6 +1285,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
         if (atomicAdd(p.sync + 1, 1u) == mergers - 1u) {
           atomicExch(p.sync, 0u);
           atomicExch(p.sync + 1, 0u);
+          atomicExch(p.sync + 4, 0u);  // tile counter of the dynamic scheduler
         }
       }
     }
@@ -1237,7 +1297,7 @@ size_t fused_tail_smem_bytes(int n_lists, int k, int world) {
   return merge_res_bytes(k) + std::max((size_t)n_lists * k * 8, (size_t)world * k * 12);
 }
 int fused_tail_smem_capacity(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages) {
-  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages).bar_off;
+  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages, kBufC).bar_off;
 }
 
 // Plain merge: one CTA per query, lists -> out[q][0..k).
@@ -1330,7 +1390,7 @@ cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dt
 
 template <int NACC, bool REGLIST, bool QRES>
 static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t stream) {
-  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, QRES, p.qstages);
+  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, QRES, p.qstages, p.bufc);
   auto kern = fused_search_kernel<NACC, REGLIST, QRES>;
   const int bytes = (int)map.total + 1024;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -1339,8 +1399,8 @@ static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t 
   return cudaGetLastError();
 }
 
-int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages) {
-  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages).total + 1024;
+int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages, int bufc) {
+  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages, bufc).total + 1024;
 }
 int fused_reg_k() { return kRegK; }
 

@@ -27,9 +27,10 @@ g = torch.Generator().manual_seed(0)
 q = torch.randn(256, 1024, generator=g); q = q / q.norm(dim=1, keepdim=True)
 q = ({"bf16": q.bfloat16(), "fp16": q.half(), "fp32": q}[dtype]).float().cuda()
 terms = 2 if dtype == "fp32" else 1
-oi = torch.empty((B, k), dtype=torch.int64, device="cuda")
-os_ = torch.empty((B, k), dtype=torch.float32, device="cuda")
+oi = torch.empty((256, 128), dtype=torch.int64, device="cuda")
+os_ = torch.empty((256, 128), dtype=torch.float32, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
+B0, k0 = B, k
 
 
 def go(n):
@@ -48,14 +49,15 @@ for rep in range(reps):
     for env in envs:
         for key in KEYS:
             os.environ.pop(key, None)
-        os.environ.update({k_: str(v) for k_, v in env.items()})
+        os.environ.update({k_: str(v) for k_, v in env.items() if not k_.startswith("_")})
+        B, k = int(env.get("_B", B0)), int(env.get("_k", k0))      # "_B" / "_k" override the batch / k per variant
         name = json.dumps(env)
         try:
             go(3); torch.cuda.synchronize()
             time.sleep(1.0)
             go(5); torch.cuda.synchronize()
             est = timed(10)
-            nb = max(20, int(0.05 / (est / 1e3)))           # ~50 ms burst
+            nb = max(8, int(0.05 / (est / 1e3)))            # ~50 ms burst
             burst = timed(nb)
             with Power() as pw:
                 t0 = time.time()
