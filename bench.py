@@ -61,10 +61,12 @@ def workload_config(a, world):
 # clocks sampler (nvml), runs during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+    # NVML clocks-event-reason bits
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
 
     def __init__(self, device_index):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.power, self.mask, self.max_mhz, self.limit_w = [], [], 0, None, None
         self._stop = threading.Event()
         self._thr = None
         try:
@@ -73,20 +75,23 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            try:
+                self.limit_w = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.h) / 1000.0
+            except Exception:
+                pass
         except Exception:
             self.nv = None
 
     def _run(self):
         while not self._stop.is_set():
             try:
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def __enter__(self):
         if self.nv:
@@ -100,10 +105,13 @@ class ClockSampler:
             self._thr.join()
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": reasons, "reasons_mask": hex(self.mask), "samples": len(self.samples)}
+        if self.power:
+            out["power_w_max"] = round(max(self.power), 1)
+            out["power_limit_w"] = self.limit_w
+        return out
 
 
 # ------------------------------------------------------------------------------------------------

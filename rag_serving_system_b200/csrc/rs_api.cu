@@ -78,8 +78,7 @@ struct rs_index {
   float* cand_score = nullptr;
   int* cand_idx = nullptr;
   float* q_dev = nullptr;           // staging for host queries
-  long long* out_idx_dev = nullptr;  // staging for host outputs
-  float* out_score_dev = nullptr;
+  long long* out_idx_dev = nullptr;  // staging for host outputs: [indices][scores] of one call, back to back
   void* ingest_dev = nullptr;
   void* pinned = nullptr;  // pinned host staging (queries in, results out, ingest chunks)
   size_t pinned_bytes = 0;
@@ -207,7 +206,6 @@ void free_all(rs_index* ix) {
   cudaFree(ix->cand_idx);
   cudaFree(ix->q_dev);
   cudaFree(ix->out_idx_dev);
-  cudaFree(ix->out_score_dev);
   cudaFree(ix->ingest_dev);
   cudaFree(ix->sync);
   cudaFree(ix->debug_ts);
@@ -450,8 +448,8 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   RS_ALLOC(cudaMalloc(&ix->cand_score, cand_elems * sizeof(float)));
   RS_ALLOC(cudaMalloc(&ix->cand_idx, cand_elems * sizeof(int)));
   RS_ALLOC(cudaMalloc(&ix->q_dev, q_bytes));
-  RS_ALLOC(cudaMalloc(&ix->out_idx_dev, out_elems * sizeof(long long)));
-  RS_ALLOC(cudaMalloc(&ix->out_score_dev, out_elems * sizeof(float)));
+  // host-buffer searches write [indices int64][scores float] back to back so ONE copy brings both home
+  RS_ALLOC(cudaMalloc(&ix->out_idx_dev, out_elems * (sizeof(long long) + sizeof(float))));
   RS_ALLOC(cudaMalloc(&ix->ingest_dev, kIngestChunkBytes));
   RS_ALLOC(cudaMallocHost(&ix->pinned, ix->pinned_bytes));
   RS_ALLOC(cudaMalloc(&ix->sync, 256));
@@ -603,10 +601,11 @@ RS_API int rs_search(rs_index* ix, const float* q_host, int32_t B, int32_t k, in
   if (ix->planes == 2) query_terms = 2;
   auto enqueue = [&]() -> int {  // H2D -> prep -> fused -> merge -> D2H, all on ix->stream
     RS_CUDA(cudaMemcpyAsync(ix->q_dev, pin, q_bytes, cudaMemcpyHostToDevice, ix->stream));
-    int rc = search_device_locked(ix, ix->q_dev, B, k, metric, query_terms, ix->out_idx_dev, ix->out_score_dev, ix->stream);
+    float* score_dev = reinterpret_cast<float*>(ix->out_idx_dev + n_out);  // right behind this call's indices
+    int rc = search_device_locked(ix, ix->q_dev, B, k, metric, query_terms, ix->out_idx_dev, score_dev, ix->stream);
     if (rc != RS_OK) return rc;
-    RS_CUDA(cudaMemcpyAsync(pin_idx, ix->out_idx_dev, n_out * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
-    RS_CUDA(cudaMemcpyAsync(pin_score, ix->out_score_dev, n_out * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+    RS_CUDA(cudaMemcpyAsync(pin_idx, ix->out_idx_dev, n_out * (sizeof(long long) + sizeof(float)), cudaMemcpyDeviceToHost,
+                            ix->stream));  // pin_score == pin_idx + n_out
     return RS_OK;
   };
   memcpy(pin, q_host, q_bytes);
