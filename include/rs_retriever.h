@@ -131,10 +131,11 @@ RS_API int rs_merge_device(int32_t device, const float* scores_dev, const int64_
 /* Multi-GPU candidate exchange over NVLink peer memory, one process per GPU (an alternative to
  * the NCCL all-gather + rs_merge_device above; same results).  Each rank creates an exchange
  * buffer, exports its 64-byte CUDA IPC handle, and imports every peer's handle (exchanged by the
- * host program, e.g. with torch.distributed.all_gather).  rs_search_exchange then runs
+ * host program, e.g. with torch.distributed.all_gather).  rs_search_exchange then runs, as ONE kernel
+ * launch per search (two when the batch or dimension needs the separate query-prep kernel),
  *   query prep -> fused score+select -> [local merge + peer stores of each query's k candidates
  *   into every GPU's buffer + per-query epoch flag + wait for all ranks' flags + final merge]
- * as three kernels with no collective call; every rank ends with the same global top-k.
+ * with no collective call; every rank ends with the same global top-k.
  * All ranks must call it in the same order with the same B and k. */
 typedef struct rs_xchg rs_xchg;
 RS_API int rs_xchg_create(int32_t device, int32_t world, int32_t rank, int32_t max_batch, int32_t max_k, rs_xchg** out);
