@@ -144,6 +144,17 @@ RS_API int rs_xchg_import(rs_xchg* x, int32_t peer_rank, const void* handle64);
 RS_API int rs_xchg_destroy(rs_xchg* x);
 RS_API int rs_search_exchange(rs_index* ix, rs_xchg* x, const float* q_dev, int32_t B, int32_t k, int32_t metric,
                        int32_t query_terms, int64_t* out_idx_dev, float* out_score_dev, void* stream);
+/* Deferred (pipelined) form for back-to-back searches: the launch pushes this search's rows to the peers and
+ * returns without waiting for them; its final merge - into the out_* buffers given HERE - is done by the tail
+ * of the NEXT rs_search_exchange_async launch (while that launch waits for its own slowest CTAs) or by
+ * rs_xchg_flush.  The out_* buffers of call i are therefore valid, in stream order, after call i+1 or after the
+ * flush, and must stay allocated until then.  No rank ever waits for a peer's current search, so ranks run at
+ * their own pace with one search of slack (three exchange-buffer parities).  Every rank must issue the same
+ * sequence of calls.  rs_search_exchange flushes a pending search first; call rs_xchg_flush before
+ * rs_xchg_destroy. */
+RS_API int rs_search_exchange_async(rs_index* ix, rs_xchg* x, const float* q_dev, int32_t B, int32_t k, int32_t metric,
+                             int32_t query_terms, int64_t* out_idx_dev, float* out_score_dev, void* stream);
+RS_API int rs_xchg_flush(rs_index* ix, rs_xchg* x, void* stream);
 
 /* Read back the represented values of rows [row0,row0+nrows) as float (inverse of the tiling);
  * used by the tests (ingest round trip) and by the CPU-baseline sampler. */

@@ -20,7 +20,7 @@ EXPORTS = (
     "rs_version", "rs_last_error", "rs_create", "rs_destroy", "rs_load_rows", "rs_fill_synthetic",
     "rs_finalize", "rs_search", "rs_search_device", "rs_merge_device", "rs_get_rows",
     "rs_get_norms", "rs_get_image", "rs_get_stats", "rs_get_kernel_times",
-    "rs_debug_plan", "rs_debug_timestamps", "rs_xchg_create", "rs_xchg_export", "rs_xchg_import", "rs_xchg_destroy", "rs_search_exchange",
+    "rs_debug_plan", "rs_debug_timestamps", "rs_xchg_create", "rs_xchg_export", "rs_xchg_import", "rs_xchg_destroy", "rs_search_exchange", "rs_search_exchange_async", "rs_xchg_flush",
 )
 
 
@@ -86,6 +86,8 @@ def load() -> C.CDLL:
         "rs_xchg_import": [vp, i32, vp],
         "rs_xchg_destroy": [vp],
         "rs_search_exchange": [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
+        "rs_search_exchange_async": [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
+        "rs_xchg_flush": [vp, vp, vp],
         "rs_get_rows": [vp, i64, i64, vp],
         "rs_get_norms": [vp, i64, i64, vp],
         "rs_get_image": [vp, i64, i64, vp],
@@ -223,6 +225,15 @@ class Exchange:
                metric: str = "dot", query_terms: int = 1, stream: int = 0):
         check(self.lib.rs_search_exchange(index.h, self.h, q_ptr, B, k, METRICS[metric], query_terms, out_idx_ptr,
                                           out_score_ptr, stream), "rs_search_exchange")
+
+    def search_async(self, index: "Index", q_ptr: int, B: int, k: int, out_idx_ptr: int, out_score_ptr: int,
+                     metric: str = "dot", query_terms: int = 1, stream: int = 0):
+        """Deferred exchange: the out buffers of this call are valid after the NEXT search_async or flush."""
+        check(self.lib.rs_search_exchange_async(index.h, self.h, q_ptr, B, k, METRICS[metric], query_terms, out_idx_ptr,
+                                                out_score_ptr, stream), "rs_search_exchange_async")
+
+    def flush(self, index: "Index", stream: int = 0):
+        check(self.lib.rs_xchg_flush(index.h, self.h, stream), "rs_xchg_flush")
 
     def close(self):
         if getattr(self, "h", None):

@@ -110,13 +110,62 @@ struct rs_xchg {
   int device = 0, world = 1, rank = 0, max_batch = 0, max_k = 0;
   size_t slot_bytes = 0, parity_bytes = 0, total_bytes = 0;
   size_t header_bytes = 0;               // flags[2 parities][8 ranks][max_batch] u32, padded to 256 B
-  uint8_t* local = nullptr;              // [flags][parity 0: world slots][parity 1: world slots]
+  uint8_t* local = nullptr;              // [flags][parity 0: world slots][parity 1: ...][parity 2: ...]
   uint8_t* peer[rs::kMaxPeers] = {};     // peer[g] = GPU g's buffer mapped into this process (peer[rank] = local)
   bool opened[rs::kMaxPeers] = {};
   unsigned int epoch = 0;
+  // deferred mode: the search whose rows are pushed but whose final merge has not run yet
+  struct Pending {
+    bool valid = false;
+    unsigned int epoch = 0;
+    int B = 0, k = 0;
+    long long* out_idx = nullptr;
+    float* out_score = nullptr;
+  } pending;
 };
+constexpr unsigned int kXchgParities = 3;  // epoch % 3: a rank is never more than one search ahead of a peer's reads
 
 namespace {
+
+// kernel arguments of one search's exchange: where this rank's rows go on every GPU, where the world's rows
+// for it arrive locally, and (deferred mode) where its final rows are to be written
+rs::ExchangeArgs make_exchange_args(const rs_xchg* xg, unsigned int epoch, int B, int k, int q0, long long* out_idx,
+                                    float* out_score) {
+  rs::ExchangeArgs ea;
+  memset(&ea, 0, sizeof(ea));
+  const unsigned int parity = epoch % kXchgParities;
+  ea.world = xg->world;
+  ea.q0 = q0;
+  ea.epoch = epoch;
+  for (int g = 0; g < xg->world; ++g) {
+    uint8_t* slot = xg->peer[g] + xg->header_bytes + parity * xg->parity_bytes + (size_t)xg->rank * xg->slot_bytes;
+    ea.dest_idx[g] = reinterpret_cast<long long*>(slot);
+    ea.dest_score[g] = reinterpret_cast<float*>(slot + (size_t)B * k * 8);
+    ea.dest_flag[g] = reinterpret_cast<unsigned int*>(xg->peer[g]) + ((size_t)parity * rs::kMaxPeers + xg->rank) * xg->max_batch;
+  }
+  ea.wait_flags = reinterpret_cast<const unsigned int*>(xg->local) + (size_t)parity * rs::kMaxPeers * xg->max_batch;
+  ea.flag_stride = xg->max_batch;
+  const uint8_t* base = xg->local + xg->header_bytes + parity * xg->parity_bytes;
+  ea.local_idx = reinterpret_cast<const long long*>(base);
+  ea.local_score = reinterpret_cast<const float*>(base + (size_t)B * k * 8);
+  ea.idx_list_stride = (long long)(xg->slot_bytes / 8);
+  ea.score_list_stride = (long long)(xg->slot_bytes / 4);
+  ea.out_idx = out_idx;
+  ea.out_score = out_score;
+  ea.n_queries = B;
+  ea.k = k;
+  return ea;
+}
+
+// final merge of the pending (pushed, unmerged) search as a kernel of its own
+int flush_pending(rs_xchg* xg, cudaStream_t stream) {
+  if (!xg->pending.valid) return RS_OK;
+  const rs_xchg::Pending& pd = xg->pending;
+  rs::ExchangeArgs ea = make_exchange_args(xg, pd.epoch, pd.B, pd.k, 0, pd.out_idx, pd.out_score);
+  RS_CUDA(rs::launch_exchange_finalize(ea, stream));
+  xg->pending.valid = false;
+  return RS_OK;
+}
 
 int max_cap_rows(int kc, int terms, int k, int min_stages, int cps, int q_resident, int bufc = 32) {
   // largest bpad (multiple of 8, <= 128) that leaves at least min_stages ring slots
@@ -224,7 +273,7 @@ void free_all(rs_index* ix) {
 
 // one search on device buffers; all launches go to `stream`
 int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int metric, int terms, long long* out_idx,
-                         float* out_score, cudaStream_t stream, rs_xchg* xg = nullptr) {
+                         float* out_score, cudaStream_t stream, rs_xchg* xg = nullptr, bool deferred = false) {
   if (!ix->finalized) return fail(RS_E_STATE, "rs_finalize has not been called");
   if (B <= 0 || B > ix->cfg.max_batch) return fail(RS_E_INVALID, "B=%d outside [1,%d]", B, ix->cfg.max_batch);
   if (k <= 0 || k > ix->cfg.max_k) return fail(RS_E_INVALID, "k=%d outside [1,%d]", k, ix->cfg.max_k);
@@ -247,7 +296,16 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   const int tail_cap = rs::fused_tail_smem_capacity(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms);
   const bool fused_tail = env_int("RS_FUSED_TAIL", 1) != 0 &&
                           rs::fused_tail_smem_bytes(n_work, k, xg ? xg->world : 1) <= (size_t)tail_cap;
-  const int grid = fused_tail ? std::max(n_work, std::min(pl.per_pass, ix->sm_count)) : n_work;
+  // deferred exchange: this launch pushes its rows and final-merges the pending search; anything that cannot
+  // do both in the fused tail flushes the pending search with a kernel of its own and runs synchronously
+  const bool defer = deferred && xg && fused_tail && pl.passes == 1;
+  if (xg && xg->pending.valid &&
+      (!defer || rs::fused_tail_smem_bytes(1, xg->pending.k, xg->world) > (size_t)tail_cap)) {
+    rc = flush_pending(xg, stream);
+    if (rc != RS_OK) return rc;
+  }
+  const int merge_ctas = std::max(pl.per_pass, (defer && xg->pending.valid) ? xg->pending.B : 0);
+  const int grid = fused_tail ? std::max(n_work, std::min(merge_ctas, ix->sm_count)) : n_work;
   ix->stats.grid = grid;
   ix->stats.stages = pl.stages;
   ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms, pl.bufc);
@@ -259,13 +317,12 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   ix->stats.query_terms = terms;
   ix->stats.launches = 0;
   ix->stats.bytes_streamed = 0;
-  unsigned int epoch = 0, parity = 0;
+  unsigned int epoch = 0;
   if (xg) {
     if (B > xg->max_batch || k > xg->max_k) return fail(RS_E_INVALID, "B=%d k=%d exceed the exchange buffer (%d, %d)", B, k, xg->max_batch, xg->max_k);
     for (int g = 0; g < xg->world; ++g)
       if (!xg->peer[g]) return fail(RS_E_STATE, "exchange buffer of rank %d has not been imported", g);
     epoch = ++xg->epoch;
-    parity = epoch & 1u;
   }
   for (int pass = 0; pass < pl.passes; ++pass) {
     const int b0 = pass * pl.per_pass;
@@ -323,24 +380,14 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.lo_coef = ix->plane_dtype == RS_DTYPE_FP16 ? ldexpf(1.0f, -RS_FP16_SPLIT_SHIFT) : 1.0f;
     rs::ExchangeArgs ea;
     memset(&ea, 0, sizeof(ea));
-    if (xg) {
-      ea.world = xg->world;
-      ea.q0 = b0;
-      ea.epoch = epoch;
-      for (int g = 0; g < xg->world; ++g) {
-        uint8_t* slot = xg->peer[g] + xg->header_bytes + parity * xg->parity_bytes + (size_t)xg->rank * xg->slot_bytes;
-        ea.dest_idx[g] = reinterpret_cast<long long*>(slot);
-        ea.dest_score[g] = reinterpret_cast<float*>(slot + (size_t)B * k * 8);
-        ea.dest_flag[g] = reinterpret_cast<unsigned int*>(xg->peer[g]) +
-                          ((size_t)parity * rs::kMaxPeers + xg->rank) * xg->max_batch;
-      }
-      ea.wait_flags = reinterpret_cast<const unsigned int*>(xg->local) + (size_t)parity * rs::kMaxPeers * xg->max_batch;
-      ea.flag_stride = xg->max_batch;
-      const uint8_t* base = xg->local + xg->header_bytes + parity * xg->parity_bytes;
-      ea.local_idx = reinterpret_cast<const long long*>(base);
-      ea.local_score = reinterpret_cast<const float*>(base + (size_t)B * k * 8);
-      ea.idx_list_stride = (long long)(xg->slot_bytes / 8);
-      ea.score_list_stride = (long long)(xg->slot_bytes / 4);
+    if (xg) ea = make_exchange_args(xg, epoch, B, k, b0, out_idx, out_score);
+    if (defer) {
+      // this launch pushes the rows of search `epoch` and final-merges the pending one
+      p.tail_mode = 3;
+      memset(&p.xp, 0, sizeof(p.xp));
+      if (xg->pending.valid)
+        p.xp = make_exchange_args(xg, xg->pending.epoch, xg->pending.B, xg->pending.k, 0, xg->pending.out_idx,
+                                  xg->pending.out_score);
     }
     p.x = ea;
     if (!ix->record_events || env_int("RS_NO_EVENTS", 0)) {
@@ -361,6 +408,14 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
         RS_CUDA(rs::launch_exchange_merge(ix->cand_score, ix->cand_idx, n_work, nb, k, ix->cfg.row_offset,
                                           out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, ea, stream));
       }
+    }
+    if (defer) {
+      xg->pending.valid = true;
+      xg->pending.epoch = epoch;
+      xg->pending.B = B;
+      xg->pending.k = k;
+      xg->pending.out_idx = out_idx;
+      xg->pending.out_score = out_score;
     }
     ix->stats.launches += 1 + (inline_prep ? 0 : 1) + (fused_tail ? 0 : 1);
     ix->stats.bytes_streamed += (int64_t)ix->corpus_bytes;
@@ -676,8 +731,8 @@ RS_API int rs_xchg_create(int32_t device, int32_t world, int32_t rank, int32_t m
   x->max_k = max_k;
   x->slot_bytes = (((size_t)max_batch * max_k * 12) + 255) & ~size_t(255);
   x->parity_bytes = x->slot_bytes * world;
-  x->header_bytes = (((size_t)2 * rs::kMaxPeers * max_batch * sizeof(unsigned int)) + 255) & ~size_t(255);
-  x->total_bytes = x->header_bytes + 2 * x->parity_bytes;
+  x->header_bytes = (((size_t)kXchgParities * rs::kMaxPeers * max_batch * sizeof(unsigned int)) + 255) & ~size_t(255);
+  x->total_bytes = x->header_bytes + kXchgParities * x->parity_bytes;
   cudaError_t e = cudaMalloc(&x->local, x->total_bytes);
   if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->total_bytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -734,6 +789,23 @@ RS_API int rs_search_exchange(rs_index* ix, rs_xchg* x, const float* q_dev, int3
   RS_CUDA(cudaSetDevice(ix->cfg.device));
   return search_device_locked(ix, q_dev, B, k, metric, query_terms, reinterpret_cast<long long*>(out_idx_dev),
                               out_score_dev, static_cast<cudaStream_t>(stream), x);
+}
+
+RS_API int rs_search_exchange_async(rs_index* ix, rs_xchg* x, const float* q_dev, int32_t B, int32_t k, int32_t metric,
+                                    int32_t query_terms, int64_t* out_idx_dev, float* out_score_dev, void* stream) {
+  if (!ix || !x || !q_dev || !out_idx_dev || !out_score_dev) return fail(RS_E_INVALID, "null argument");
+  if (x->device != ix->cfg.device) return fail(RS_E_INVALID, "index and exchange buffer live on different devices");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  return search_device_locked(ix, q_dev, B, k, metric, query_terms, reinterpret_cast<long long*>(out_idx_dev),
+                              out_score_dev, static_cast<cudaStream_t>(stream), x, /*deferred=*/true);
+}
+
+RS_API int rs_xchg_flush(rs_index* ix, rs_xchg* x, void* stream) {
+  if (!ix || !x) return fail(RS_E_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  return flush_pending(x, static_cast<cudaStream_t>(stream));
 }
 
 RS_API int rs_get_rows(rs_index* ix, int64_t row0, int64_t nrows, float* out_host) {

@@ -20,6 +20,11 @@ struct ExchangeArgs {
   const float* local_score;             //                                      (score block)
   long long idx_list_stride;            // elements between consecutive ranks' slots
   long long score_list_stride;
+  // deferred mode: where the final rows of THIS search go once a later launch (or rs_xchg_flush) merges them
+  float* out_score;
+  long long* out_idx;
+  int n_queries;                        // queries of the search these arguments describe
+  int k;
 };
 
 struct SearchParams {
@@ -56,14 +61,16 @@ struct SearchParams {
   int inline_prep;                   // 1: the CTA builds its own resident Q image (no query_prep_kernel launch)
   int corpus_scale_exp;              // power-of-two pre-scale of an fp32 corpus (folded into qscale)
   int n_work;                        // CTAs that own tiles and write candidate lists (= lists per query)
-  int tail_mode;                     // 0: candidates only; 1: + in-kernel merge; 2: + peer exchange and final merge
+  int tail_mode;                     // 0: candidates only; 1: + in-kernel merge; 2: + peer exchange and final merge;
+                                     // 3: deferred exchange - push this search's rows, final-merge the PREVIOUS search (xp)
   unsigned int* sync;                // [0] arrivals of worker CTAs, [1] departures of merging CTAs, [4] next tile (dynamic scheduler)
   int dyn_sched;                     // 1: supertiles after the first come from sync[4] (work stealing); 0: static round-robin
   unsigned int* err_flag;            // mapped host word, set to 1 if the arrival wait timed out
   float* out_score;                  // tail_mode != 0: final [n_queries][k]
   long long* out_idx;
   long long idx_offset;              // global index of this shard's row 0
-  ExchangeArgs x;                    // tail_mode == 2
+  ExchangeArgs x;                    // tail_mode >= 2
+  ExchangeArgs xp;                   // tail_mode == 3: the previous, still unmerged search (n_queries == 0: none)
   unsigned long long* debug_ts;      // null, or [grid][8] globaltimer stamps of the kernel's phases (RS_DEBUG_TS=1)
 };
 
@@ -79,6 +86,7 @@ cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n
 cudaError_t launch_exchange_merge(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int k,
                                   long long idx_offset, float* out_score, long long* out_idx, const ExchangeArgs& x,
                                   cudaStream_t stream);
+cudaError_t launch_exchange_finalize(const ExchangeArgs& x, cudaStream_t stream);
 cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx, int n_lists, int n_queries, int kc,
                              int k, long long score_list_stride, long long idx_list_stride, float* out_score,
                              long long* out_idx, cudaStream_t stream);

@@ -687,7 +687,8 @@ __device__ __forceinline__ void merge_query_local(const float* __restrict__ cand
 // the search epoch, wait until every rank's flag for this query shows the epoch, then merge the
 // world lists from the local exchange buffer back into m.res_*.  A CTA only ever waits for the CTAs
 // of the same query on other GPUs.  Buffers are double-buffered by epoch parity (host side).
-__device__ __forceinline__ void exchange_query(const ExchangeArgs& x, int q, int k, const MergeSmem& m, int nthr) {
+// push: called by the whole CTA after the local merge left query q's row in m.res_*
+__device__ __forceinline__ void push_row(const ExchangeArgs& x, int q, int k, const MergeSmem& m) {
   const int lane = threadIdx.x & 31;
   if (threadIdx.x < 32) {
     const size_t qg = (size_t)(x.q0 + q) * k;
@@ -700,6 +701,11 @@ __device__ __forceinline__ void exchange_query(const ExchangeArgs& x, int q, int
     __syncwarp();
     if (lane < x.world) st_volatile_u32(x.dest_flag[lane] + x.q0 + q, x.epoch);
   }
+}
+// finalize: wait until every rank's flag for query q shows x.epoch, then merge the world lists from the
+// local exchange buffer into m.res_*.  Ends with a barrier.
+__device__ __forceinline__ void finalize_query(const ExchangeArgs& x, int q, int k, const MergeSmem& m, int nthr) {
+  const int lane = threadIdx.x & 31;
   if (threadIdx.x < x.world) {
     long long spins = 0;
     const unsigned int* f = x.wait_flags + (size_t)threadIdx.x * x.flag_stride + x.q0 + q;
@@ -739,6 +745,11 @@ __device__ __forceinline__ void exchange_query(const ExchangeArgs& x, int q, int
     select_rounds(load, x.world, k, k, 0, m.res_s, m.res_i, lane);
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void exchange_query(const ExchangeArgs& x, int q, int k, const MergeSmem& m, int nthr) {
+  push_row(x, q, k, m);
+  finalize_query(x, q, k, m, nthr);
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
@@ -1255,7 +1266,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       atomicAdd(p.sync, 1u);
       stamp(p.debug_ts, 4);  // candidates published, arrived
     }
-    if ((int)blockIdx.x < p.n_queries) {
+    // tail_mode 3 (deferred exchange): this launch also final-merges the PREVIOUS search, whose rows the
+    // peers pushed one search ago - it does so before waiting for its own grid, i.e. while slower CTAs of
+    // this GPU are still scanning, and it never waits for a peer's current search: every rank runs at its
+    // own pace (one search of slack), and the NVLink round trip leaves the critical path.
+    const int prev_nq = p.tail_mode == 3 ? p.xp.n_queries : 0;
+    const int duty = max(p.n_queries, prev_nq);
+    if ((int)blockIdx.x < duty) {
+      for (int q = blockIdx.x; q < prev_nq; q += gridDim.x) {
+        const MergeSmem mp = merge_smem_at(smem, p.xp.k);
+        finalize_query(p.xp, q, p.xp.k, mp, kThreads);
+        for (int j = threadIdx.x; j < p.xp.k; j += kThreads) {
+          p.xp.out_score[(size_t)q * p.xp.k + j] = mp.res_s[j];
+          p.xp.out_idx[(size_t)q * p.xp.k + j] = mp.res_i[j];
+        }
+        __syncthreads();
+      }
       if (threadIdx.x == 0) {
         long long spins = 0;
         while (ld_acquire_gpu_u32(p.sync) < (unsigned int)p.n_work) {
@@ -1272,16 +1298,20 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       const MergeSmem m = merge_smem_at(smem, p.k);
       for (int q = blockIdx.x; q < ((p.debug_flags & 4) ? 0 : p.n_queries); q += gridDim.x) {
         merge_query_local(p.cand_score, p.cand_idx, p.n_work, p.k, p.idx_offset, q, m, kThreads, p.debug_ts);
-        if (p.tail_mode == 2) exchange_query(p.x, q, p.k, m, kThreads);
-        for (int j = threadIdx.x; j < p.k; j += kThreads) {
-          p.out_score[(size_t)q * p.k + j] = m.res_s[j];
-          p.out_idx[(size_t)q * p.k + j] = m.res_i[j];
+        if (p.tail_mode == 3) {
+          push_row(p.x, q, p.k, m);  // the final merge of this search happens in the next launch / the flush
+        } else {
+          if (p.tail_mode == 2) exchange_query(p.x, q, p.k, m, kThreads);
+          for (int j = threadIdx.x; j < p.k; j += kThreads) {
+            p.out_score[(size_t)q * p.k + j] = m.res_s[j];
+            p.out_idx[(size_t)q * p.k + j] = m.res_i[j];
+          }
         }
         __syncthreads();
       }
       if (threadIdx.x == 0) {
         stamp(p.debug_ts, 6);  // this CTA's queries merged and written
-        const unsigned int mergers = (unsigned int)min((int)gridDim.x, p.n_queries);
+        const unsigned int mergers = (unsigned int)min((int)gridDim.x, duty);
         if (atomicAdd(p.sync + 1, 1u) == mergers - 1u) {
           atomicExch(p.sync, 0u);
           atomicExch(p.sync + 1, 0u);
@@ -1375,6 +1405,18 @@ __global__ void __launch_bounds__(kMergeThreads) exchange_merge_kernel(const flo
   for (int j = threadIdx.x; j < k; j += kMergeThreads) {
     out_score[(size_t)q * k + j] = m.res_s[j];
     out_idx[(size_t)q * k + j] = m.res_i[j];
+  }
+}
+
+// Deferred exchange, last step: final merge of a search whose rows have already been pushed (rs_xchg_flush).
+__global__ void __launch_bounds__(kMergeThreads) exchange_finalize_kernel(const ExchangeArgs x) {
+  extern __shared__ __align__(16) uint8_t merge_smem[];
+  const int q = blockIdx.x;
+  const MergeSmem m = merge_smem_at(merge_smem, x.k);
+  finalize_query(x, q, x.k, m, kMergeThreads);
+  for (int j = threadIdx.x; j < x.k; j += kMergeThreads) {
+    x.out_score[(size_t)q * x.k + j] = m.res_s[j];
+    x.out_idx[(size_t)q * x.k + j] = m.res_i[j];
   }
 }
 
@@ -1478,6 +1520,13 @@ cudaError_t launch_exchange_merge(const float* cand_score, const int* cand_idx, 
   }
   exchange_merge_kernel<<<n_queries, kMergeThreads, bytes, stream>>>(cand_score, cand_idx, n_lists, k, idx_offset,
                                                                      out_score, out_idx, x);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_exchange_finalize(const ExchangeArgs& x, cudaStream_t stream) {
+  if (x.world > kMaxPeers || x.n_queries <= 0) return cudaErrorInvalidValue;
+  const size_t bytes = merge_res_bytes(x.k) + (size_t)x.world * x.k * 12;
+  exchange_finalize_kernel<<<x.n_queries, kMergeThreads, bytes, stream>>>(x);
   return cudaGetLastError();
 }
 

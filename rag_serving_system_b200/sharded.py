@@ -131,6 +131,34 @@ class ShardedSearcher:
                            stream, score_list_stride=nb // 4, idx_list_stride=nb // 8)
         return out_i, out_s
 
+    def search_async(self, q_dev: torch.Tensor, k: int, metric: str = "dot", query_terms: int = 1):
+        """Pipelined form for back-to-back searches (p2p exchange): the launch pushes this search's rows to
+        the peers and never waits for them; the final merge of search i runs in the tail of search i+1 (or
+        in ``flush``).  The returned tensors are therefore valid, in stream order, after the NEXT
+        ``search_async`` / ``flush``; three output sets rotate, so keep at most two searches un-flushed
+        before reading.  Falls back to ``search`` when there is nothing to pipeline."""
+        if self.xchg is None:
+            return self.search(q_dev, k, metric, query_terms)
+        assert q_dev.is_cuda and q_dev.dtype == torch.float32 and q_dev.is_contiguous()
+        B = q_dev.shape[0]
+        key = ("async", B, k)
+        if key not in self._bufs:
+            dev = torch.device("cuda", self.device)
+            self._bufs[key] = [0] + [(torch.empty((B, k), dtype=torch.int64, device=dev),
+                                      torch.empty((B, k), dtype=torch.float32, device=dev)) for _ in range(3)]
+        ring = self._bufs[key]
+        ring[0] = (ring[0] + 1) % 3
+        out_i, out_s = ring[1 + ring[0]]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.xchg.search_async(self.index, q_dev.data_ptr(), B, k, out_i.data_ptr(), out_s.data_ptr(), metric,
+                               query_terms, stream)
+        return out_i, out_s
+
+    def flush(self):
+        """Final merge of the last ``search_async`` (no-op when nothing is pending)."""
+        if self.xchg is not None:
+            self.xchg.flush(self.index, torch.cuda.current_stream(self.device).cuda_stream)
+
     def search_host(self, q_host: torch.Tensor, k: int, metric: str = "dot", query_terms: int = 1):
         """End-to-end call with HOST buffers: pinned H2D of the queries, search, D2H of the result."""
         dev = torch.device("cuda", self.device)
@@ -140,6 +168,7 @@ class ShardedSearcher:
 
     def close(self):
         if self.xchg is not None:
+            self.flush()
             torch.cuda.synchronize(self.device)
             if dist.is_initialized():
                 dist.barrier(group=self.group)      # nobody unmaps a buffer a peer may still write

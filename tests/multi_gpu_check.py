@@ -50,6 +50,31 @@ def main():
             sw = o.check_topk(idx, sc, S, k, rtol=1e-5 if dtype == "fp32" else 2e-3, atol=1e-6)
             assert (idx[:, 0] == src).all()
             print(f"multi-gpu ok world={world} {dtype} {metric} k={k} B={B} exchange={exch} near-tie swaps={sw}", flush=True)
+        if exch == "p2p":
+            # pipelined (deferred) exchange: the final merge of search i runs in the tail of search i+1 or in
+            # flush(); every result must equal the synchronous search of the same queries, also when B and k
+            # change between calls and when synchronous searches are interleaved
+            seq = [(Q, k), (Q[::-1].copy(), k), (Q[: max(1, B // 2)].copy(), max(1, k // 2)), (Q, k), (Q[::-1].copy(), k)]
+            want = []
+            for Qi, ki in seq:
+                wi, ws = s.search(torch.from_numpy(Qi).cuda(), ki, metric, terms)
+                want.append((wi.clone(), ws.clone()))
+            got, prev = [], None
+            for Qi, ki in seq:
+                cur = s.search_async(torch.from_numpy(Qi).cuda(), ki, metric, terms)
+                if prev is not None:
+                    got.append((prev[0].clone(), prev[1].clone()))      # valid after the NEXT call (stream order)
+                prev = cur
+            s.flush()
+            got.append((prev[0].clone(), prev[1].clone()))
+            mid_i, mid_s = s.search_async(q_dev, k, metric, terms)          # pending search, then a synchronous one
+            si, ss = s.search(q_dev, k, metric, terms)
+            torch.cuda.synchronize()
+            assert torch.equal(mid_i, si) and torch.equal(mid_s, ss)
+            for n, ((gi, gs), (wi, ws)) in enumerate(zip(got, want)):
+                assert torch.equal(gi, wi) and torch.equal(gs, ws), f"deferred exchange: search {n} differs"
+            if rank == 0:
+                print(f"deferred exchange ok world={world} {dtype} {metric} k={k} B={B}", flush=True)
         s.close()
     dist.barrier()
     dist.destroy_process_group()

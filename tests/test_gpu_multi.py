@@ -25,6 +25,7 @@ def test_sharded_search_under_torchrun():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("multi-gpu ok") == 5
+    assert res.stdout.count("deferred exchange ok") == 3          # every p2p case also runs the pipelined form
 
 
 def test_single_process_multi_device_class(squad):
