@@ -54,7 +54,7 @@ struct SearchParams {
   int mma_m;                         // 128, or 64 when bpad <= 64 (half the tensor work / operand reads)
   int nbuf;                          // TMEM accumulator buffers (1 or 2); nbuf*sub*NACC*128 <= 512 columns
   int bufc;                          // k > 16: candidate-buffer entries per query before a flush (32, or 16 to save smem)
-  int debug_flags;                   // timing experiments only (RS_DEBUG_FLAGS): 1 = skip MMAs, 2 = skip epilogue, 4 = skip tail merge, 8 = skip inline prep
+  int debug_flags;                   // timing experiments only (RS_DEBUG_FLAGS): 1 = skip MMAs, 2 = skip epilogue, 4 = skip tail merge
   float lo_coef;                     // weight of the low-order accumulator (2^-11 for fp16 terms, 1 for bf16)
   // ---- single-launch search: query prep in the prologue, candidate merge (+ exchange) in the tail
   const float* q_f32;                // fp32 queries [n_queries][D]; read when inline_prep

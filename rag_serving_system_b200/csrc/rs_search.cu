@@ -656,9 +656,9 @@ __device__ __forceinline__ void select_parallel_keys(const unsigned long long* s
 
 // Local merge of one query: this GPU's per-CTA lists ([query][cta][k] layout, local int32 row ids)
 // -> m.res_* (global indices).  Called by the whole CTA; warp 0 runs the rounds.  Ends with a barrier.
-__device__ __forceinline__ void merge_query_local(const float* __restrict__ cand_score, const int* __restrict__ cand_idx,
-                                                  int n_lists, int k, long long idx_offset, int q, const MergeSmem& m,
-                                                  int nthr, unsigned long long* ts = nullptr) {
+__device__ __noinline__ void merge_query_local(const float* __restrict__ cand_score, const int* __restrict__ cand_idx,
+                                             int n_lists, int k, long long idx_offset, int q, const MergeSmem m,
+                                             int nthr, unsigned long long* ts = nullptr) {
   if (k <= kParMaxK) {
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(m.stage);
     stage_keys(cand_score, cand_idx, n_lists * k, (size_t)q * n_lists * k, s_key, nthr);
@@ -704,8 +704,10 @@ __device__ __forceinline__ void push_row(const ExchangeArgs& x, int q, int k, co
 }
 // finalize: wait until every rank's flag for query q shows x.epoch, then merge the world lists from the
 // local exchange buffer into m.res_*.  Ends with a barrier.
+__device__ __noinline__ void merge_world_lists(const float* __restrict__ local_score, const long long* __restrict__ local_idx,
+                                               long long score_list_stride, long long idx_list_stride, int world, size_t qoff,
+                                               int k, const MergeSmem m, int nthr);
 __device__ __forceinline__ void finalize_query(const ExchangeArgs& x, int q, int k, const MergeSmem& m, int nthr) {
-  const int lane = threadIdx.x & 31;
   if (threadIdx.x < x.world) {
     long long spins = 0;
     const unsigned int* f = x.wait_flags + (size_t)threadIdx.x * x.flag_stride + x.q0 + q;
@@ -714,20 +716,27 @@ __device__ __forceinline__ void finalize_query(const ExchangeArgs& x, int q, int
   }
   __threadfence_system();
   __syncthreads();
+  merge_world_lists(x.local_score, x.local_idx, x.score_list_stride, x.idx_list_stride, x.world, (size_t)(x.q0 + q) * k, k, m,
+                    nthr);
+}
+// merge of the G world lists of query q (already complete in the local exchange buffer) into m.res_*
+__device__ __noinline__ void merge_world_lists(const float* __restrict__ local_score, const long long* __restrict__ local_idx,
+                                               long long score_list_stride, long long idx_list_stride, int world, size_t qoff,
+                                               int k, const MergeSmem m, int nthr) {
+  const int lane = threadIdx.x & 31;
   long long* s_idx = reinterpret_cast<long long*>(m.stage);
-  float* s_score = reinterpret_cast<float*>(m.stage + (size_t)x.world * k * sizeof(long long));
-  stage_lists<long long>(x.local_score, x.local_idx, x.world, k, x.score_list_stride, x.idx_list_stride,
-                         (size_t)(x.q0 + q) * k, s_idx, s_score, nthr);
+  float* s_score = reinterpret_cast<float*>(m.stage + (size_t)world * k * sizeof(long long));
+  stage_lists<long long>(local_score, local_idx, world, k, score_list_stride, idx_list_stride, qoff, s_idx, s_score, nthr);
   if (k <= kParMaxK) {
     // the local row was consumed by the fan-out above (same warp 0 lanes) before the flags were raised
     for (int j = threadIdx.x; j < k; j += nthr) {
       m.res_s[j] = -CUDART_INF_F;
       m.res_i[j] = -1;
     }
-    for (int g = threadIdx.x; g < kMaxPeers; g += nthr) m.slot[g] = g < x.world ? g : -1;
+    for (int g = threadIdx.x; g < kMaxPeers; g += nthr) m.slot[g] = g < world ? g : -1;
     __syncthreads();
     rank_active_lists(
-        m.slot, x.world, k, k, [&](int pos) { return s_idx[pos] >= 0; },
+        m.slot, world, k, k, [&](int pos) { return s_idx[pos] >= 0; },
         [&](int a, int b) { return s_score[a] > s_score[b] || (s_score[a] == s_score[b] && s_idx[a] < s_idx[b]); },
         [&](int rank, int pos) {
           m.res_s[rank] = s_score[pos];
@@ -742,7 +751,7 @@ __device__ __forceinline__ void finalize_query(const ExchangeArgs& x, int q, int
       sc = s_score[l * k + j];
       id = s_idx[l * k + j];
     };
-    select_rounds(load, x.world, k, k, 0, m.res_s, m.res_i, lane);
+    select_rounds(load, world, k, k, 0, m.res_s, m.res_i, lane);
   }
   __syncthreads();
 }
