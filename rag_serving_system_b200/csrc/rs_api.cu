@@ -84,6 +84,7 @@ struct rs_index {
   size_t pinned_bytes = 0;
   cudaStream_t stream = nullptr;
   unsigned int* sync = nullptr;      // device counters of the fused kernel's tail (arrivals, departures)
+  float* g_best = nullptr;           // shared bound table [sm_count][128] (k > 16 searches)
   unsigned long long* debug_ts = nullptr;  // RS_DEBUG_TS=1: [grid][8] phase stamps of the last fused launch
   unsigned int* err_flag = nullptr;  // mapped pinned word the kernel raises if its arrival wait times out
   // CUDA-event pairs around every fused-kernel launch (on the launching stream) so callers can
@@ -257,6 +258,7 @@ void free_all(rs_index* ix) {
   cudaFree(ix->out_idx_dev);
   cudaFree(ix->ingest_dev);
   cudaFree(ix->sync);
+  cudaFree(ix->g_best);
   cudaFree(ix->debug_ts);
   if (ix->err_flag) cudaFreeHost(ix->err_flag);
   if (ix->pinned) cudaFreeHost(ix->pinned);
@@ -345,6 +347,11 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.out_score = out_score + (size_t)b0 * k;
     p.out_idx = out_idx + (size_t)b0 * k;
     p.idx_offset = ix->cfg.row_offset;
+    if (k > rs::fused_reg_k() && n_work >= k && env_int("RS_SHARED_BOUND", 1) != 0) {
+      // 0xff bytes = NaN = "this CTA has not published a score for this query yet"
+      RS_CUDA(cudaMemsetAsync(ix->g_best, 0xff, (size_t)n_work * pl.bpad * sizeof(float), stream));
+      p.g_best = ix->g_best;
+    }
     if (env_int("RS_DEBUG_TS", 0)) {
       if (!ix->debug_ts) RS_CUDA(cudaMalloc(&ix->debug_ts, (size_t)ix->sm_count * 8 * sizeof(unsigned long long)));
       RS_CUDA(cudaMemsetAsync(ix->debug_ts, 0, (size_t)ix->sm_count * 8 * sizeof(unsigned long long), stream));
@@ -507,6 +514,7 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   RS_ALLOC(cudaMalloc(&ix->out_idx_dev, out_elems * (sizeof(long long) + sizeof(float))));
   RS_ALLOC(cudaMalloc(&ix->ingest_dev, kIngestChunkBytes));
   RS_ALLOC(cudaMallocHost(&ix->pinned, ix->pinned_bytes));
+  RS_ALLOC(cudaMalloc(&ix->g_best, (size_t)prop.multiProcessorCount * 128 * sizeof(float)));
   RS_ALLOC(cudaMalloc(&ix->sync, 256));
   RS_ALLOC(cudaMemsetAsync(ix->sync, 0, 256, ix->stream));
   RS_ALLOC(cudaHostAlloc(&ix->err_flag, 64, cudaHostAllocMapped));

@@ -71,6 +71,7 @@ struct SearchParams {
   long long idx_offset;              // global index of this shard's row 0
   ExchangeArgs x;                    // tail_mode >= 2
   ExchangeArgs xp;                   // tail_mode == 3: the previous, still unmerged search (n_queries == 0: none)
+  float* g_best;                     // k > 16: [n_work][bpad] best score seen per (CTA, query), NaN = none yet; null = off
   unsigned long long* debug_ts;      // null, or [grid][8] globaltimer stamps of the kernel's phases (RS_DEBUG_TS=1)
 };
 

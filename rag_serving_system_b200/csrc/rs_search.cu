@@ -1095,6 +1095,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       }
       float thr = live ? -CUDART_INF_F : CUDART_INF_F;  // in metric units (dot: raw units)
       float thr_raw = thr;
+      // k > 16: bound shared between the CTAs of this GPU.  Every CTA publishes the best score it has seen
+      // for each query; t = min over the n_work CTAs of those maxima means at least n_work >= k documents
+      // score >= t, so anything strictly below t cannot be in the top-k.  t is ~(ln n_work)/m in tail
+      // probability after m documents per CTA, the CTA's own k-th best is k/m: ~18x fewer candidates at
+      // k = 100.  Ties with t are kept (the filter uses the next float below t).  The per-CTA list is then
+      // no longer the CTA's exact top-k, but everything it drops is provably outside the GPU's top-k.
+      const bool shared_bound = !REGLIST && p.g_best != nullptr && worker;
+      float best_seen = -CUDART_INF_F, gbound = -CUDART_INF_F;
+      int tiles_done = 0, next_refresh = 1;
 
       int acc = 0;
       uint32_t acc_ph = 0;
@@ -1113,6 +1122,26 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
         const int nsub = min(S, p.n_tiles - u * S);
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
+        if (shared_bound && tiles_done >= next_refresh) {  // after 1, 2, 4, ... tiles, then every 64
+          next_refresh = tiles_done < 64 ? 2 * tiles_done : tiles_done + 64;
+          float mn = CUDART_INF_F;
+          if (live) {
+#pragma unroll 8
+            for (int c = 0; c < p.n_work; ++c) {
+              const float v = __ldcg(p.g_best + (size_t)c * p.bpad + row);
+              mn = fminf(mn, v == v ? v : -CUDART_INF_F);  // NaN = that CTA has not published yet
+            }
+            if (mn > -CUDART_INF_F && mn < CUDART_INF_F) {
+              gbound = __uint_as_float(__float_as_uint(mn) + (mn > 0.f ? -1 : (mn < 0.f ? 1 : 0)));  // next float below
+              if (mn == 0.f) gbound = -1.401298464e-45f;
+              if (gbound > thr) {
+                thr = gbound;
+                thr_raw = cosine ? CUDART_INF_F : thr;  // cosine: recomputed per tile just below
+              }
+            }
+          }
+        }
+        tiles_done += nsub;
         for (int sub = 0; sub < ((p.debug_flags & 2) ? 0 : nsub); ++sub) {
           const int t = u * S + sub;
           float ndmin = 1.f, ndmax = 1.f;
@@ -1190,6 +1219,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
                       Bs[(cnt) + row * lstride] = x;  // O(1) append; threshold stays stale until the flush
                       Bi[(cnt) + row * lstride] = idx;
                       ++cnt;
+                      if (p.debug_ts) atomicAdd(p.debug_ts + (size_t)blockIdx.x * 8 + 7, 1ull);  // appends (low word)
+                      if (shared_bound && x > best_seen) {
+                        best_seen = x;
+                        __stcg(p.g_best + (size_t)blockIdx.x * p.bpad + row, x);
+                      }
                     }
                   }
                 }
@@ -1199,8 +1233,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
                     const int ql = __ffs(full) - 1;
                     full &= full - 1;
                     const float nt = flush_candidates(Ls, Li, Bs, Bi, lstride, quarter * rows_per_warp + ql, p.bufc, k, lane);
+                    if (p.debug_ts && lane == 0) atomicAdd(p.debug_ts + (size_t)blockIdx.x * 8 + 7, 1ull << 32);  // flushes
                     if (lane == ql) {
-                      thr = nt;
+                      thr = fmaxf(nt, gbound);
                       cnt = 0;
                       thr_raw = cosine ? cosine_raw_bound(thr, nq, inv_qs, ndmin, ndmax) : thr;
                     }

@@ -8,6 +8,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["RS_DEBUG_TS"] = "1"
+for a in [a for a in sys.argv[1:] if "=" in a]:      # NAME=VALUE arguments go to the environment
+    os.environ[a.split("=")[0]] = a.split("=")[1]
+    sys.argv.remove(a)
 from rag_serving_system_b200 import _cabi
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1_250_000
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
@@ -34,4 +37,7 @@ for it in range(6):
         col = rel[:, j][rel[:, j] >= 0]
         if len(col):
             out[nm] = {"min": round(float(col.min()), 2), "med": round(float(np.median(col)), 2), "max": round(float(col.max()), 2)}
+    cnt = ts[:, 7].astype(np.uint64)
+    out["appends_per_cta"] = float((cnt & np.uint64(0xffffffff)).mean())
+    out["flushes_per_cta"] = float((cnt >> np.uint64(32)).mean())
     print(json.dumps(out), flush=True)
