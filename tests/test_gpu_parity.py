@@ -377,6 +377,27 @@ def test_all_equal_rows_and_zero_query():
         assert (idx == np.arange(12)).all()               # every score ties -> first k rows, in order
 
 
+def test_shared_bound_keeps_ties_at_the_bound():
+    """k > 16 with at least k CTAs at work: the bound shared between CTAs (min over CTAs of each CTA's best
+    score) must keep documents that TIE with it.  All rows identical -> every score equals the bound and the
+    answer is the first k rows; a zero query makes the bound exactly 0; a corpus whose best rows sit in one
+    tile makes one CTA hold the whole top-k while every other CTA only publishes a low best."""
+    N = 128 * 148 * 2 + 50
+    E = np.tile(np.linspace(-1, 1, 256, dtype=np.float32), (N, 1))
+    Q = np.stack([E[0], -E[0], np.zeros(256, np.float32)])
+    for k in (17, 100):
+        for metric in ("dot", "cosine"):
+            idx, sc, _ = run_case(E, Q, k, "bf16", metric, 1, exact_idx=True)
+            assert (idx == np.arange(k)).all()
+    rng = np.random.default_rng(3)
+    E2 = o.synth_rows(33, np.arange(N), 256)
+    hot = 128 * 177                                            # one tile holds 120 near-copies of the query
+    q = o.round_to_bf16(E2[5])
+    E2[hot:hot + 120] = q * (1.0 - 1e-3 * np.arange(120, dtype=np.float32))[:, None]
+    idx, sc, _ = run_case(E2, np.stack([q, o.round_to_bf16(E2[9])]), 100, "bf16", "dot", 1, exact_idx=True)
+    assert set(idx[0, :99].tolist()) <= set(range(hot, hot + 120)) | {5}
+
+
 def test_negative_scores_and_cosine_clip(squad):
     E = squad.E[:500]
     Q = -squad.Q[:8]                                      # every similarity negative (thr < 0 branch)
