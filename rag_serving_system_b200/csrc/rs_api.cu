@@ -52,6 +52,7 @@ struct Plan {
   int mma_m;       // MMA M: 64 when the padded batch fits, else 128
   int cps;         // k-chunks per ring stage
   int bufc;        // k > 16: candidate-buffer entries per query (32; 16 when that saves a pass)
+  int lg;          // k > 16: sorted lists in global memory (L2) instead of shared memory
 };
 
 int env_int(const char* name, int dflt) {
@@ -168,11 +169,11 @@ int flush_pending(rs_xchg* xg, cudaStream_t stream) {
   return RS_OK;
 }
 
-int max_cap_rows(int kc, int terms, int k, int min_stages, int cps, int q_resident, int bufc = 32) {
+int max_cap_rows(int kc, int terms, int k, int min_stages, int cps, int q_resident, int bufc = 32, int lg = 0) {
   // largest bpad (multiple of 8, <= 128) that leaves at least min_stages ring slots
   int best = 0;
   for (int bpad = 8; bpad <= 128; bpad += 8) {
-    if (rs::fused_smem_bytes(bpad, kc, terms, min_stages, cps, k, q_resident, 2 * terms, bufc) <= kMaxSmem) best = bpad;
+    if (rs::fused_smem_bytes(bpad, kc, terms, min_stages, cps, k, q_resident, 2 * terms, bufc, lg) <= kMaxSmem) best = bpad;
   }
   return best;
 }
@@ -187,6 +188,8 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
   const int force_res = env_int("RS_QRESIDENT", -1), force_cps = env_int("RS_CPS", 0), force_sub = env_int("RS_SUB", 0);
   const int force_bufc = env_int("RS_BUFC", 0), force_lean = env_int("RS_LEAN", -1);
   const bool lists_in_smem = k > rs::fused_reg_k();
+  // k > 16: keep the sorted lists in global memory (default) so the ring keeps its bytes; RS_LISTS_GLOBAL=0: shared memory
+  const int lg = lists_in_smem && env_int("RS_LISTS_GLOBAL", 1) != 0 ? 1 : 0;
   long long best_cost = -1;
   for (int resident = 1; resident >= 0; --resident) {
     if (force_res >= 0 && resident != force_res) continue;
@@ -205,7 +208,7 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
             // k-chunk group + 1
             int need = std::max(2, ((lean ? 3 : 4) + cps - 1) / cps);
             if (!resident) need = std::max(need, ix->planes * sub + 1);
-            const int cap = max_cap_rows(ix->kc, terms, k, need, cps, resident, bufc);
+            const int cap = max_cap_rows(ix->kc, terms, k, need, cps, resident, bufc, lg);
             if (cap <= 0) continue;
             const int passes = (B + cap - 1) / cap;
             const long long cost = ((long long)passes << 32) | ((long long)(1 - resident) << 28) |
@@ -219,6 +222,7 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
               pl->passes = passes;
               pl->stages = need;
               pl->bufc = bufc;
+              pl->lg = lg;
             }
           }
         }
@@ -237,7 +241,7 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
   if (pl->nbuf < 1 || pl->nbuf > 4 || (cols != 1 && cols != 2 && cols != 4))
     return fail(RS_E_INVALID, "sub=%d nbuf=%d nacc=%d does not map onto 128/256/512 TMEM columns", pl->sub, pl->nbuf, nacc);
   auto bytes = [&](int stages) {
-    return rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages, pl->cps, k, pl->q_resident, 2 * terms, pl->bufc);
+    return rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages, pl->cps, k, pl->q_resident, 2 * terms, pl->bufc, pl->lg);
   };
   while (pl->stages < kMaxStages && bytes(pl->stages + 1) <= kMaxSmem) ++pl->stages;
   if (bytes(pl->stages) > kMaxSmem) return fail(RS_E_UNSUPPORTED, "B=%d k=%d does not fit in shared memory", B, k);
@@ -310,7 +314,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   const int grid = fused_tail ? std::max(n_work, std::min(merge_ctas, ix->sm_count)) : n_work;
   ix->stats.grid = grid;
   ix->stats.stages = pl.stages;
-  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms, pl.bufc);
+  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms, pl.bufc, pl.lg);
   ix->stats.q_resident = pl.q_resident;
   ix->stats.sub = pl.sub;
   ix->stats.nbuf = pl.nbuf;
@@ -378,6 +382,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.stages = pl.stages;
     p.cps = pl.cps;
     p.bufc = pl.bufc;
+    p.lists_global = pl.lg;
     p.qstages = 2 * terms;
     p.q_resident = pl.q_resident;
     p.sub = pl.sub;

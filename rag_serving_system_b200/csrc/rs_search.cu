@@ -289,15 +289,20 @@ constexpr int kBufC = 32;                                       // k > kRegK: un
 constexpr int kMaxListK = 128;                                  // k > kRegK: sorted list in smem, <= 4 slots per lane
 
 // words per query of the k > kRegK selection state (odd: see the epilogue)
-__host__ __device__ inline int list_row_words(int k, int bufc) { return (2 * (k + bufc)) | 1; }
+// lists_global: only the candidate buffers stay in shared memory (+ one list-sized scratch per warp)
+__host__ __device__ inline int list_row_words(int k, int bufc, bool lists_global = false) {
+  return (2 * ((lists_global ? 0 : k) + bufc)) | 1;
+}
 
+constexpr int kNumEpiWarpsC = 4;
 struct SmemMap {
   uint32_t q_bytes, stage_off, bar_off, dump_off, list_off, total;
 };
 // q_resident: the whole Q image lives in shared memory for the kernel's lifetime (small batches);
 // otherwise Q k-chunks travel through the ring next to the document blocks (large batches).
 __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, int stages, int cps, int k,
-                                                 bool reglist, bool q_resident, int qstages, int bufc = kBufC) {
+                                                 bool reglist, bool q_resident, int qstages, int bufc = kBufC,
+                                                 bool lists_global = false) {
   SmemMap m;
   // resident: the whole Q image; streamed: a private ring of qstages slots of cps k-chunks each
   m.q_bytes = q_resident ? (uint32_t)terms * kc * bpad * RS_KCHUNK_BYTES
@@ -307,7 +312,8 @@ __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, in
   m.dump_off = m.bar_off + 2048;                       // [bar_off, +1 KiB) barriers, then qnorm[128], qscale[128];
                                                        // dump = rare-path chunk: 32 columns x live rows, fp32
   m.list_off = m.dump_off + (uint32_t)((bpad + 31) / 32 * 32) * 128u;   // whole warps of 32 (M=128) or 2x16 (M=64) rows
-  m.total = m.list_off + (reglist ? 0u : (uint32_t)list_row_words(k, bufc) * (uint32_t)bpad * 4u);
+  m.total = m.list_off + (reglist ? 0u : (uint32_t)list_row_words(k, bufc, lists_global) * (uint32_t)bpad * 4u +
+                                             (lists_global ? (uint32_t)kNumEpiWarpsC * 2u * (uint32_t)k * 4u : 0u));
   return m;
 }
 
@@ -340,10 +346,13 @@ __device__ __forceinline__ float cosine_raw_bound(float thr_cos, float nq, float
 // search in the other sequence and is written straight to that position.  Ties: list elements were
 // seen earlier (lower index) so they win; candidates order by (score desc, index asc).
 // Must be called by the full, converged warp.  Returns the new k-th best score.
-__device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs, int* Bi, int stride, int qrow, int n,
-                                                  int k, int lane) {
-  float cs = lane < n ? Bs[(lane) + qrow * stride] : -CUDART_INF_F;
-  int ci = lane < n ? Bi[(lane) + qrow * stride] : 0x7fffffff;
+// All four pointers address ONE query's arrays (unit stride).  Candidate scores are multiplied by `scale` (an
+// exact power of two, or 1) on the way in, so a list may be kept in final units while the filter runs in raw
+// accumulator units; the returned k-th best is in list units.
+__device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs, const int* Bi, int n, int k, int lane,
+                                                  float scale = 1.0f) {
+  float cs = lane < n ? Bs[lane] * scale : -CUDART_INF_F;
+  int ci = lane < n ? Bi[lane] : 0x7fffffff;
 #pragma unroll
   for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
@@ -360,7 +369,7 @@ __device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs,
       }
     }
   }
-  Bs[(lane) + qrow * stride] = cs;  // now sorted, best first
+  Bs[lane] = cs;  // now sorted, best first
   __syncwarp();
   float es[kMaxListK / 32];
   int ei[kMaxListK / 32], er[kMaxListK / 32];
@@ -369,38 +378,38 @@ __device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs,
     const int pos = lane + 32 * g;
     er[g] = k;
     if (pos < k) {
-      es[g] = Ls[(pos) + qrow * stride];
-      ei[g] = Li[(pos) + qrow * stride];
+      es[g] = Ls[pos];
+      ei[g] = Li[pos];
       // candidates strictly better than this list element: fixed-trip binary search (count in
       // [0,32]) so the four independent searches of a lane interleave their shared-memory loads
       int c = 0;
 #pragma unroll
       for (int step = 16; step > 0; step >>= 1)
-        if (Bs[((c + step - 1)) + qrow * stride] > es[g]) c += step;
-      if (c == 31 && Bs[(31) + qrow * stride] > es[g]) c = 32;
+        if (Bs[c + step - 1] > es[g]) c += step;
+      if (c == 31 && Bs[31] > es[g]) c = 32;
       er[g] = pos + c;
     }
   }
   int lo = 0, hi = k;  // list elements at least as good as this candidate
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (Ls[(mid) + qrow * stride] >= cs) lo = mid + 1; else hi = mid;
+    if (Ls[mid] >= cs) lo = mid + 1; else hi = mid;
   }
   const int cr = lane + lo;
   __syncwarp();
 #pragma unroll
   for (int g = 0; g < kMaxListK / 32; ++g) {
     if (er[g] < k) {
-      Ls[er[g] + qrow * stride] = es[g];
-      Li[er[g] + qrow * stride] = ei[g];
+      Ls[er[g]] = es[g];
+      Li[er[g]] = ei[g];
     }
   }
   if (lane < n && cr < k) {
-    Ls[(cr) + qrow * stride] = cs;
-    Li[(cr) + qrow * stride] = ci;
+    Ls[cr] = cs;
+    Li[cr] = ci;
   }
   __syncwarp();
-  return Ls[((k - 1)) + qrow * stride];
+  return Ls[k - 1];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -778,7 +787,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr bool q_resident = QRES;
-  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, q_resident, p.qstages, p.bufc);
+  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, q_resident, p.qstages, p.bufc,
+                                    p.lists_global != 0);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t q_smem = smem_base;
   const uint32_t stage_smem = smem_base + map.stage_off;
@@ -1070,11 +1080,41 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       // per query one contiguous row [list scores k][list ids k][buffer scores bufc][buffer ids bufc] with an
       // ODD word stride: lanes that walk one query's slots (flush) and lanes that touch the same slot of
       // 32 different queries (append) both spread over all shared-memory banks
-      const int lstride = list_row_words(k, p.bufc);
+      // lists_global: the sorted lists live where the per-CTA candidates end up anyway (cand_* in global
+      // memory, i.e. L2), in FINAL units; a flush pulls one list into a per-warp scratch, merges there and
+      // writes it back.  Only the candidate buffers stay in shared memory, which gives the ring its bytes
+      // back (the shared bound leaves only ~15 flushes per query per CTA).
+      const bool lg = !REGLIST && p.lists_global != 0;
+      const int lstride = list_row_words(k, p.bufc, lg);
       float* Ls = reinterpret_cast<float*>(smem + map.list_off);
       int* Li = reinterpret_cast<int*>(Ls + k);
-      float* Bs = Ls + 2 * k;
-      int* Bi = reinterpret_cast<int*>(Ls + 2 * k + p.bufc);
+      float* Bs = lg ? Ls : Ls + 2 * k;
+      int* Bi = reinterpret_cast<int*>(Bs + p.bufc);
+      float* Ws = Ls + (size_t)lstride * p.bpad + (size_t)quarter * 2 * k;  // per-warp scratch: k scores, k ids
+      int* Wi = reinterpret_cast<int*>(Ws + k);
+      auto glist_s = [&](int qrow) { return p.cand_score + ((size_t)qrow * p.n_work + blockIdx.x) * k; };
+      auto glist_i = [&](int qrow) { return p.cand_idx + ((size_t)qrow * p.n_work + blockIdx.x) * k; };
+      // one query's buffer -> its list; returns the new k-th best in FILTER units (raw for dot)
+      auto flush_query = [&](int ql, int n) -> float {
+        const int qrow = quarter * rows_per_warp + ql;
+        if (!lg) return flush_candidates(Ls + (size_t)qrow * lstride, Li + (size_t)qrow * lstride, Bs + (size_t)qrow * lstride,
+                                         Bi + (size_t)qrow * lstride, n, k, lane);
+        const float unit = cosine ? 1.0f : __shfl_sync(0xffffffffu, qs, ql);  // list units = final units
+        float* gs = glist_s(qrow);
+        int* gi = glist_i(qrow);
+        for (int j = lane; j < k; j += 32) {
+          Ws[j] = __ldcg(gs + j);
+          Wi[j] = __ldcg(gi + j);
+        }
+        __syncwarp();
+        const float nt = flush_candidates(Ws, Wi, Bs + (size_t)qrow * lstride, Bi + (size_t)qrow * lstride, n, k, lane, unit);
+        for (int j = lane; j < k; j += 32) {
+          __stcg(gs + j, Ws[j]);
+          __stcg(gi + j, Wi[j]);
+        }
+        __syncwarp();
+        return cosine ? nt : nt * __shfl_sync(0xffffffffu, inv_qs, ql);  // exact: qs is a power of two
+      };
       int cnt = 0;
       // per warp: [32 columns][rows_per_warp lanes] floats
       float* dump = reinterpret_cast<float*>(smem + map.dump_off) + (size_t)quarter * 32 * rows_per_warp;
@@ -1085,10 +1125,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
           li[j] = -1;
         }
       } else {
-        if (live) {
+        if (live && (!lg || worker)) {
+          float* l0 = lg ? glist_s(row) : Ls + (size_t)row * lstride;
+          int* i0 = lg ? glist_i(row) : Li + (size_t)row * lstride;
           for (int j = 0; j < k; ++j) {
-            Ls[(j) + row * lstride] = -CUDART_INF_F;
-            Li[(j) + row * lstride] = -1;
+            l0[j] = -CUDART_INF_F;
+            i0[j] = -1;
           }
         }
         __syncwarp();
@@ -1232,7 +1274,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
                   while (full) {
                     const int ql = __ffs(full) - 1;
                     full &= full - 1;
-                    const float nt = flush_candidates(Ls, Li, Bs, Bi, lstride, quarter * rows_per_warp + ql, p.bufc, k, lane);
+                    const float nt = flush_query(ql, p.bufc);
                     if (p.debug_ts && lane == 0) atomicAdd(p.debug_ts + (size_t)blockIdx.x * 8 + 7, 1ull << 32);  // flushes
                     if (lane == ql) {
                       thr = fmaxf(nt, gbound);
@@ -1262,7 +1304,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
           const int ql = __ffs(rem) - 1;
           rem &= rem - 1;
           const int n = __shfl_sync(0xffffffffu, cnt, ql);
-          flush_candidates(Ls, Li, Bs, Bi, lstride, quarter * rows_per_warp + ql, n, k, lane);
+          flush_query(ql, n);
         }
       }
       // per-CTA candidates, best first; dot scores leave raw units here
@@ -1278,7 +1320,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
               ci[k - 1 - j] = li[j];
             }
           }
-        } else {
+        } else if (!lg) {  // (lists_global: the lists already sit in cand_*, in final units)
           for (int j = 0; j < k; ++j) {
             const float raw = Ls[(j) + row * lstride];
             const int id = Li[(j) + row * lstride];
@@ -1476,7 +1518,8 @@ cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dt
 
 template <int NACC, bool REGLIST, bool QRES>
 static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t stream) {
-  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, QRES, p.qstages, p.bufc);
+  const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, QRES, p.qstages, p.bufc,
+                                    p.lists_global != 0);
   auto kern = fused_search_kernel<NACC, REGLIST, QRES>;
   const int bytes = (int)map.total + 1024;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -1485,8 +1528,10 @@ static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t 
   return cudaGetLastError();
 }
 
-int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages, int bufc) {
-  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages, bufc).total + 1024;
+int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages, int bufc,
+                     int lists_global) {
+  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages, bufc, lists_global != 0)
+             .total + 1024;
 }
 int fused_reg_k() { return kRegK; }
 

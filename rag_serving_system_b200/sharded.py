@@ -160,11 +160,22 @@ class ShardedSearcher:
             self.xchg.flush(self.index, torch.cuda.current_stream(self.device).cuda_stream)
 
     def search_host(self, q_host: torch.Tensor, k: int, metric: str = "dot", query_terms: int = 1):
-        """End-to-end call with HOST buffers: pinned H2D of the queries, search, D2H of the result."""
+        """End-to-end call with HOST buffers: pinned H2D of the queries, search, D2H of the result into
+        pinned host tensors (reused by the next call with the same B and k), one synchronisation."""
         dev = torch.device("cuda", self.device)
-        q_dev = q_host.to(dev, non_blocking=True)
+        B = q_host.shape[0]
+        key = ("host", B, k)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.empty((B, q_host.shape[1]), dtype=torch.float32, device=dev),
+                               torch.empty((B, k), dtype=torch.int64).pin_memory(),
+                               torch.empty((B, k), dtype=torch.float32).pin_memory())
+        q_dev, pin_i, pin_s = self._bufs[key]
+        q_dev.copy_(q_host, non_blocking=True)
         oi, os_ = self.search(q_dev, k, metric, query_terms)
-        return oi.cpu(), os_.cpu()
+        pin_i.copy_(oi, non_blocking=True)
+        pin_s.copy_(os_, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return pin_i, pin_s
 
     def close(self):
         if self.xchg is not None:
