@@ -232,6 +232,33 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
   if (best_cost < 0) return fail(RS_E_UNSUPPORTED, "B=%d k=%d dim=%d does not fit in shared memory", B, k, ix->cfg.dim);
   pl->per_pass = (B + pl->passes - 1) / pl->passes;
   pl->bpad = (pl->per_pass + 7) / 8 * 8;
+  // Optional (RS_QLO_STREAM=1, or 2 to force it for any corpus size; default off): with two query terms and a
+  // resident Q, keep only the hi term resident and stream the lo term (one MMA chain uses it) through a ring.
+  // That halves the resident image (128 -> 64 KiB at B=32, D=1024) in favour of the document ring.  Measured on
+  // 1M x 1024 fp32: 0.775 -> 0.738 ms at B=32, but 0.665 -> 0.736 ms at B=16 and 0.625 -> 0.709 ms at B=1 (smaller
+  // ring stages, one more launch), so it stays an opt-in.
+  if (pl->q_resident == 1 && terms == 2 && env_int("RS_QLO_STREAM", 0) != 0 && force_res != 1 &&
+      ((size_t)ix->corpus_bytes >= ((size_t)256 << 20) || env_int("RS_QLO_STREAM", 0) == 2)) {  // 2: force (tests)
+    auto ring_bytes = [&](int mode, int cps) {
+      int st = std::max(2, (4 + cps - 1) / cps);
+      if (rs::fused_smem_bytes(pl->bpad, ix->kc, terms, st, cps, k, mode, 2 * terms, pl->bufc, pl->lg) > kMaxSmem) return 0;
+      while (st < kMaxStages &&
+             rs::fused_smem_bytes(pl->bpad, ix->kc, terms, st + 1, cps, k, mode, 2 * terms, pl->bufc, pl->lg) <= kMaxSmem)
+        ++st;
+      return st * cps * RS_BLOCK_BYTES;
+    };
+    const int have = ring_bytes(1, pl->cps);
+    for (int cps = 4; cps >= 1; cps >>= 1) {
+      if (ix->kc % cps != 0 || (force_cps && cps != force_cps)) continue;
+      const int got = ring_bytes(2, cps);
+      if (got > have) {
+        pl->q_resident = 2;
+        pl->cps = cps;
+        pl->stages = std::max(2, (4 + cps - 1) / cps);
+        break;
+      }
+    }
+  }
   pl->mma_m = env_int("RS_MMA_M", pl->bpad <= 64 ? 64 : 128);
   if (pl->mma_m != 128 && !(pl->mma_m == 64 && pl->bpad <= 64)) return fail(RS_E_INVALID, "RS_MMA_M=%d invalid for bpad=%d", pl->mma_m, pl->bpad);
   // as many accumulator buffers as the 512 TMEM columns hold: the epilogue's start-up burst (every
@@ -298,7 +325,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   // single-launch search (default): query prep in the fused kernel's prologue (resident-Q plans) and the
   // candidate merge (+ exchange) in its tail.  RS_INLINE_PREP=0 / RS_FUSED_TAIL=0 fall back to the
   // separate query_prep_kernel / merge kernels.
-  const bool inline_prep = pl.q_resident && ix->cfg.dim <= 1024 && pl.bpad <= 32 && env_int("RS_INLINE_PREP", 1) != 0;
+  const bool inline_prep = pl.q_resident == 1 && ix->cfg.dim <= 1024 && pl.bpad <= 32 && env_int("RS_INLINE_PREP", 1) != 0;
   const int tail_cap = rs::fused_tail_smem_capacity(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms);
   const bool fused_tail = env_int("RS_FUSED_TAIL", 1) != 0 &&
                           rs::fused_tail_smem_bytes(n_work, k, xg ? xg->world : 1) <= (size_t)tail_cap;

@@ -296,17 +296,19 @@ __host__ __device__ inline int list_row_words(int k, int bufc, bool lists_global
 
 constexpr int kNumEpiWarpsC = 4;
 struct SmemMap {
-  uint32_t q_bytes, stage_off, bar_off, dump_off, list_off, total;
+  uint32_t q_bytes, q_res_bytes, stage_off, bar_off, dump_off, list_off, total;
 };
 // q_resident: the whole Q image lives in shared memory for the kernel's lifetime (small batches);
 // otherwise Q k-chunks travel through the ring next to the document blocks (large batches).
 __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, int stages, int cps, int k,
                                                  bool reglist, bool q_resident, int qstages, int bufc = kBufC,
-                                                 bool lists_global = false) {
+                                                 bool lists_global = false, bool lo_stream = false) {
   SmemMap m;
   // resident: the whole Q image; streamed: a private ring of qstages slots of cps k-chunks each
-  m.q_bytes = q_resident ? (uint32_t)terms * kc * bpad * RS_KCHUNK_BYTES
-                         : (uint32_t)qstages * cps * bpad * RS_KCHUNK_BYTES;
+  // lo_stream (resident mode, two query terms): only the hi term is resident, the lo term - used by one MMA
+  // chain instead of two - streams through a small ring, which halves the resident Q image
+  m.q_res_bytes = q_resident ? (uint32_t)(lo_stream ? 1 : terms) * kc * bpad * RS_KCHUNK_BYTES : 0u;
+  m.q_bytes = m.q_res_bytes + ((!q_resident || lo_stream) ? (uint32_t)qstages * cps * bpad * RS_KCHUNK_BYTES : 0u);
   m.stage_off = m.q_bytes;  // multiple of 1024 because bpad % 8 == 0
   m.bar_off = m.stage_off + (uint32_t)stages * (uint32_t)cps * RS_BLOCK_BYTES;
   m.dump_off = m.bar_off + 2048;                       // [bar_off, +1 KiB) barriers, then qnorm[128], qscale[128];
@@ -787,8 +789,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr bool q_resident = QRES;
+  const bool lo_stream = QRES && p.q_resident == 2;  // hi term resident, lo term streamed (needs terms == 2, prep kernel)
   const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, q_resident, p.qstages, p.bufc,
-                                    p.lists_global != 0);
+                                    p.lists_global != 0, lo_stream);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t q_smem = smem_base;
   const uint32_t stage_smem = smem_base + map.stage_off;
@@ -834,7 +837,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       mbar_init(tempty_bar(a), nact_warps);
     }
     mbar_init(qfull_bar, inline_prep ? kNumEpiWarps : 1);
-    if (!q_resident)
+    if (!q_resident || lo_stream)
       for (int s = 0; s < p.qstages; ++s) {
         mbar_init(qring_full(s), 1);
         mbar_init(qring_empty(s), 1);
@@ -870,9 +873,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
     const uint64_t pol_stream = l2_policy_evict_first();
     const uint64_t pol_keep = l2_policy_evict_last();
     if (q_resident && !inline_prep && worker && lane == 0) {
-      mbar_arrive_expect_tx(qfull_bar, map.q_bytes);
-      for (uint32_t off = 0; off < map.q_bytes; off += 32768u) {
-        uint32_t n = min(32768u, map.q_bytes - off);
+      mbar_arrive_expect_tx(qfull_bar, map.q_res_bytes);
+      for (uint32_t off = 0; off < map.q_res_bytes; off += 32768u) {
+        uint32_t n = min(32768u, map.q_res_bytes - off);
         bulk_g2s(q_smem + off, p.qimg + off, n, qfull_bar, pol_keep);
       }
     }
@@ -895,7 +898,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       mbar_wait(qring_empty(qs), qph ^ 1u);
       if (lane == 0) {
         mbar_arrive_expect_tx(qring_full(qs), bytes);
-        bulk_g2s(q_smem + (uint32_t)qs * (uint32_t)cps * qblk, src, bytes, qring_full(qs), pol_keep);
+        bulk_g2s(q_smem + map.q_res_bytes + (uint32_t)qs * (uint32_t)cps * qblk, src, bytes, qring_full(qs), pol_keep);
       }
       if (++qs == p.qstages) {
         qs = 0;
@@ -927,6 +930,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       for (int kc = 0; kc < p.kc; kc += cps) {
         if (!q_resident)
           for (int j = 0; j < p.terms; ++j) push_q(p.qimg + (size_t)(j * p.kc + kc) * qblk, cps * qblk);
+        if (lo_stream) push_q(p.qimg + (size_t)(p.kc + kc) * qblk, cps * qblk);
         for (int pl = 0; pl < p.planes; ++pl)
           for (int sub = 0; sub < nsub; ++sub)
             push(src + (size_t)sub * tile_bytes + (size_t)(pl * p.kc + kc) * RS_BLOCK_BYTES, stage_bytes, pol_stream);
@@ -984,6 +988,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
           }
           qa0 = q_smem + (uint32_t)kc * qblk;
           qa1 = q_smem + (uint32_t)(p.kc + kc) * qblk;
+          if (lo_stream) {  // the lo term of this k-chunk group arrives through the Q ring
+            mbar_wait(qring_full(qs), qph);
+            qa1 = q_smem + map.q_res_bytes + (uint32_t)qs * (uint32_t)cps * qblk;
+            qslot1 = qs;
+            if (++qs == p.qstages) {
+              qs = 0;
+              qph ^= 1u;
+            }
+          }
         } else {
           mbar_wait(qring_full(qs), qph);
           qa0 = q_smem + (uint32_t)qs * (uint32_t)cps * qblk;
@@ -1031,6 +1044,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
           umma_commit(qring_empty(qslot0));
           if (p.terms == 2) umma_commit(qring_empty(qslot1));
         }
+        if (lo_stream && lane == 0) umma_commit(qring_empty(qslot1));
       }
       q_pending = false;
       __syncwarp();
@@ -1413,7 +1427,8 @@ size_t fused_tail_smem_bytes(int n_lists, int k, int world) {
   return merge_res_bytes(k) + std::max((size_t)n_lists * k * 8, (size_t)world * k * 12);
 }
 int fused_tail_smem_capacity(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages) {
-  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages, kBufC).bar_off;
+  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages, kBufC, false, q_resident == 2)
+      .bar_off;
 }
 
 // Plain merge: one CTA per query, lists -> out[q][0..k).
@@ -1519,7 +1534,7 @@ cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dt
 template <int NACC, bool REGLIST, bool QRES>
 static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t stream) {
   const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, QRES, p.qstages, p.bufc,
-                                    p.lists_global != 0);
+                                    p.lists_global != 0, QRES && p.q_resident == 2);
   auto kern = fused_search_kernel<NACC, REGLIST, QRES>;
   const int bytes = (int)map.total + 1024;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -1530,7 +1545,8 @@ static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t 
 
 int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages, int bufc,
                      int lists_global) {
-  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages, bufc, lists_global != 0)
+  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages, bufc, lists_global != 0,
+                            q_resident == 2)
              .total + 1024;
 }
 int fused_reg_k() { return kRegK; }
