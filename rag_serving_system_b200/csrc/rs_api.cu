@@ -321,6 +321,12 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     cudaMemsetAsync(ix->sync, 0, 256, stream);
     return fail(RS_E_CUDA, "a previous search timed out waiting for its own CTAs (device shared with another job?)");
   }
+  // doc-major kernel variant (documents on the MMA's M): half the tensor work and a quarter of the Q-operand reads
+  // at B=32; for B <= 32, k <= 16, one query term, 16-bit storage, dot metric, resident Q (RS_DOCM=0: off)
+  const bool docm = pl.q_resident == 1 && terms == 1 && ix->planes == 1 && k <= rs::fused_reg_k() && pl.bpad <= 32 &&
+                    pl.sub == 1 && metric == RS_METRIC_DOT && env_int("RS_DOCM", 1) != 0 &&
+                    rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, 1, 2 * terms, pl.bufc, pl.lg, 1) <= kMaxSmem;
+  if (docm) pl.nbuf = 8;
   const int n_work = std::min(ix->sm_count, ix->n_tiles);  // CTAs that own tiles = candidate lists per query
   // single-launch search (default): query prep in the fused kernel's prologue (resident-Q plans) and the
   // candidate merge (+ exchange) in its tail.  RS_INLINE_PREP=0 / RS_FUSED_TAIL=0 fall back to the
@@ -341,7 +347,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   const int grid = fused_tail ? std::max(n_work, std::min(merge_ctas, ix->sm_count)) : n_work;
   ix->stats.grid = grid;
   ix->stats.stages = pl.stages;
-  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms, pl.bufc, pl.lg);
+  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms, pl.bufc, pl.lg, docm);
   ix->stats.q_resident = pl.q_resident;
   ix->stats.sub = pl.sub;
   ix->stats.nbuf = pl.nbuf;
@@ -410,6 +416,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.cps = pl.cps;
     p.bufc = pl.bufc;
     p.lists_global = pl.lg;
+    p.docm = docm ? 1 : 0;
     p.qstages = 2 * terms;
     p.q_resident = pl.q_resident;
     p.sub = pl.sub;

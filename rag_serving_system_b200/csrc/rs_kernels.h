@@ -54,6 +54,7 @@ struct SearchParams {
   int mma_m;                         // 128, or 64 when bpad <= 64 (half the tensor work / operand reads)
   int nbuf;                          // TMEM accumulator buffers (1 or 2); nbuf*sub*NACC*128 <= 512 columns
   int bufc;                          // k > 16: candidate-buffer entries per query before a flush (32, or 16 to save smem)
+  int docm;                          // doc-major kernel variant: documents on the MMA's M, queries on its N (B <= 32, k <= 16, dot)
   int lists_global;                  // k > 16: sorted lists in global memory (cand_*), only the buffers in shared memory
   int debug_flags;                   // timing experiments only (RS_DEBUG_FLAGS): 1 = skip MMAs, 2 = skip epilogue, 4 = skip tail merge
   float lo_coef;                     // weight of the low-order accumulator (2^-11 for fp16 terms, 1 for bf16)
@@ -80,7 +81,7 @@ cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dt
                               uint8_t* qimg, float* qnorm, float* qscale, cudaStream_t stream);
 cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t stream);
 int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages, int bufc,
-                     int lists_global);
+                     int lists_global, int docm = 0);
 int fused_reg_k();
 size_t fused_tail_smem_bytes(int n_lists, int k, int world);
 int fused_tail_smem_capacity(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages);

@@ -302,7 +302,7 @@ struct SmemMap {
 // otherwise Q k-chunks travel through the ring next to the document blocks (large batches).
 __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, int stages, int cps, int k,
                                                  bool reglist, bool q_resident, int qstages, int bufc = kBufC,
-                                                 bool lists_global = false, bool lo_stream = false) {
+                                                 bool lists_global = false, bool lo_stream = false, bool docm = false) {
   SmemMap m;
   // resident: the whole Q image; streamed: a private ring of qstages slots of cps k-chunks each
   // lo_stream (resident mode, two query terms): only the hi term is resident, the lo term - used by one MMA
@@ -313,7 +313,8 @@ __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, in
   m.bar_off = m.stage_off + (uint32_t)stages * (uint32_t)cps * RS_BLOCK_BYTES;
   m.dump_off = m.bar_off + 2048;                       // [bar_off, +1 KiB) barriers, then qnorm[128], qscale[128];
                                                        // dump = rare-path chunk: 32 columns x live rows, fp32
-  m.list_off = m.dump_off + (uint32_t)((bpad + 31) / 32 * 32) * 128u;   // whole warps of 32 (M=128) or 2x16 (M=64) rows
+  m.list_off = m.dump_off + (uint32_t)(docm ? 128 : (bpad + 31) / 32 * 32) * 128u;   // whole warps of 32 (M=128) or 2x16 (M=64) rows;
+                                                                                       // doc-major: 4 warps x [32 queries][32 docs]
   m.total = m.list_off + (reglist ? 0u : (uint32_t)list_row_words(k, bufc, lists_global) * (uint32_t)bpad * 4u +
                                              (lists_global ? (uint32_t)kNumEpiWarpsC * 2u * (uint32_t)k * 4u : 0u));
   return m;
@@ -778,10 +779,133 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
   return v;
 }
 
+// ------------------------------------------------------------------------------------------
+// Doc-major variant (B <= 32, k <= 16, one query term, 16-bit storage, dot metric): DOCUMENTS are the
+// MMA's M (128 per tile, one TMEM lane each) and the QUERIES its N (16 or 32 columns).  Against the
+// query-major M=64 x N=128 MMA that is half the tensor work at B=32 (no padding rows), a quarter of the
+// Q-operand reads, and 16-32 accumulator columns per tile instead of 128, i.e. up to 16 tiles of TMEM
+// buffering.  Epilogue: warp w owns the tile's documents 32w..32w+31; a thread holds the 32 query
+// scores of ITS document.  Thresholds are warp-uniform registers thr[j]; lane j of every warp keeps
+// query j's running top-k for that warp's document slice in registers.  When anything passes, the
+// 32x32 scores are parked in shared memory ([query][doc]) and every lane walks its own query's passing
+// documents in ascending order - lane-parallel across queries, like the query-major rare path.  At the
+// end the four warps' lists of a query are merged in shared memory into the CTA's one list.
+// ------------------------------------------------------------------------------------------
+struct DmBars {
+  uint32_t tfull0, tempty0, sched_full0, sched_empty0, qfull;
+  volatile int* tile_u;
+};
+template <int KS>
+__device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars& b, uint32_t tmem_base, int w, int lane,
+                                            float* dump /* this warp's [32][32] */, const float* s_qscale, bool inline_prep,
+                                            bool worker, float* out_s /* [4][32][k] */, int* out_i) {
+  constexpr int kSched = KS;
+  const int k = p.k, nq = p.n_queries;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(w * 32) << 16);
+  float thr[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) thr[j] = j < nq ? -CUDART_INF_F : CUDART_INF_F;
+  float ls[kRegK];
+  int li[kRegK];
+#pragma unroll
+  for (int j = 0; j < kRegK; ++j) {
+    ls[j] = j < k ? -CUDART_INF_F : CUDART_INF_F;  // ascending, slot 0 = current k-th best
+    li[j] = -1;
+  }
+  float mythr = lane < nq ? -CUDART_INF_F : CUDART_INF_F;
+  if (inline_prep && worker) mbar_wait(b.qfull, 0);
+  int acc = 0, sslot = 0;
+  uint32_t acc_ph = 0, sph = 0;
+  while (true) {
+    mbar_wait(b.sched_full0 + 8u * sslot, sph);
+    const int t = b.tile_u[sslot];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(b.sched_empty0 + 8u * sslot);
+    if (++sslot == kSched) {
+      sslot = 0;
+      sph ^= 1u;
+    }
+    if (t < 0) break;
+    mbar_wait(b.tfull0 + 8u * acc, acc_ph);
+    tc_fence_after();
+    float v[32];
+    {
+      uint32_t r[32];
+      tmem_ld_x32(lane_base + (uint32_t)acc * 32u, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    }
+    // the scores are in registers: hand the accumulator back before looking at them
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(b.tempty0 + 8u * acc);
+    if (++acc == p.nbuf) {
+      acc = 0;
+      acc_ph ^= 1u;
+    }
+    if (p.debug_flags & 2) continue;
+    const int doc0 = t * RS_TILE_ROWS + w * 32;
+    if (doc0 + 32 > p.n_rows && doc0 + lane >= p.n_rows) {  // ragged last tile: padded documents never pass
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = -CUDART_INF_F;
+    }
+    uint32_t pm = 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) pm |= (v[j] > thr[j]) ? (1u << j) : 0u;
+    if (__any_sync(0xffffffffu, pm != 0u)) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dump[j * 32 + lane] = v[j];  // [query][doc]: conflict-free
+      uint32_t mine = 0u;  // documents (lanes) of this warp that pass for query `lane`
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t m = __ballot_sync(0xffffffffu, (pm >> j) & 1u);
+        if (lane == j) mine = m;
+      }
+      __syncwarp();
+      while (mine) {  // ascending document index: strict > keeps the lower index on ties
+        const int d = __ffs(mine) - 1;
+        mine &= mine - 1;
+        const float x = dump[lane * 32 + d];
+        if (x > mythr) {
+          const int idx = doc0 + d;
+          bool prev = true;
+#pragma unroll
+          for (int jj = 0; jj < kRegK; ++jj) {
+            const bool lt = (jj + 1 < kRegK) && (ls[jj + 1 < kRegK ? jj + 1 : jj] < x);
+            const float ns = lt ? ls[jj + 1 < kRegK ? jj + 1 : jj] : (prev ? x : ls[jj]);
+            const int ni = lt ? li[jj + 1 < kRegK ? jj + 1 : jj] : (prev ? idx : li[jj]);
+            ls[jj] = ns;
+            li[jj] = ni;
+            prev = lt;
+          }
+          mythr = ls[0];
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) thr[j] = __shfl_sync(0xffffffffu, mythr, j);
+    }
+  }
+  // this warp's list of query `lane`, best first, final units (exact power-of-two scale)
+  if (lane < nq && worker) {
+    const float qs = inline_prep ? s_qscale[lane] : p.qscale[lane];
+    float* os = out_s + (size_t)(w * 32 + lane) * k;
+    int* oi = out_i + (size_t)(w * 32 + lane) * k;
+#pragma unroll
+    for (int j = 0; j < kRegK; ++j) {
+      if (j < k) {
+        os[k - 1 - j] = li[j] < 0 ? -CUDART_INF_F : ls[j] * qs;
+        oi[k - 1 - j] = li[j];
+      }
+    }
+  }
+}
+
 // One CTA walks "supertiles" of p.sub consecutive 128-document tiles.  Per supertile the K loop
 // is outermost: for every 64-element k-chunk the (optional) Q blocks arrive once and are reused
 // by the MMAs of all p.sub document blocks, each accumulating into its own TMEM columns.
-template <int NACC, bool REGLIST, bool QRES>
+template <int NACC, bool REGLIST, bool QRES, bool DOCM = false>
 __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned shared memory; the launcher over-allocates by 1 KiB
@@ -791,33 +915,34 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   constexpr bool q_resident = QRES;
   const bool lo_stream = QRES && p.q_resident == 2;  // hi term resident, lo term streamed (needs terms == 2, prep kernel)
   const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, q_resident, p.qstages, p.bufc,
-                                    p.lists_global != 0, lo_stream);
+                                    p.lists_global != 0, lo_stream, DOCM);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t q_smem = smem_base;
   const uint32_t stage_smem = smem_base + map.stage_off;
   const uint32_t bar_base = smem_base + map.bar_off;
-  // barrier slots (8 B each): full[s], empty[s], tfull[4], tempty[4], qfull, qring_full[], qring_empty[]
+  // barrier slots (8 B each): full[s], empty[s], tfull[8], tempty[8], qfull, qring_full[], qring_empty[], sched[]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 4 + a); };
-  const uint32_t qfull_bar = bar_base + 8u * (2 * p.stages + 8);
-  auto qring_full = [&](int s) { return bar_base + 8u * (2 * p.stages + 9 + s); };              // streamed Q ring
-  auto qring_empty = [&](int s) { return bar_base + 8u * (2 * p.stages + 9 + p.qstages + s); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 8 + a); };
+  const uint32_t qfull_bar = bar_base + 8u * (2 * p.stages + 16);
+  auto qring_full = [&](int s) { return bar_base + 8u * (2 * p.stages + 17 + s); };              // streamed Q ring
+  auto qring_empty = [&](int s) { return bar_base + 8u * (2 * p.stages + 17 + p.qstages + s); };
   // tile scheduler queue: the producer warp publishes the supertile ids this CTA works on (-1 = done)
   constexpr int kSched = 8;
-  auto sched_full = [&](int s) { return bar_base + 8u * (2 * p.stages + 9 + 2 * p.qstages + s); };
-  auto sched_empty = [&](int s) { return bar_base + 8u * (2 * p.stages + 9 + 2 * p.qstages + kSched + s); };
+  auto sched_full = [&](int s) { return bar_base + 8u * (2 * p.stages + 17 + 2 * p.qstages + s); };
+  auto sched_empty = [&](int s) { return bar_base + 8u * (2 * p.stages + 17 + 2 * p.qstages + kSched + s); };
   volatile int* tile_u = reinterpret_cast<volatile int*>(smem + map.bar_off + 1016 - 4 * kSched);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + map.bar_off + 1016);
 
   // M=128: query row r lives in TMEM lane r.  M=64 (half the tensor work, used when bpad <= 64):
   // row r lives in lane (r/16)*32 + r%16, i.e. 16 live lanes in each of the four lane quarters.
   const int rows_per_warp = p.mma_m == 64 ? 16 : 32;
-  const int nact_warps = (p.bpad + rows_per_warp - 1) / rows_per_warp;
+  const int nact_warps = DOCM ? kNumEpiWarps : (p.bpad + rows_per_warp - 1) / rows_per_warp;
   const int S = p.sub;     // 128-document tiles per supertile
   const int NB = p.nbuf;   // accumulator buffers in TMEM (>1: the epilogue overlaps the next supertiles' MMAs)
-  const uint32_t tmem_cols = (uint32_t)(NB * S * NACC) * RS_TILE_ROWS;  // 128, 256 or 512
+  // doc-major: 32 query columns per tile, NB (8 or 16) buffers
+  const uint32_t tmem_cols = DOCM ? (uint32_t)NB * 32u : (uint32_t)(NB * S * NACC) * RS_TILE_ROWS;  // 128, 256 or 512
   const int n_super = (p.n_tiles + S - 1) / S;
   const uint32_t qblk = (uint32_t)p.bpad * RS_KCHUNK_BYTES;
   // CTAs >= n_work own no tiles: they exist only so that every query has a CTA for the tail merge
@@ -832,7 +957,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < 8; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), nact_warps);
     }
@@ -940,7 +1065,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (lane 0 issues) =====================
-    const uint32_t idesc = umma_idesc_f16(p.dtype == RS_DTYPE_BF16, p.mma_m, RS_TILE_ROWS);
+    const uint32_t idesc = DOCM ? umma_idesc_f16(p.dtype == RS_DTYPE_BF16, RS_TILE_ROWS, p.bpad <= 16 ? 16 : 32)
+                                : umma_idesc_f16(p.dtype == RS_DTYPE_BF16, p.mma_m, RS_TILE_ROWS);
     if (q_resident && !inline_prep && worker) {
       mbar_wait(qfull_bar, 0);
       tc_fence_after();
@@ -956,7 +1082,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
     // 16-byte units: one UMMA K step (16 elements x 2 B) advances the start address by 2
     auto issue = [&](uint32_t d, uint32_t a_smem, uint32_t b_smem, bool fresh) {
       if (lane == 0 && !skip_mma) {
-        const uint64_t a = umma_smem_desc(a_smem), b = umma_smem_desc(b_smem);
+        // doc-major: the document block is the M operand, the Q block the N operand
+        const uint64_t a = umma_smem_desc(DOCM ? b_smem : a_smem), b = umma_smem_desc(DOCM ? a_smem : b_smem);
 #pragma unroll
         for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
           umma_f16(d, a + 2u * ks, b + 2u * ks, idesc, (fresh && ks == 0) ? 0u : 1u);
@@ -977,7 +1104,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       const int nsub = min(S, p.n_tiles - u * S);
       mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
       tc_fence_after();
-      const uint32_t dbase = tmem_base + (uint32_t)(acc * S * NACC) * RS_TILE_ROWS;
+      const uint32_t dbase = DOCM ? tmem_base + (uint32_t)acc * 32u : tmem_base + (uint32_t)(acc * S * NACC) * RS_TILE_ROWS;
       for (int kc = 0; kc < p.kc; kc += cps) {
         uint32_t qa0, qa1 = 0;
         int qslot0 = 0, qslot1 = 0;
@@ -1075,7 +1202,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       if (lane == 0) mbar_arrive(qfull_bar);  // this warp's norms / scales are in shared memory
       if (threadIdx.x == kFirstEpiWarp * 32) stamp(p.debug_ts, 1);  // query prep done
     }
-    if (quarter < nact_warps) {
+    if constexpr (DOCM) {
+      const DmBars bars{tfull_bar(0), tempty_bar(0), sched_full(0), sched_empty(0), qfull_bar, tile_u};
+      // lists of the four warps go to shared memory at offset 0: by then the last accumulator is complete, so
+      // the Q image and the ring are dead
+      dm_epilogue<kSched>(p, bars, tmem_base, quarter, lane, reinterpret_cast<float*>(smem + map.dump_off) + quarter * 1024,
+                          s_qscale, inline_prep, worker, reinterpret_cast<float*>(smem),
+                          reinterpret_cast<int*>(smem + 4 * 32 * kRegK * sizeof(float)));
+    } else if (quarter < nact_warps) {
       const int row = quarter * rows_per_warp + lane;
       const bool live = lane < rows_per_warp && row < p.n_queries;
       const int k = p.k;
@@ -1354,6 +1488,41 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
     tmem_dealloc(tmem_base, tmem_cols);
   }
 
+  if constexpr (DOCM) {
+    // the four warps' lists of query q (best first, shared memory) -> the CTA's one list in cand_*
+    if (worker && (int)threadIdx.x < p.n_queries) {
+      const int q = threadIdx.x, k = p.k;
+      const float* ss = reinterpret_cast<const float*>(smem);
+      const int* si = reinterpret_cast<const int*>(smem + 4 * 32 * kRegK * sizeof(float));
+      float* cs = p.cand_score + ((size_t)q * p.n_work + blockIdx.x) * k;
+      int* ci = p.cand_idx + ((size_t)q * p.n_work + blockIdx.x) * k;
+      int h[4] = {0, 0, 0, 0};
+      for (int r = 0; r < k; ++r) {
+        int bw = -1, bi = 0;
+        float bs = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          if (h[w] < k) {
+            const int id = si[(size_t)(w * 32 + q) * k + h[w]];
+            const float sc = ss[(size_t)(w * 32 + q) * k + h[w]];
+            if (id >= 0 && (bw < 0 || sc > bs || (sc == bs && id < bi))) {
+              bw = w;
+              bs = sc;
+              bi = id;
+            }
+          }
+        }
+        cs[r] = bw < 0 ? -CUDART_INF_F : bs;
+        ci[r] = bw < 0 ? -1 : bi;
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+          if (w == bw) ++h[w];
+      }
+    }
+    if (p.tail_mode != 0) __threadfence();
+    __syncthreads();
+  }
+
   // ===================== tail: candidate merge (+ multi-GPU exchange) inside the same launch ============
   // Worker CTAs publish their lists and arrive on a device counter; CTA q (q < n_queries) waits for all
   // n_work arrivals, merges query q's lists out of L2 (ring/Q shared memory is free by now) and - multi-GPU
@@ -1531,11 +1700,11 @@ cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dt
   return cudaGetLastError();
 }
 
-template <int NACC, bool REGLIST, bool QRES>
+template <int NACC, bool REGLIST, bool QRES, bool DOCM = false>
 static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t stream) {
   const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, QRES, p.qstages, p.bufc,
-                                    p.lists_global != 0, QRES && p.q_resident == 2);
-  auto kern = fused_search_kernel<NACC, REGLIST, QRES>;
+                                    p.lists_global != 0, QRES && p.q_resident == 2, DOCM);
+  auto kern = fused_search_kernel<NACC, REGLIST, QRES, DOCM>;
   const int bytes = (int)map.total + 1024;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
@@ -1544,9 +1713,9 @@ static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t 
 }
 
 int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages, int bufc,
-                     int lists_global) {
+                     int lists_global, int docm) {
   return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages, bufc, lists_global != 0,
-                            q_resident == 2)
+                            q_resident == 2, docm != 0)
              .total + 1024;
 }
 int fused_reg_k() { return kRegK; }
@@ -1560,6 +1729,10 @@ static cudaError_t launch_fused_q(const SearchParams& p, int grid, cudaStream_t 
 cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t stream) {
   const bool reglist = p.k <= kRegK;
   const int nacc = (p.terms == 2 || p.planes == 2) ? 2 : 1;
+  if (p.docm) {
+    if (nacc != 1 || !reglist || p.q_resident != 1 || p.bpad > 32 || p.sub != 1 || p.nbuf > 8) return cudaErrorInvalidValue;
+    return launch_fused_t<1, true, true, true>(p, grid, stream);
+  }
   if (nacc == 1) return reglist ? launch_fused_q<1, true>(p, grid, stream) : launch_fused_q<1, false>(p, grid, stream);
   return reglist ? launch_fused_q<2, true>(p, grid, stream) : launch_fused_q<2, false>(p, grid, stream);
 }
