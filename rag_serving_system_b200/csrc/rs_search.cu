@@ -780,7 +780,7 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
 }
 
 // ------------------------------------------------------------------------------------------
-// Doc-major variant (B <= 32, k <= 16, one query term, 16-bit storage, dot metric): DOCUMENTS are the
+// Doc-major variant (B <= 32, k <= 16, one query term, 16-bit storage; dot or cosine): DOCUMENTS are the
 // MMA's M (128 per tile, one TMEM lane each) and the QUERIES its N (16 or 32 columns).  Against the
 // query-major M=64 x N=128 MMA that is half the tensor work at B=32 (no padding rows), a quarter of the
 // Q-operand reads, and 16-32 accumulator columns per tile instead of 128, i.e. up to 16 tiles of TMEM
@@ -790,6 +790,9 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
 // 32x32 scores are parked in shared memory ([query][doc]) and every lane walks its own query's passing
 // documents in ascending order - lane-parallel across queries, like the query-major rare path.  At the
 // end the four warps' lists of a query are merged in shared memory into the CTA's one list.
+// Cosine: a thread knows its document's norm, so it turns its 32 raw scores into exact cosines
+// (retriever.py:605-609, same operation order as the query-major kernel) before comparing - no
+// conservative per-tile bounds are needed.
 // ------------------------------------------------------------------------------------------
 struct DmBars {
   uint32_t tfull0, tempty0, sched_full0, sched_empty0, qfull;
@@ -797,8 +800,8 @@ struct DmBars {
 };
 template <int KS>
 __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars& b, uint32_t tmem_base, int w, int lane,
-                                            float* dump /* this warp's [32][32] */, const float* s_qscale, bool inline_prep,
-                                            bool worker, float* out_s /* [4][32][k] */, int* out_i) {
+                                            float* dump /* this warp's [32][32] */, float* s_qnorm, float* s_qscale,
+                                            bool inline_prep, bool worker, float* out_s /* [4][32][k] */, int* out_i) {
   constexpr int kSched = KS;
   const int k = p.k, nq = p.n_queries;
   const uint32_t lane_base = tmem_base + ((uint32_t)(w * 32) << 16);
@@ -813,7 +816,16 @@ __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars&
     li[j] = -1;
   }
   float mythr = lane < nq ? -CUDART_INF_F : CUDART_INF_F;
-  if (inline_prep && worker) mbar_wait(b.qfull, 0);
+  const bool cosine = p.metric == RS_METRIC_COSINE;
+  if (inline_prep && worker) {
+    mbar_wait(b.qfull, 0);
+  } else if (worker) {
+    // separate prep kernel: bring the per-query constants into shared memory (every warp writes the same
+    // values, so no cross-warp synchronisation is needed before this warp reads them back)
+    s_qnorm[lane] = lane < nq ? p.qnorm[lane] : 0.f;
+    s_qscale[lane] = lane < nq ? p.qscale[lane] : 1.f;
+    __syncwarp();
+  }
   int acc = 0, sslot = 0;
   uint32_t acc_ph = 0, sph = 0;
   while (true) {
@@ -826,6 +838,8 @@ __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars&
       sph ^= 1u;
     }
     if (t < 0) break;
+    const int doc0 = t * RS_TILE_ROWS + w * 32;
+    const float nd = cosine ? __ldg(p.dnorm + doc0 + lane) : 1.f;  // dnorm is padded to whole tiles
     mbar_wait(b.tfull0 + 8u * acc, acc_ph);
     tc_fence_after();
     float v[32];
@@ -845,7 +859,13 @@ __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars&
       acc_ph ^= 1u;
     }
     if (p.debug_flags & 2) continue;
-    const int doc0 = t * RS_TILE_ROWS + w * 32;
+    if (cosine) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float denom = __fadd_rn(__fmul_rn(s_qnorm[j], nd), 1e-8f);      // retriever.py:605,607
+        v[j] = fminf(fmaxf(__fdiv_rn(v[j] * s_qscale[j], denom), -1.0f), 1.0f);  // :607,:609
+      }
+    }
     if (doc0 + 32 > p.n_rows && doc0 + lane >= p.n_rows) {  // ragged last tile: padded documents never pass
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = -CUDART_INF_F;
@@ -889,7 +909,7 @@ __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars&
   }
   // this warp's list of query `lane`, best first, final units (exact power-of-two scale)
   if (lane < nq && worker) {
-    const float qs = inline_prep ? s_qscale[lane] : p.qscale[lane];
+    const float qs = cosine ? 1.0f : s_qscale[lane];  // cosine lists are already in final units
     float* os = out_s + (size_t)(w * 32 + lane) * k;
     int* oi = out_i + (size_t)(w * 32 + lane) * k;
 #pragma unroll
@@ -1207,7 +1227,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       // lists of the four warps go to shared memory at offset 0: by then the last accumulator is complete, so
       // the Q image and the ring are dead
       dm_epilogue<kSched>(p, bars, tmem_base, quarter, lane, reinterpret_cast<float*>(smem + map.dump_off) + quarter * 1024,
-                          s_qscale, inline_prep, worker, reinterpret_cast<float*>(smem),
+                          s_qnorm, s_qscale, inline_prep, worker, reinterpret_cast<float*>(smem),
                           reinterpret_cast<int*>(smem + 4 * 32 * kRegK * sizeof(float)));
     } else if (quarter < nact_warps) {
       const int row = quarter * rows_per_warp + lane;
