@@ -322,8 +322,9 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     return fail(RS_E_CUDA, "a previous search timed out waiting for its own CTAs (device shared with another job?)");
   }
   // doc-major kernel variant (documents on the MMA's M): half the tensor work and a quarter of the Q-operand reads
-  // at B=32; for B <= 32, k <= 16, one query term, 16-bit storage, resident Q (RS_DOCM=0: off)
-  const bool docm = pl.q_resident == 1 && terms == 1 && ix->planes == 1 && k <= rs::fused_reg_k() && pl.bpad <= 32 &&
+  // at B=32; for B <= 32, k <= 16, resident Q (RS_DOCM=0: off; RS_DOCM=2: only one-term 16-bit searches)
+  const bool docm = pl.q_resident == 1 && (env_int("RS_DOCM", 1) == 1 ? true : (terms == 1 && ix->planes == 1)) &&
+                    k <= rs::fused_reg_k() && pl.bpad <= 32 &&
                     pl.sub == 1 && env_int("RS_DOCM", 1) != 0 &&
                     rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, 1, 2 * terms, pl.bufc, pl.lg, 1) <= kMaxSmem;
   if (docm) pl.nbuf = 8;

@@ -780,7 +780,7 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
 }
 
 // ------------------------------------------------------------------------------------------
-// Doc-major variant (B <= 32, k <= 16, one query term, 16-bit storage; dot or cosine): DOCUMENTS are the
+// Doc-major variant (B <= 32, k <= 16, resident Q; any storage type, one or two query terms, dot or cosine): DOCUMENTS are the
 // MMA's M (128 per tile, one TMEM lane each) and the QUERIES its N (16 or 32 columns).  Against the
 // query-major M=64 x N=128 MMA that is half the tensor work at B=32 (no padding rows), a quarter of the
 // Q-operand reads, and 16-32 accumulator columns per tile instead of 128, i.e. up to 16 tiles of TMEM
@@ -798,7 +798,7 @@ struct DmBars {
   uint32_t tfull0, tempty0, sched_full0, sched_empty0, qfull;
   volatile int* tile_u;
 };
-template <int KS>
+template <int KS, int NACC>
 __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars& b, uint32_t tmem_base, int w, int lane,
                                             float* dump /* this warp's [32][32] */, float* s_qnorm, float* s_qscale,
                                             bool inline_prep, bool worker, float* out_s /* [4][32][k] */, int* out_i) {
@@ -845,10 +845,18 @@ __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars&
     float v[32];
     {
       uint32_t r[32];
-      tmem_ld_x32(lane_base + (uint32_t)acc * 32u, r);
-      tmem_wait_ld();
+      tmem_ld_x32(lane_base + (uint32_t)(acc * NACC) * 32u, r);
+      if (NACC == 2) {  // hi + lo accumulators (two query terms and/or an fp32 corpus stored as two planes)
+        uint32_t r1[32];
+        tmem_ld_x32(lane_base + (uint32_t)(acc * NACC) * 32u + 32u, r1);
+        tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r1[j]), p.lo_coef, __uint_as_float(r[j]));
+      } else {
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      }
     }
     // the scores are in registers: hand the accumulator back before looking at them
     tc_fence_before();
@@ -962,7 +970,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   const int S = p.sub;     // 128-document tiles per supertile
   const int NB = p.nbuf;   // accumulator buffers in TMEM (>1: the epilogue overlaps the next supertiles' MMAs)
   // doc-major: 32 query columns per tile, NB (8 or 16) buffers
-  const uint32_t tmem_cols = DOCM ? (uint32_t)NB * 32u : (uint32_t)(NB * S * NACC) * RS_TILE_ROWS;  // 128, 256 or 512
+  const uint32_t tmem_cols = DOCM ? (uint32_t)(NB * NACC) * 32u : (uint32_t)(NB * S * NACC) * RS_TILE_ROWS;  // 128, 256 or 512
   const int n_super = (p.n_tiles + S - 1) / S;
   const uint32_t qblk = (uint32_t)p.bpad * RS_KCHUNK_BYTES;
   // CTAs >= n_work own no tiles: they exist only so that every query has a CTA for the tail merge
@@ -1124,7 +1132,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       const int nsub = min(S, p.n_tiles - u * S);
       mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
       tc_fence_after();
-      const uint32_t dbase = DOCM ? tmem_base + (uint32_t)acc * 32u : tmem_base + (uint32_t)(acc * S * NACC) * RS_TILE_ROWS;
+      const uint32_t dbase = DOCM ? tmem_base + (uint32_t)(acc * NACC) * 32u : tmem_base + (uint32_t)(acc * S * NACC) * RS_TILE_ROWS;
+      constexpr uint32_t kAcc2 = DOCM ? 32u : (uint32_t)RS_TILE_ROWS;  // column offset of the low-order accumulator
       for (int kc = 0; kc < p.kc; kc += cps) {
         uint32_t qa0, qa1 = 0;
         int qslot0 = 0, qslot1 = 0;
@@ -1173,10 +1182,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
               const uint32_t bc = b_smem + (uint32_t)c * RS_BLOCK_BYTES;
               if (pl == 0) {
                 issue(d0, qa0 + (uint32_t)c * qblk, bc, fresh);
-                if (NACC == 2) issue(d0 + RS_TILE_ROWS, qa1 + (uint32_t)c * qblk, bc, fresh);
+                if (NACC == 2) issue(d0 + kAcc2, qa1 + (uint32_t)c * qblk, bc, fresh);
               } else {
                 // lo plane of an fp32 corpus: q_hi . d_lo joins the low-order accumulator
-                issue(d0 + RS_TILE_ROWS, qa0 + (uint32_t)c * qblk, bc, false);
+                issue(d0 + kAcc2, qa0 + (uint32_t)c * qblk, bc, false);
               }
             }
             __syncwarp();
@@ -1226,7 +1235,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       const DmBars bars{tfull_bar(0), tempty_bar(0), sched_full(0), sched_empty(0), qfull_bar, tile_u};
       // lists of the four warps go to shared memory at offset 0: by then the last accumulator is complete, so
       // the Q image and the ring are dead
-      dm_epilogue<kSched>(p, bars, tmem_base, quarter, lane, reinterpret_cast<float*>(smem + map.dump_off) + quarter * 1024,
+      dm_epilogue<kSched, NACC>(p, bars, tmem_base, quarter, lane, reinterpret_cast<float*>(smem + map.dump_off) + quarter * 1024,
                           s_qnorm, s_qscale, inline_prep, worker, reinterpret_cast<float*>(smem),
                           reinterpret_cast<int*>(smem + 4 * 32 * kRegK * sizeof(float)));
     } else if (quarter < nact_warps) {
@@ -1750,8 +1759,8 @@ cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t st
   const bool reglist = p.k <= kRegK;
   const int nacc = (p.terms == 2 || p.planes == 2) ? 2 : 1;
   if (p.docm) {
-    if (nacc != 1 || !reglist || p.q_resident != 1 || p.bpad > 32 || p.sub != 1 || p.nbuf > 8) return cudaErrorInvalidValue;
-    return launch_fused_t<1, true, true, true>(p, grid, stream);
+    if (!reglist || p.q_resident != 1 || p.bpad > 32 || p.sub != 1 || p.nbuf > 8) return cudaErrorInvalidValue;
+    return nacc == 1 ? launch_fused_t<1, true, true, true>(p, grid, stream) : launch_fused_t<2, true, true, true>(p, grid, stream);
   }
   if (nacc == 1) return reglist ? launch_fused_q<1, true>(p, grid, stream) : launch_fused_q<1, false>(p, grid, stream);
   return reglist ? launch_fused_q<2, true>(p, grid, stream) : launch_fused_q<2, false>(p, grid, stream);
