@@ -276,6 +276,8 @@ MODES = [
     {"RS_QLO_STREAM": "2"}, {"RS_QLO_STREAM": "2", "RS_CPS": "1"}, {"RS_QLO_STREAM": "0"},
     # k > 16 state: lists in shared memory instead of global memory, no bound shared between CTAs
     {"RS_LISTS_GLOBAL": "0"}, {"RS_SHARED_BOUND": "0"}, {"RS_DYN_SCHED": "0"},
+    # query-major kernel everywhere / doc-major kernel only for one-term 16-bit searches
+    {"RS_DOCM": "0"}, {"RS_DOCM": "2"}, {"RS_DOCM": "0", "RS_FUSED_TAIL": "0", "RS_INLINE_PREP": "0"},
 ]
 
 
