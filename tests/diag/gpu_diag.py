@@ -11,7 +11,7 @@ import traceback
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import retrieval_oracle as o  # noqa: E402
 from rag_serving_system_b200 import _cabi  # noqa: E402

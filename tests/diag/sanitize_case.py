@@ -1,10 +1,10 @@
 """Small searches for compute-sanitizer (memcheck / racecheck / synccheck):
 
-    compute-sanitizer --tool memcheck python tools/sanitize_case.py
+    compute-sanitizer --tool memcheck python tests/diag/sanitize_case.py
 """
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import retrieval_oracle as o
 from rag_serving_system_b200 import _cabi
