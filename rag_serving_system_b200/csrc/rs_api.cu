@@ -1,5 +1,6 @@
 // C-ABI host side of the retriever backend (include/rs_retriever.h).  Owns all device memory,
-// plans the per-call launch sequence (query prep -> fused score+select -> candidate merge) and
+// plans each search (make_plan: passes, Q residency, ring geometry, kernel orientation; normally ONE
+// launch: query prep, score+select and candidate merge / exchange inside fused_search_kernel) and
 // never computes a result on the CPU.
 #include <cuda_runtime.h>
 #include <math.h>

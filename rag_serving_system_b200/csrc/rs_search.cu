@@ -1,17 +1,26 @@
 // Fused score-and-select for the retriever hot path (replaces retriever.py:594-611 + :750-769
 // of the reference: SGEMM + 5 elementwise temporaries + B full-length sorts).
 //
-//   query_prep_kernel      fp32 queries -> MMA-ready "Q image" (+ norms, power-of-two scales)
-//   fused_search_kernel    persistent, warp-specialised: bulk-copy (TMA engine) producer warp,
-//                          single-thread tcgen05.mma issuer, epilogue warps that read the score
-//                          tile from TMEM and keep one running top-k per query (one thread per
-//                          query) - the B x N score matrix never exists in HBM
-//   merge_topk_kernel      multi-way merge of the per-CTA (or per-GPU) sorted candidate lists
+//   fused_search_kernel    ONE launch per search.  Persistent (one CTA per SM), warp-specialised:
+//                            warp 0     bulk-copy (TMA engine) producer + dynamic tile scheduler
+//                            warp 1     single-thread tcgen05.mma issuer, accumulators in TMEM
+//                            warps 2-5  prologue: fp32 queries -> swizzled Q image in shared memory (k-major,
+//                                       per-group barriers); epilogue: scores from TMEM -> running top-k,
+//                                       the B x N score matrix never exists in HBM
+//                            tail       per-CTA lists -> arrival counter -> CTA q merges query q
+//                                       (+ multi-GPU: peer stores over NVLink, epoch flags, final merge)
+//                          Two orientations (template DOCM):
+//                            doc-major   (B <= 32, k <= 16): the 128 documents of a tile are the MMA's M, the
+//                                        queries its N; a thread holds the 32 query scores of its document
+//                            query-major (everything else): queries are M (64 or 128 TMEM lanes, one per
+//                                        query), documents N = 128; a thread owns one query's top-k
+//   query_prep_kernel      stand-alone query prep (streamed-Q plans, B > 32, D > 1024, RS_INLINE_PREP=0)
+//   merge_local_kernel, exchange_merge_kernel, exchange_finalize_kernel, merge_topk_kernel
+//                          stand-alone merges: fallbacks of the tail, deferred-exchange flush, rs_merge_device
 //
-// Orientation: queries are the MMA A operand (M = 128 lanes of TMEM, one lane per query row),
-// documents are the B operand (N = 128 documents per tile).  Only Bpad <= 64 A rows exist in
-// shared memory; the remaining rows of the M=128 operand alias whatever follows in shared
-// memory and produce garbage in TMEM lanes that are never read (rows of D are independent).
+// Query-major operand note: only Bpad A rows exist in shared memory; the remaining rows of the M=64/128
+// operand alias whatever follows in shared memory and produce garbage in TMEM lanes that are never read
+// (rows of D are independent).  The same holds for the doc-major N operand when Bpad < 16 or 32.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
