@@ -178,11 +178,14 @@ class B200Retriever:
         metric = metric or self._metric
         terms = query_terms or self._query_terms or _auto_query_terms(q, self._dtype)
         B = q.shape[0]
-        out_i = np.full((B, k), -1, dtype=np.int64)
-        out_s = np.full((B, k), -np.inf, dtype=np.float32)
         kk = min(k, self._max_k)
         if kk < k:
             raise ValueError(f"k={k} exceeds max_k={self._max_k} given at construction")
+        if B <= self._max_batch and len(self._shards) == 1:      # the serving case: one call, fresh arrays
+            with self._lock:
+                return self._shards[0].search(q, k, metric, terms)
+        out_i = np.full((B, k), -1, dtype=np.int64)
+        out_s = np.full((B, k), -np.inf, dtype=np.float32)
         with self._lock:
             for b0 in range(0, B, self._max_batch):
                 qb = q[b0:b0 + self._max_batch]
@@ -301,22 +304,39 @@ class B200Retriever:
             return [[] for _ in ks]
         try:
             idx, _ = self.search(query_embeddings, max_k)                 # :736-773
-            docs = self.documents
-            out: List[List[str]] = []
-            for i in range(batch_size):                                   # :776-790
-                k_i = ks[i]
-                if k_i <= 0:
-                    out.append([])
-                    continue
-                row = idx[i]
-                out.append(_gather(docs, row[row >= 0][:k_i]))
-            return out
+            return _rows_to_docs(self.documents, idx, ks)                 # :776-790
         except Exception as e:                                            # :796-799
             log.error("Error during batch_retrieve: %s", e, exc_info=True)
             return [[] for _ in ks]
 
     def stats(self) -> List[dict]:
         return [ix.stats() for ix in self._shards]
+
+
+def _rows_to_docs(documents, idx: np.ndarray, ks) -> List[List[str]]:
+    """retriever.py:776-790 for a whole batch: row i -> documents of its first k_i valid (>= 0) indices, [] for
+    k_i <= 0.  One ``tolist()`` for the index matrix and ``itemgetter`` for the lookups keep the per-query
+    work out of NumPy (32 queries x 3 small-array operations cost more than the GPU search on a small
+    corpus)."""
+    rows = idx.tolist()
+    has_pad = bool((idx < 0).any())
+    is_list = isinstance(documents, list)
+    out: List[List[str]] = []
+    for row, k_i in zip(rows, ks):
+        if k_i <= 0:
+            out.append([])
+            continue
+        if has_pad:
+            row = [j for j in row if j >= 0]
+        row = row[:k_i]
+        n = len(row)
+        if n == 0:
+            out.append([])
+        elif n == 1 or not is_list:
+            out.append([documents[j] for j in row])
+        else:
+            out.append(list(itemgetter(*row)(documents)))
+    return out
 
 
 def _gather(documents, idx) -> List[str]:

@@ -192,3 +192,32 @@ def test_packed_buffer_alignment():
         buf = torch.zeros(nb, dtype=torch.uint8)
         i, s = sharded.pack_views(buf, B, k)
         assert i.shape == (B, k) and s.shape == (B, k) and i.dtype == torch.int64 and s.dtype == torch.float32
+
+
+def test_rows_to_docs_matches_reference_slicing():
+    """The batch helper behind batch_retrieve (retriever.py:776-790): same lists as the per-row
+    ``row[row >= 0][:k_i]`` + lookup it replaces, for padded rows, k_i <= 0, k_i > row length, tuple docs."""
+    from rag_serving_system_b200.retriever import _rows_to_docs
+    rng = np.random.default_rng(0)
+    docs = [f"d{i}" for i in range(50)]
+    for trial in range(200):
+        B, k = int(rng.integers(1, 9)), int(rng.integers(1, 12))
+        idx = rng.integers(0, 50, size=(B, k)).astype(np.int64)
+        if trial % 2:                                   # -1 padding at the end of some rows (N < k)
+            for r in range(B):
+                n_pad = int(rng.integers(0, k + 1))
+                if n_pad:
+                    idx[r, k - n_pad:] = -1
+        ks = [int(x) for x in rng.integers(-2, k + 3, size=B)]
+        want = []
+        for i in range(B):
+            if ks[i] <= 0:
+                want.append([])
+            else:
+                row = idx[i]
+                want.append([docs[int(j)] for j in row[row >= 0][:ks[i]]])
+        assert _rows_to_docs(docs, idx, ks) == want
+        assert _rows_to_docs(tuple(docs), idx, ks) == want
+    got = _rows_to_docs(docs, np.array([[3, 4]], dtype=np.int64), [2])
+    got[0].append("x")                                  # fresh lists: mutating the result never touches documents
+    assert docs[3] == "d3" and len(docs) == 50
