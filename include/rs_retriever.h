@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 1
+#define RS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RS_API __attribute__((visibility("default")))
@@ -72,6 +72,8 @@ typedef struct rs_stats {
   int32_t sub;              /* 128-document tiles per supertile */
   int32_t nbuf;             /* TMEM accumulator buffers */
   int32_t mma_m;            /* MMA M of the last fused kernel (64 or 128) */
+  int32_t overlapped;       /* 1: the last search was launched with programmatic dependent launch (RS_OVERLAP) */
+  int32_t doc_major;        /* 1: the last search ran the doc-major kernel variant */
   int64_t bytes_streamed;   /* corpus bytes read by the last search (passes * shard bytes) */
   int64_t corpus_bytes;     /* device bytes of the tiled corpus image */
   int64_t total_launches;   /* kernels launched since rs_create */
@@ -115,9 +117,26 @@ RS_API int rs_search(rs_index* ix, const float* q_host, int32_t B, int32_t k, in
 
 /* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t passed as void*; NULL =
  * the legacy default stream).  This is the per-GPU step of the sharded search; the outputs are
- * the B x k candidates that the NCCL all-gather exchanges. */
+ * the B x k candidates that the NCCL all-gather exchanges.
+ * Streams: an index has ONE set of workspaces.  Searches are serialised by the library: a search enqueued
+ * on another stream than the previous one first waits (cudaStreamWaitEvent) for the previous search, so
+ * callers may mix rs_search, rs_search_device on torch's current stream, etc.; a stream handed in must stay
+ * valid until the next search call.  A device-side time-out (a wait inside the kernel gave up) cannot be
+ * reported by this asynchronous call: it surfaces from rs_check, or from the next search call. */
 RS_API int rs_search_device(rs_index* ix, const float* q_dev, int32_t B, int32_t k, int32_t metric, int32_t query_terms,
                      int64_t* out_idx_dev, float* out_score_dev, void* stream);
+/* RS_OK, or RS_E_CUDA if a kernel of an earlier asynchronous search raised the error word (and clears it).
+ * Call after synchronising the stream.  rs_search and the other host-buffer calls check it themselves and
+ * fail the call whose result is affected. */
+RS_API int rs_check(rs_index* ix);
+
+/* Switches of an index (replaces nothing in the reference; tests and A/B measurements).  The RS_* environment
+ * variables of the same names are read ONCE, by rs_create; this call changes one afterwards.
+ * RS_OVERLAP=1 lets consecutive rs_search_device / rs_search_exchange calls on one stream overlap: the scan of
+ * search i+1 starts while the tail of search i (merge, exchange) drains (programmatic dependent launch).  The
+ * caller then guarantees that the queries of a search are not written by the kernel that precedes it on that
+ * stream (the prologue reads them before the predecessor has finished), and rs_get_kernel_times is unavailable. */
+RS_API int rs_set_option(rs_index* ix, const char* name, int32_t value);
 
 /* Final merge of n_lists sorted candidate lists per query (the multi-GPU step):
  * list l holds scores float[B][kc] at scores_dev + l*score_list_stride and indices int64[B][kc]
@@ -133,10 +152,11 @@ RS_API int rs_merge_device(int32_t device, const float* scores_dev, const int64_
  * buffer, exports its 64-byte CUDA IPC handle, and imports every peer's handle (exchanged by the
  * host program, e.g. with torch.distributed.all_gather).  rs_search_exchange then runs, as ONE kernel
  * launch per search (two when the batch or dimension needs the separate query-prep kernel),
- *   query prep -> fused score+select -> [local merge + peer stores of each query's k candidates
- *   into every GPU's buffer + per-query epoch flag + wait for all ranks' flags + final merge]
- * with no collective call; every rank ends with the same global top-k.
- * All ranks must call it in the same order with the same B and k. */
+ *   query prep -> fused score+select -> [local merge + peer stores of each query's k candidates into every
+ *   GPU's buffer as 16-byte {index, score, epoch} entries + poll of the local entries + final merge]
+ * with no collective call; every rank ends with the same global top-k.  The search epoch lives in device
+ * memory, so the call can be captured in a CUDA graph.  All ranks must issue the same sequence of searches
+ * (same B and k); a rank whose peers never show up gets RS_E_CUDA (rs_check / next call), not a hang. */
 typedef struct rs_xchg rs_xchg;
 RS_API int rs_xchg_create(int32_t device, int32_t world, int32_t rank, int32_t max_batch, int32_t max_k, rs_xchg** out);
 RS_API int rs_xchg_export(rs_xchg* x, void* handle64);
@@ -144,21 +164,34 @@ RS_API int rs_xchg_import(rs_xchg* x, int32_t peer_rank, const void* handle64);
 RS_API int rs_xchg_destroy(rs_xchg* x);
 RS_API int rs_search_exchange(rs_index* ix, rs_xchg* x, const float* q_dev, int32_t B, int32_t k, int32_t metric,
                        int32_t query_terms, int64_t* out_idx_dev, float* out_score_dev, void* stream);
-/* Deferred (pipelined) form for back-to-back searches: the launch pushes this search's rows to the peers and
- * returns without waiting for them; its final merge - into the out_* buffers given HERE - is done by the tail
- * of the NEXT rs_search_exchange_async launch (while that launch waits for its own slowest CTAs) or by
- * rs_xchg_flush.  The out_* buffers of call i are therefore valid, in stream order, after call i+1 or after the
- * flush, and must stay allocated until then.  No rank ever waits for a peer's current search, so ranks run at
- * their own pace with one search of slack (three exchange-buffer parities).  Every rank must issue the same
- * sequence of calls.  rs_search_exchange flushes a pending search first; call rs_xchg_flush before
- * rs_xchg_destroy. */
-RS_API int rs_search_exchange_async(rs_index* ix, rs_xchg* x, const float* q_dev, int32_t B, int32_t k, int32_t metric,
-                             int32_t query_terms, int64_t* out_idx_dev, float* out_score_dev, void* stream);
-RS_API int rs_xchg_flush(rs_index* ix, rs_xchg* x, void* stream);
+/* The same search with HOST buffers, blocking (the sharded counterpart of rs_search): pinned H2D of the
+ * queries, the search with the in-kernel exchange, D2H of the result; replayed from a CUDA graph from the
+ * second call of a shape on.  out_idx == out_score == NULL: this rank takes part but does not need the result
+ * on the host (only one rank of a sharded service answers the caller) - no D2H. */
+RS_API int rs_search_exchange_host(rs_index* ix, rs_xchg* x, const float* q_host, int32_t B, int32_t k, int32_t metric,
+                            int32_t query_terms, int64_t* out_idx, float* out_score);
+/* Same-process peers: make `peer`'s buffer reachable from `x` through CUDA peer access instead of an IPC handle. */
+RS_API int rs_xchg_attach(rs_xchg* x, rs_xchg* peer);
+
+/* Single-process multi-GPU (replaces nothing: the reference has one GPU; this is what `CupyRetriever(...)`
+ * constructed once in one process - main.py:52-55 - drives when it owns several devices).  `shards` are n
+ * indices on n DISTINCT devices holding consecutive row ranges (row_offset) of one corpus, with the same dim,
+ * dtype, max_batch and max_k; the group does not own them (destroy the group first).  rs_group_search is
+ * rs_search for the whole corpus: one pinned copy of the queries, H2D + ONE fused kernel per GPU (candidate
+ * exchange and final merge inside the kernels, over NVLink peer memory), ONE D2H from the first shard's GPU;
+ * the whole multi-device sequence is replayed from one CUDA graph from the second call of a shape on. */
+typedef struct rs_group rs_group;
+RS_API int rs_group_create(rs_index** shards, int32_t n, rs_group** out);
+RS_API int rs_group_search(rs_group* g, const float* q_host, int32_t B, int32_t k, int32_t metric, int32_t query_terms,
+                    int64_t* out_idx, float* out_score);
+RS_API int rs_group_destroy(rs_group* g);
 
 /* Read back the represented values of rows [row0,row0+nrows) as float (inverse of the tiling);
  * used by the tests (ingest round trip) and by the CPU-baseline sampler. */
 RS_API int rs_get_rows(rs_index* ix, int64_t row0, int64_t nrows, float* out_host);
+/* Same rows into DEVICE memory (float[nrows*dim] on the index's device), asynchronous on `stream`: lets a test
+ * recompute scores of the whole shard on the GPU with an independent matmul. */
+RS_API int rs_get_rows_device(rs_index* ix, int64_t row0, int64_t nrows, float* out_dev, void* stream);
 RS_API int rs_get_norms(rs_index* ix, int64_t row0, int64_t nrows, float* out_host);
 /* Raw tiled image bytes [off, off+nbytes) - layout tests compare them bit-exactly with the oracle. */
 RS_API int rs_get_image(rs_index* ix, int64_t off, int64_t nbytes, void* out_host);
@@ -167,7 +200,7 @@ RS_API int rs_get_stats(rs_index* ix, rs_stats* out);
 /* Launch plan the host would pick for a search (no device needed; used by the CPU tests):
  * out9 = {passes, queries_per_pass, bpad, ring_stages, q_resident, sub, nbuf, mma_m, chunks_per_stage}. */
 RS_API int rs_debug_plan(int32_t dim, int32_t dtype, int32_t B, int32_t k, int32_t query_terms, int32_t* out9);
-/* Timing experiments only: with RS_DEBUG_TS=1 in the environment the fused kernel stamps %globaltimer
+/* Timing experiments only: with RS_DEBUG_TS=1 (environment at rs_create, or rs_set_option) the fused kernel stamps %globaltimer
  * (ns) at 7 phase boundaries per CTA (entry, query prep done, first accumulator, last tile, arrival,
  * all arrived, merged); out = uint64[n_ctas][8] of the last launch. */
 RS_API int rs_debug_timestamps(rs_index* ix, uint64_t* out, int32_t n_ctas);

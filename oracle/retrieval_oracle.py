@@ -220,6 +220,40 @@ def check_topk(idx, val, S_exact: np.ndarray, k: int, rtol: float, atol: float =
     return swaps
 
 
+def check_topk_candidates(idx, val, cand_idx, cand_score, got_exact, k: int, rtol: float, atol: float = 0.0):
+    """``check_topk`` for corpora too large to hold the full score matrix.  ``cand_idx`` / ``cand_score``
+    ([B, M], M > k) are the exact best M documents per query from an INDEPENDENT computation (ordered score
+    desc, index asc); ``got_exact`` [B, k] holds the exact scores of the returned indices.  Same bar: returned
+    scores within tolerance, rows descending, and every difference from the exact top-k set lies inside the
+    rounding band around the k-th score.  Returns the number of near-tie substitutions."""
+    idx = np.asarray(idx)
+    val = np.asarray(val, dtype=np.float64)
+    cand_idx = np.asarray(cand_idx)
+    cand_score = np.asarray(cand_score, dtype=np.float64)
+    got_exact = np.asarray(got_exact, dtype=np.float64)
+    B, M = cand_idx.shape
+    assert M > k
+    swaps = 0
+    for b in range(B):
+        got = idx[b, :k]
+        assert (got >= 0).all() and len(set(got.tolist())) == k, f"row {b}: bad indices {got}"
+        tol = atol + rtol * np.abs(got_exact[b])
+        assert (np.abs(val[b, :k] - got_exact[b]) <= tol).all(), f"row {b}: score mismatch {val[b, :k]} vs {got_exact[b]}"
+        assert (np.diff(val[b, :k]) <= 0).all(), f"row {b}: not descending"
+        kth = cand_score[b, k - 1]
+        band = atol + rtol * abs(kth)
+        want = set(cand_idx[b, :k].tolist())
+        have = set(got.tolist())
+        exact_of = dict(zip(got.tolist(), got_exact[b].tolist()))
+        exact_of.update(zip(cand_idx[b].tolist(), cand_score[b].tolist()))
+        for j in (want - have) | (have - want):
+            assert abs(exact_of[j] - kth) <= 2 * band, (
+                f"row {b}: index {j} (score {exact_of[j]}) differs from the exact top-{k} (k-th score {kth}) "
+                f"by more than rounding")
+        swaps += len(have - want)
+    return swaps
+
+
 # ----------------------------------------------------------------------------------------------
 # class-level restatements (return conventions, validation order)
 # ----------------------------------------------------------------------------------------------

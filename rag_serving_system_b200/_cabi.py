@@ -20,8 +20,18 @@ EXPORTS = (
     "rs_version", "rs_last_error", "rs_create", "rs_destroy", "rs_load_rows", "rs_fill_synthetic",
     "rs_finalize", "rs_search", "rs_search_device", "rs_merge_device", "rs_get_rows",
     "rs_get_norms", "rs_get_image", "rs_get_stats", "rs_get_kernel_times",
-    "rs_debug_plan", "rs_debug_timestamps", "rs_xchg_create", "rs_xchg_export", "rs_xchg_import", "rs_xchg_destroy", "rs_search_exchange", "rs_search_exchange_async", "rs_xchg_flush",
+    "rs_debug_plan", "rs_debug_timestamps", "rs_xchg_create", "rs_xchg_export", "rs_xchg_import", "rs_xchg_attach",
+    "rs_xchg_destroy", "rs_search_exchange", "rs_search_exchange_host", "rs_check", "rs_set_option",
+    "rs_get_rows_device", "rs_group_create", "rs_group_search", "rs_group_destroy",
 )
+ABI_VERSION = 2          # include/rs_retriever.h: RS_ABI_VERSION
+# switches of an index and their defaults (csrc/rs_api.cu: Options); rs_create reads the environment once
+OPTION_DEFAULTS = {
+    "RS_DOCM": 1, "RS_INLINE_PREP": 1, "RS_FUSED_TAIL": 1, "RS_DYN_SCHED": 1, "RS_SHARED_BOUND": 1,
+    "RS_LISTS_GLOBAL": 1, "RS_QLO_STREAM": 0, "RS_GRAPH": 1, "RS_NO_EVENTS": 0, "RS_OVERLAP": 0,
+    "RS_DEBUG_FLAGS": 0, "RS_DEBUG_TS": 0, "RS_QRESIDENT": -1, "RS_CPS": 0, "RS_SUB": 0, "RS_BUFC": 0,
+    "RS_LEAN": -1, "RS_MMA_M": 0, "RS_NBUF": 0, "RS_QSTAGES": 0,
+}
 
 
 class RsError(RuntimeError):
@@ -42,7 +52,8 @@ class rs_stats(C.Structure):
         ("struct_size", C.c_int32), ("sm_count", C.c_int32), ("grid", C.c_int32),
         ("stages", C.c_int32), ("smem_bytes", C.c_int32), ("passes", C.c_int32),
         ("launches", C.c_int32), ("query_terms", C.c_int32), ("q_resident", C.c_int32), ("sub", C.c_int32),
-        ("nbuf", C.c_int32), ("mma_m", C.c_int32), ("bytes_streamed", C.c_int64),
+        ("nbuf", C.c_int32), ("mma_m", C.c_int32), ("overlapped", C.c_int32), ("doc_major", C.c_int32),
+        ("bytes_streamed", C.c_int64),
         ("corpus_bytes", C.c_int64), ("total_launches", C.c_int64),
     ]
 
@@ -60,14 +71,17 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.exists(path):
-        path = _build.build()
+    if not os.path.exists(path) or (_build.is_stale() and _build.have_nvcc()):
+        path = _build.build()                   # no-op when the library is newer than every source
     if not os.path.exists(path):
         raise RsError(f"{path} is missing: run `python -m rag_serving_system_b200.build`; "
                       "there is no CPU fallback")
     lib = C.CDLL(path)
     vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
     lib.rs_version.restype = C.c_int
+    if lib.rs_version() != ABI_VERSION:
+        raise RsError(f"{path} has ABI version {lib.rs_version()}, this package expects {ABI_VERSION}: rebuild with "
+                      "`python -m rag_serving_system_b200.build --force`")
     lib.rs_last_error.restype = C.c_char_p
     sigs = {
         "rs_create": [C.POINTER(rs_config), C.POINTER(vp)],
@@ -86,8 +100,14 @@ def load() -> C.CDLL:
         "rs_xchg_import": [vp, i32, vp],
         "rs_xchg_destroy": [vp],
         "rs_search_exchange": [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
-        "rs_search_exchange_async": [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
-        "rs_xchg_flush": [vp, vp, vp],
+        "rs_search_exchange_host": [vp, vp, vp, i32, i32, i32, i32, vp, vp],
+        "rs_xchg_attach": [vp, vp],
+        "rs_check": [vp],
+        "rs_set_option": [vp, C.c_char_p, i32],
+        "rs_get_rows_device": [vp, i64, i64, vp, vp],
+        "rs_group_create": [C.POINTER(vp), i32, C.POINTER(vp)],
+        "rs_group_search": [vp, vp, i32, i32, i32, i32, vp, vp],
+        "rs_group_destroy": [vp],
         "rs_get_rows": [vp, i64, i64, vp],
         "rs_get_norms": [vp, i64, i64, vp],
         "rs_get_image": [vp, i64, i64, vp],
@@ -169,7 +189,25 @@ class Index:
         check(self.lib.rs_search_device(self.h, q_ptr, B, k, METRICS[metric], query_terms, out_idx_ptr,
                                         out_score_ptr, stream), "rs_search_device")
 
+    def check(self):
+        """Raise if a kernel of an earlier asynchronous search reported a time-out (rs_check)."""
+        check(self.lib.rs_check(self.h), "rs_check")
+
+    def set_option(self, name: str, value: int):
+        """Change one RS_* switch after construction (the environment is read once, by rs_create)."""
+        check(self.lib.rs_set_option(self.h, name.encode(), int(value)), "rs_set_option")
+
+    def reload_env_options(self):
+        """Re-read every RS_* switch from the environment (A/B tools flip them between runs on one index)."""
+        for name, dflt in OPTION_DEFAULTS.items():
+            v = os.environ.get(name, "")
+            self.set_option(name, int(v) if v.strip() else dflt)
+
     # ---- introspection
+    def get_rows_device(self, row0: int, nrows: int, out_ptr: int, stream: int = 0):
+        """Rows [row0, row0+nrows) as float32 into DEVICE memory at out_ptr (asynchronous on `stream`)."""
+        check(self.lib.rs_get_rows_device(self.h, row0, nrows, out_ptr, stream), "rs_get_rows_device")
+
     def get_rows(self, row0: int, nrows: int) -> np.ndarray:
         out = np.empty((nrows, self.dim), dtype=np.float32)
         check(self.lib.rs_get_rows(self.h, row0, nrows, out.ctypes.data), "rs_get_rows")
@@ -226,18 +264,53 @@ class Exchange:
         check(self.lib.rs_search_exchange(index.h, self.h, q_ptr, B, k, METRICS[metric], query_terms, out_idx_ptr,
                                           out_score_ptr, stream), "rs_search_exchange")
 
-    def search_async(self, index: "Index", q_ptr: int, B: int, k: int, out_idx_ptr: int, out_score_ptr: int,
-                     metric: str = "dot", query_terms: int = 1, stream: int = 0):
-        """Deferred exchange: the out buffers of this call are valid after the NEXT search_async or flush."""
-        check(self.lib.rs_search_exchange_async(index.h, self.h, q_ptr, B, k, METRICS[metric], query_terms, out_idx_ptr,
-                                                out_score_ptr, stream), "rs_search_exchange_async")
-
-    def flush(self, index: "Index", stream: int = 0):
-        check(self.lib.rs_xchg_flush(index.h, self.h, stream), "rs_xchg_flush")
+    def search_host(self, index: "Index", q: np.ndarray, k: int, metric: str = "dot", query_terms: int = 1,
+                    want_result: bool = True):
+        """Host buffers in and out, blocking (rs_search_exchange_host).  want_result=False: this rank only takes
+        part (no D2H) and gets (None, None)."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        B = q.shape[0]
+        if not want_result:
+            check(self.lib.rs_search_exchange_host(index.h, self.h, q.ctypes.data, B, k, METRICS[metric], query_terms,
+                                                   None, None), "rs_search_exchange_host")
+            return None, None
+        idx = np.empty((B, k), dtype=np.int64)
+        sc = np.empty((B, k), dtype=np.float32)
+        check(self.lib.rs_search_exchange_host(index.h, self.h, q.ctypes.data, B, k, METRICS[metric], query_terms,
+                                               idx.ctypes.data, sc.ctypes.data), "rs_search_exchange_host")
+        return idx, sc
 
     def close(self):
         if getattr(self, "h", None):
             self.lib.rs_xchg_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class Group:
+    """Single-process multi-GPU search over several ``Index`` shards on distinct devices (rs_group_*)."""
+
+    def __init__(self, shards):
+        self.lib = load()
+        self.shards = list(shards)
+        arr = (C.c_void_p * len(self.shards))(*[ix.h for ix in self.shards])
+        h = C.c_void_p()
+        check(self.lib.rs_group_create(arr, len(self.shards), C.byref(h)), "rs_group_create")
+        self.h = h
+
+    def search(self, q: np.ndarray, k: int, metric: str = "dot", query_terms: int = 1):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        B = q.shape[0]
+        idx = np.empty((B, k), dtype=np.int64)
+        sc = np.empty((B, k), dtype=np.float32)
+        check(self.lib.rs_group_search(self.h, q.ctypes.data, B, k, METRICS[metric], query_terms, idx.ctypes.data,
+                                       sc.ctypes.data), "rs_group_search")
+        return idx, sc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rs_group_destroy(self.h)
             self.h = None
 
     __del__ = close

@@ -32,12 +32,32 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; cannot build librs_retriever.so")
 
 
-def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    except RuntimeError:
+        return False
+
+
+STAMP_PATH = LIB_PATH + ".stamp"
+
+
+def _source_hash() -> str:
+    """Content hash of everything the library is built from (mtimes do not survive a snapshot copy)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for name in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH) or not os.path.exists(STAMP_PATH):
+        return True
+    with open(STAMP_PATH) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -48,12 +68,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [_nvcc()] + NVCC_FLAGS
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    tmp = LIB_PATH + f".tmp{os.getpid()}"       # several ranks may build at once: publish with an atomic rename
+    cmd += ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode == 0:
+        os.replace(tmp, LIB_PATH)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
+    with open(STAMP_PATH, "w") as f:
+        f.write(_source_hash() + "\n")
     return LIB_PATH
 
 

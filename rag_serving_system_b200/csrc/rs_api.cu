@@ -54,6 +54,7 @@ struct Plan {
   int cps;         // k-chunks per ring stage
   int bufc;        // k > 16: candidate-buffer entries per query (32; 16 when that saves a pass)
   int lg;          // k > 16: sorted lists in global memory (L2) instead of shared memory
+  int qstages;     // streamed Q: slots of the private Q ring
 };
 
 int env_int(const char* name, int dflt) {
@@ -61,10 +62,48 @@ int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
+// Switches of an index.  Read from the environment ONCE, in rs_create (a search never calls getenv), and
+// changeable afterwards with rs_set_option.  Every non-default value is parity-tested.
+struct Options {
+  int docm = 1;          // RS_DOCM         1: doc-major kernel wherever it applies; 2: one-term 16-bit searches only; 0: never
+  int inline_prep = 1;   // RS_INLINE_PREP  0: separate query_prep_kernel launch
+  int fused_tail = 1;    // RS_FUSED_TAIL   0: separate merge / exchange kernel launch
+  int dyn_sched = 1;     // RS_DYN_SCHED    0: static round-robin tiles
+  int shared_bound = 1;  // RS_SHARED_BOUND k > 16: 0 = no bound shared between CTAs
+  int lists_global = 1;  // RS_LISTS_GLOBAL k > 16: 0 = sorted lists in shared memory
+  int qlo_stream = 0;    // RS_QLO_STREAM   two-term searches: 1/2 = stream the lo query term
+  int graph = 1;         // RS_GRAPH        0: host-buffer searches enqueue eagerly instead of replaying a CUDA graph
+  int no_events = 0;     // RS_NO_EVENTS    1: no CUDA events around the fused launch
+  int overlap = 0;       // RS_OVERLAP      1: consecutive device-buffer searches on one stream may overlap (PDL)
+  int debug_flags = 0;   // RS_DEBUG_FLAGS  timing experiments: skip MMAs (1) / the epilogue (2) / the tail merge (4)
+  int debug_ts = 0;      // RS_DEBUG_TS     per-CTA %globaltimer phase stamps
+  // planner overrides (tests and A/B runs): -1 / 0 = let the planner decide
+  int qresident = -1, cps = 0, sub = 0, bufc = 0, lean = -1, mma_m = 0, nbuf = 0, qstages = 0;
+};
+struct OptDef {
+  const char* name;
+  int Options::*field;
+};
+const OptDef kOptDefs[] = {
+    {"RS_DOCM", &Options::docm}, {"RS_INLINE_PREP", &Options::inline_prep}, {"RS_FUSED_TAIL", &Options::fused_tail},
+    {"RS_DYN_SCHED", &Options::dyn_sched}, {"RS_SHARED_BOUND", &Options::shared_bound},
+    {"RS_LISTS_GLOBAL", &Options::lists_global}, {"RS_QLO_STREAM", &Options::qlo_stream}, {"RS_GRAPH", &Options::graph},
+    {"RS_NO_EVENTS", &Options::no_events}, {"RS_OVERLAP", &Options::overlap}, {"RS_DEBUG_FLAGS", &Options::debug_flags},
+    {"RS_DEBUG_TS", &Options::debug_ts}, {"RS_QRESIDENT", &Options::qresident}, {"RS_CPS", &Options::cps},
+    {"RS_SUB", &Options::sub}, {"RS_BUFC", &Options::bufc}, {"RS_LEAN", &Options::lean}, {"RS_MMA_M", &Options::mma_m},
+    {"RS_NBUF", &Options::nbuf}, {"RS_QSTAGES", &Options::qstages},
+};
+Options options_from_env() {
+  Options o;
+  for (const OptDef& d : kOptDefs) o.*(d.field) = env_int(d.name, o.*(d.field));
+  return o;
+}
+
 }  // namespace
 
 struct rs_index {
   rs_config cfg;
+  Options opt;
   int sm_count = 0;
   int kc = 0, planes = 1, n_tiles = 0;
   int plane_dtype = RS_DTYPE_BF16;
@@ -82,99 +121,74 @@ struct rs_index {
   float* q_dev = nullptr;           // staging for host queries
   long long* out_idx_dev = nullptr;  // staging for host outputs: [indices][scores] of one call, back to back
   void* ingest_dev = nullptr;
-  void* pinned = nullptr;  // pinned host staging (queries in, results out, ingest chunks)
+  void* pinned = nullptr;  // pinned host staging (queries in, results out, ingest chunks); portable across devices
   size_t pinned_bytes = 0;
   cudaStream_t stream = nullptr;
-  unsigned int* sync = nullptr;      // device counters of the fused kernel's tail (arrivals, departures)
+  unsigned int* sync = nullptr;      // two blocks of 64 counters (arrivals, departures, next tile); launches alternate
+  unsigned int launch_parity = 0;
   float* g_best = nullptr;           // shared bound table [sm_count][128] (k > 16 searches)
   unsigned long long* debug_ts = nullptr;  // RS_DEBUG_TS=1: [grid][8] phase stamps of the last fused launch
-  unsigned int* err_flag = nullptr;  // mapped pinned word the kernel raises if its arrival wait times out
+  unsigned int* err_flag = nullptr;  // mapped pinned word a kernel raises when a wait times out (1: own CTAs, 2: a peer GPU)
+  // searches share the workspaces above, so a search on another stream than the previous one is ordered after it
+  cudaStream_t last_stream = nullptr;
+  bool have_last = false;
+  cudaEvent_t order_ev = nullptr;
   // CUDA-event pairs around every fused-kernel launch (on the launching stream) so callers can
   // read the kernel's own duration without a profiler
   static constexpr int kEventRing = 256;
   cudaEvent_t ev_beg[kEventRing] = {}, ev_end[kEventRing] = {};
   cudaEvent_t ingest_done[2] = {};
-  // host-buffer searches replay a captured CUDA graph per (B, k, metric, terms): one launch instead
+  // host-buffer searches replay a captured CUDA graph per (B, k, metric, terms, exchange): one launch instead
   // of six stream operations - what a small (launch-bound) corpus feels
   struct GraphEntry {
     int B, k, metric, terms, uses;
+    const void* xg;
+    int want_out;
     cudaGraphExec_t exec;
   };
   std::vector<GraphEntry> graphs;
-  bool record_events = true;
+  bool capturing = false;
   long long ev_count = 0;
   rs_stats stats;
   std::mutex mu;
 };
 
-// Candidate exchange buffer of one rank (one process per GPU).  Every peer maps it through CUDA
-// IPC and stores its B x k candidates straight into its slot; flags carry the search epoch.
+// Candidate exchange buffer of one GPU.  Peers map it (CUDA IPC across processes, peer access inside one
+// process) and store their B x k candidates straight into their slot; entries carry the search epoch.
+//   [0, 256)  header: u32 epoch, u32 departures
+//   then      entries[2 parities][world slots][max_batch * max_k] of 16 bytes {int64 index, float score, u32 epoch}
 struct rs_xchg {
   int device = 0, world = 1, rank = 0, max_batch = 0, max_k = 0;
-  size_t slot_bytes = 0, parity_bytes = 0, total_bytes = 0;
-  size_t header_bytes = 0;               // flags[2 parities][8 ranks][max_batch] u32, padded to 256 B
-  uint8_t* local = nullptr;              // [flags][parity 0: world slots][parity 1: ...][parity 2: ...]
-  uint8_t* peer[rs::kMaxPeers] = {};     // peer[g] = GPU g's buffer mapped into this process (peer[rank] = local)
-  bool opened[rs::kMaxPeers] = {};
-  unsigned int epoch = 0;
-  // deferred mode: the search whose rows are pushed but whose final merge has not run yet
-  struct Pending {
-    bool valid = false;
-    unsigned int epoch = 0;
-    int B = 0, k = 0;
-    long long* out_idx = nullptr;
-    float* out_score = nullptr;
-  } pending;
+  size_t slot_entries = 0, total_bytes = 0;
+  uint8_t* local = nullptr;
+  uint8_t* peer[rs::kMaxPeers] = {};     // peer[g] = GPU g's buffer as seen from this GPU (peer[rank] = local)
+  bool opened[rs::kMaxPeers] = {};       // mapped through an IPC handle (to be closed)
 };
-constexpr unsigned int kXchgParities = 3;  // epoch % 3: a rank is never more than one search ahead of a peer's reads
+constexpr size_t kXchgHeaderBytes = 256;
 
 namespace {
 
-// kernel arguments of one search's exchange: where this rank's rows go on every GPU, where the world's rows
-// for it arrive locally, and (deferred mode) where its final rows are to be written
-rs::ExchangeArgs make_exchange_args(const rs_xchg* xg, unsigned int epoch, int B, int k, int q0, long long* out_idx,
-                                    float* out_score) {
+rs::ExchangeArgs make_exchange_args(const rs_xchg* xg, int q0, bool last_pass) {
   rs::ExchangeArgs ea;
   memset(&ea, 0, sizeof(ea));
-  const unsigned int parity = epoch % kXchgParities;
   ea.world = xg->world;
+  ea.rank = xg->rank;
   ea.q0 = q0;
-  ea.epoch = epoch;
-  for (int g = 0; g < xg->world; ++g) {
-    uint8_t* slot = xg->peer[g] + xg->header_bytes + parity * xg->parity_bytes + (size_t)xg->rank * xg->slot_bytes;
-    ea.dest_idx[g] = reinterpret_cast<long long*>(slot);
-    ea.dest_score[g] = reinterpret_cast<float*>(slot + (size_t)B * k * 8);
-    ea.dest_flag[g] = reinterpret_cast<unsigned int*>(xg->peer[g]) + ((size_t)parity * rs::kMaxPeers + xg->rank) * xg->max_batch;
-  }
-  ea.wait_flags = reinterpret_cast<const unsigned int*>(xg->local) + (size_t)parity * rs::kMaxPeers * xg->max_batch;
-  ea.flag_stride = xg->max_batch;
-  const uint8_t* base = xg->local + xg->header_bytes + parity * xg->parity_bytes;
-  ea.local_idx = reinterpret_cast<const long long*>(base);
-  ea.local_score = reinterpret_cast<const float*>(base + (size_t)B * k * 8);
-  ea.idx_list_stride = (long long)(xg->slot_bytes / 8);
-  ea.score_list_stride = (long long)(xg->slot_bytes / 4);
-  ea.out_idx = out_idx;
-  ea.out_score = out_score;
-  ea.n_queries = B;
-  ea.k = k;
+  ea.last_pass = last_pass ? 1 : 0;
+  ea.epoch = reinterpret_cast<unsigned int*>(xg->local);
+  for (int g = 0; g < xg->world; ++g)
+    ea.dest[g] = reinterpret_cast<uint4*>(xg->peer[g] + kXchgHeaderBytes) + (size_t)xg->rank * xg->slot_entries;
+  ea.local = reinterpret_cast<const uint4*>(xg->local + kXchgHeaderBytes);
+  ea.slot_entries = (long long)xg->slot_entries;
+  ea.parity_entries = (long long)(xg->slot_entries * xg->world);
   return ea;
 }
 
-// final merge of the pending (pushed, unmerged) search as a kernel of its own
-int flush_pending(rs_xchg* xg, cudaStream_t stream) {
-  if (!xg->pending.valid) return RS_OK;
-  const rs_xchg::Pending& pd = xg->pending;
-  rs::ExchangeArgs ea = make_exchange_args(xg, pd.epoch, pd.B, pd.k, 0, pd.out_idx, pd.out_score);
-  RS_CUDA(rs::launch_exchange_finalize(ea, stream));
-  xg->pending.valid = false;
-  return RS_OK;
-}
-
-int max_cap_rows(int kc, int terms, int k, int min_stages, int cps, int q_resident, int bufc = 32, int lg = 0) {
+int max_cap_rows(int kc, int terms, int k, int min_stages, int cps, int q_resident, int qstages, int bufc = 32, int lg = 0) {
   // largest bpad (multiple of 8, <= 128) that leaves at least min_stages ring slots
   int best = 0;
   for (int bpad = 8; bpad <= 128; bpad += 8) {
-    if (rs::fused_smem_bytes(bpad, kc, terms, min_stages, cps, k, q_resident, 2 * terms, bufc, lg) <= kMaxSmem) best = bpad;
+    if (rs::fused_smem_bytes(bpad, kc, terms, min_stages, cps, k, q_resident, qstages, bufc, lg) <= kMaxSmem) best = bpad;
   }
   return best;
 }
@@ -184,32 +198,32 @@ int max_cap_rows(int kc, int terms, int k, int min_stages, int cps, int q_reside
 // chunk over `sub` document tiles that accumulate side by side in TMEM.  Measured on B200: what
 // limits the stream is the number of barrier round trips per byte, so the planner prefers, in
 // order: fewest passes, resident Q, the largest ring stage (cps k-chunks of 16 KiB), the largest sub.
-int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
+int make_plan(const rs_index* ix, const Options& o, int B, int k, int terms, Plan* pl) {
   const int nacc = (terms == 2 || ix->planes == 2) ? 2 : 1;
-  const int force_res = env_int("RS_QRESIDENT", -1), force_cps = env_int("RS_CPS", 0), force_sub = env_int("RS_SUB", 0);
-  const int force_bufc = env_int("RS_BUFC", 0), force_lean = env_int("RS_LEAN", -1);
   const bool lists_in_smem = k > rs::fused_reg_k();
   // k > 16: keep the sorted lists in global memory (default) so the ring keeps its bytes; RS_LISTS_GLOBAL=0: shared memory
-  const int lg = lists_in_smem && env_int("RS_LISTS_GLOBAL", 1) != 0 ? 1 : 0;
+  const int lg = lists_in_smem && o.lists_global != 0 ? 1 : 0;
+  const int qstages = o.qstages > 0 ? o.qstages : 2 * terms;
+  pl->qstages = qstages;
   long long best_cost = -1;
   for (int resident = 1; resident >= 0; --resident) {
-    if (force_res >= 0 && resident != force_res) continue;
+    if (o.qresident >= 0 && resident != o.qresident) continue;
     for (int cps = 4; cps >= 1; cps >>= 1) {
-      if (ix->kc % cps != 0 || (force_cps && cps != force_cps)) continue;
+      if (ix->kc % cps != 0 || (o.cps && cps != o.cps)) continue;
       if (!resident && cps == 4) continue;
-      for (int sub = resident ? (force_sub ? force_sub : 1) : (nacc == 1 ? 4 : 2); sub >= 1; sub >>= 1) {
-        if (force_sub && sub != force_sub) continue;
+      for (int sub = resident ? (o.sub ? o.sub : 1) : (nacc == 1 ? 4 : 2); sub >= 1; sub >>= 1) {
+        if (o.sub && sub != o.sub) continue;
         // k > 16 only: a 16-entry candidate buffer (twice the flushes) and a 48 KiB ring are accepted
         // when they save a whole pass over the shard
         for (int bufc = 32; bufc >= (lists_in_smem ? 16 : 32); bufc >>= 1) {
-          if (force_bufc && bufc != force_bufc) continue;
+          if (o.bufc && bufc != o.bufc) continue;
           for (int lean = 0; lean <= (lists_in_smem ? 1 : 0); ++lean) {
-            if (force_lean >= 0 && lean != force_lean) continue;
+            if (o.lean >= 0 && lean != o.lean) continue;
             // ring depth: at least 64 KiB in flight (48 KiB when lean), and in streamed mode one whole
             // k-chunk group + 1
             int need = std::max(2, ((lean ? 3 : 4) + cps - 1) / cps);
             if (!resident) need = std::max(need, ix->planes * sub + 1);
-            const int cap = max_cap_rows(ix->kc, terms, k, need, cps, resident, bufc, lg);
+            const int cap = max_cap_rows(ix->kc, terms, k, need, cps, resident, qstages, bufc, lg);
             if (cap <= 0) continue;
             const int passes = (B + cap - 1) / cap;
             const long long cost = ((long long)passes << 32) | ((long long)(1 - resident) << 28) |
@@ -238,19 +252,19 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
   // That halves the resident image (128 -> 64 KiB at B=32, D=1024) in favour of the document ring.  Measured on
   // 1M x 1024 fp32: 0.775 -> 0.738 ms at B=32, but 0.665 -> 0.736 ms at B=16 and 0.625 -> 0.709 ms at B=1 (smaller
   // ring stages, one more launch), so it stays an opt-in.
-  if (pl->q_resident == 1 && terms == 2 && env_int("RS_QLO_STREAM", 0) != 0 && force_res != 1 &&
-      ((size_t)ix->corpus_bytes >= ((size_t)256 << 20) || env_int("RS_QLO_STREAM", 0) == 2)) {  // 2: force (tests)
+  if (pl->q_resident == 1 && terms == 2 && o.qlo_stream != 0 && o.qresident != 1 &&
+      ((size_t)ix->corpus_bytes >= ((size_t)256 << 20) || o.qlo_stream == 2)) {  // 2: force (tests)
     auto ring_bytes = [&](int mode, int cps) {
       int st = std::max(2, (4 + cps - 1) / cps);
-      if (rs::fused_smem_bytes(pl->bpad, ix->kc, terms, st, cps, k, mode, 2 * terms, pl->bufc, pl->lg) > kMaxSmem) return 0;
+      if (rs::fused_smem_bytes(pl->bpad, ix->kc, terms, st, cps, k, mode, qstages, pl->bufc, pl->lg) > kMaxSmem) return 0;
       while (st < kMaxStages &&
-             rs::fused_smem_bytes(pl->bpad, ix->kc, terms, st + 1, cps, k, mode, 2 * terms, pl->bufc, pl->lg) <= kMaxSmem)
+             rs::fused_smem_bytes(pl->bpad, ix->kc, terms, st + 1, cps, k, mode, qstages, pl->bufc, pl->lg) <= kMaxSmem)
         ++st;
       return st * cps * RS_BLOCK_BYTES;
     };
     const int have = ring_bytes(1, pl->cps);
     for (int cps = 4; cps >= 1; cps >>= 1) {
-      if (ix->kc % cps != 0 || (force_cps && cps != force_cps)) continue;
+      if (ix->kc % cps != 0 || (o.cps && cps != o.cps)) continue;
       const int got = ring_bytes(2, cps);
       if (got > have) {
         pl->q_resident = 2;
@@ -260,16 +274,16 @@ int make_plan(const rs_index* ix, int B, int k, int terms, Plan* pl) {
       }
     }
   }
-  pl->mma_m = env_int("RS_MMA_M", pl->bpad <= 64 ? 64 : 128);
+  pl->mma_m = o.mma_m ? o.mma_m : (pl->bpad <= 64 ? 64 : 128);
   if (pl->mma_m != 128 && !(pl->mma_m == 64 && pl->bpad <= 64)) return fail(RS_E_INVALID, "RS_MMA_M=%d invalid for bpad=%d", pl->mma_m, pl->bpad);
   // as many accumulator buffers as the 512 TMEM columns hold: the epilogue's start-up burst (every
   // score beats an empty list) then stalls the MMA/TMA pipeline less
-  pl->nbuf = env_int("RS_NBUF", std::max(1, 4 / (pl->sub * nacc)));
+  pl->nbuf = o.nbuf ? o.nbuf : std::max(1, 4 / (pl->sub * nacc));
   const int cols = pl->sub * pl->nbuf * nacc;
   if (pl->nbuf < 1 || pl->nbuf > 4 || (cols != 1 && cols != 2 && cols != 4))
     return fail(RS_E_INVALID, "sub=%d nbuf=%d nacc=%d does not map onto 128/256/512 TMEM columns", pl->sub, pl->nbuf, nacc);
   auto bytes = [&](int stages) {
-    return rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages, pl->cps, k, pl->q_resident, 2 * terms, pl->bufc, pl->lg);
+    return rs::fused_smem_bytes(pl->bpad, ix->kc, terms, stages, pl->cps, k, pl->q_resident, qstages, pl->bufc, pl->lg);
   };
   while (pl->stages < kMaxStages && bytes(pl->stages + 1) <= kMaxSmem) ++pl->stages;
   if (bytes(pl->stages) > kMaxSmem) return fail(RS_E_UNSUPPORTED, "B=%d k=%d does not fit in shared memory", B, k);
@@ -302,12 +316,41 @@ void free_all(rs_index* ix) {
     if (ix->ev_beg[i]) cudaEventDestroy(ix->ev_beg[i]);
     if (ix->ev_end[i]) cudaEventDestroy(ix->ev_end[i]);
   }
+  if (ix->order_ev) cudaEventDestroy(ix->order_ev);
   if (ix->stream) cudaStreamDestroy(ix->stream);
+}
+
+void drop_graphs(rs_index* ix) {  // the corpus changed: cached launch sequences are stale
+  for (auto& g : ix->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  ix->graphs.clear();
+}
+
+// A kernel raised the mapped error word (a wait timed out): clear it, reset the counters and fail.
+int take_device_error(rs_index* ix, cudaStream_t stream) {
+  const unsigned int e = *reinterpret_cast<volatile unsigned int*>(ix->err_flag);
+  if (!e) return RS_OK;
+  *ix->err_flag = 0;
+  cudaMemsetAsync(ix->sync, 0, 512, stream);
+  return fail(RS_E_CUDA, e == 2u ? "a search timed out waiting for a peer GPU's candidates (peer stalled or out of step); results are invalid"
+                                 : "a search timed out waiting for its own CTAs (device shared with another job?); results are invalid");
+}
+
+// The workspaces are per index, not per stream: order this search after the previous one when the stream changed.
+int order_after_previous(rs_index* ix, cudaStream_t stream) {
+  if (ix->have_last && ix->last_stream != stream) {
+    RS_CUDA(cudaEventRecord(ix->order_ev, ix->last_stream));
+    RS_CUDA(cudaStreamWaitEvent(stream, ix->order_ev, 0));
+  }
+  ix->last_stream = stream;
+  ix->have_last = true;
+  return RS_OK;
 }
 
 // one search on device buffers; all launches go to `stream`
 int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int metric, int terms, long long* out_idx,
-                         float* out_score, cudaStream_t stream, rs_xchg* xg = nullptr, bool deferred = false) {
+                         float* out_score, cudaStream_t stream, rs_xchg* xg = nullptr) {
+  const Options& o = ix->opt;
   if (!ix->finalized) return fail(RS_E_STATE, "rs_finalize has not been called");
   if (B <= 0 || B > ix->cfg.max_batch) return fail(RS_E_INVALID, "B=%d outside [1,%d]", B, ix->cfg.max_batch);
   if (k <= 0 || k > ix->cfg.max_k) return fail(RS_E_INVALID, "k=%d outside [1,%d]", k, ix->cfg.max_k);
@@ -315,55 +358,50 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   if (ix->planes == 2) terms = 2;
   if (terms != 1 && terms != 2) return fail(RS_E_INVALID, "query_terms must be 1 or 2");
   Plan pl;
-  int rc = make_plan(ix, B, k, terms, &pl);
+  int rc = make_plan(ix, o, B, k, terms, &pl);
   if (rc != RS_OK) return rc;
-  if (*reinterpret_cast<volatile unsigned int*>(ix->err_flag)) {
-    *ix->err_flag = 0;
-    cudaMemsetAsync(ix->sync, 0, 256, stream);
-    return fail(RS_E_CUDA, "a previous search timed out waiting for its own CTAs (device shared with another job?)");
+  if (!ix->capturing) {
+    rc = take_device_error(ix, stream);  // raised by an earlier device-buffer search (rs_check reads it sooner)
+    if (rc != RS_OK) return rc;
+    rc = order_after_previous(ix, stream);
+    if (rc != RS_OK) return rc;
   }
   // doc-major kernel variant (documents on the MMA's M): half the tensor work and a quarter of the Q-operand reads
   // at B=32; for B <= 32, k <= 16, resident Q (RS_DOCM=0: off; RS_DOCM=2: only one-term 16-bit searches)
-  const bool docm = pl.q_resident == 1 && (env_int("RS_DOCM", 1) == 1 ? true : (terms == 1 && ix->planes == 1)) &&
-                    k <= rs::fused_reg_k() && pl.bpad <= 32 &&
-                    pl.sub == 1 && env_int("RS_DOCM", 1) != 0 &&
-                    rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, 1, 2 * terms, pl.bufc, pl.lg, 1) <= kMaxSmem;
+  const bool docm = pl.q_resident == 1 && (o.docm == 1 ? true : (terms == 1 && ix->planes == 1)) &&
+                    k <= rs::fused_reg_k() && pl.bpad <= 32 && pl.sub == 1 && o.docm != 0 &&
+                    rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, 1, pl.qstages, pl.bufc, pl.lg, 1) <= kMaxSmem;
   if (docm) pl.nbuf = 8;
   const int n_work = std::min(ix->sm_count, ix->n_tiles);  // CTAs that own tiles = candidate lists per query
   // single-launch search (default): query prep in the fused kernel's prologue (resident-Q plans) and the
   // candidate merge (+ exchange) in its tail.  RS_INLINE_PREP=0 / RS_FUSED_TAIL=0 fall back to the
   // separate query_prep_kernel / merge kernels.
-  const bool inline_prep = pl.q_resident == 1 && ix->cfg.dim <= 1024 && pl.bpad <= 32 && env_int("RS_INLINE_PREP", 1) != 0;
-  const int tail_cap = rs::fused_tail_smem_capacity(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms);
-  const bool fused_tail = env_int("RS_FUSED_TAIL", 1) != 0 &&
-                          rs::fused_tail_smem_bytes(n_work, k, xg ? xg->world : 1) <= (size_t)tail_cap;
-  // deferred exchange: this launch pushes its rows and final-merges the pending search; anything that cannot
-  // do both in the fused tail flushes the pending search with a kernel of its own and runs synchronously
-  const bool defer = deferred && xg && fused_tail && pl.passes == 1;
-  if (xg && xg->pending.valid &&
-      (!defer || rs::fused_tail_smem_bytes(1, xg->pending.k, xg->world) > (size_t)tail_cap)) {
-    rc = flush_pending(xg, stream);
-    if (rc != RS_OK) return rc;
-  }
-  const int merge_ctas = std::max(pl.per_pass, (defer && xg->pending.valid) ? xg->pending.B : 0);
-  const int grid = fused_tail ? std::max(n_work, std::min(merge_ctas, ix->sm_count)) : n_work;
+  const bool inline_prep = pl.q_resident == 1 && ix->cfg.dim <= 1024 && pl.bpad <= 32 && o.inline_prep != 0;
+  const int tail_cap = rs::fused_tail_smem_capacity(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, pl.qstages);
+  const bool fused_tail = o.fused_tail != 0 && rs::fused_tail_smem_bytes(n_work, k, xg ? xg->world : 1) <= (size_t)tail_cap;
+  const int grid = fused_tail ? std::max(n_work, std::min(pl.per_pass, ix->sm_count)) : n_work;
+  // overlapped launches (RS_OVERLAP=1): the scan of this search may run while the previous search's tail drains.
+  // Only for plans that touch no shared workspace before the tail (register lists, Q image built in shared memory).
+  const bool pdl = o.overlap != 0 && !ix->capturing && inline_prep && fused_tail && pl.passes == 1 &&
+                   k <= rs::fused_reg_k() && !o.debug_ts;
+  const bool shared_bound = k > rs::fused_reg_k() && n_work >= k && o.shared_bound != 0;
   ix->stats.grid = grid;
   ix->stats.stages = pl.stages;
-  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, 2 * terms, pl.bufc, pl.lg, docm);
+  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, pl.qstages, pl.bufc, pl.lg, docm);
   ix->stats.q_resident = pl.q_resident;
   ix->stats.sub = pl.sub;
   ix->stats.nbuf = pl.nbuf;
   ix->stats.mma_m = pl.mma_m;
+  ix->stats.overlapped = pdl ? 1 : 0;
+  ix->stats.doc_major = docm ? 1 : 0;
   ix->stats.passes = pl.passes;
   ix->stats.query_terms = terms;
   ix->stats.launches = 0;
   ix->stats.bytes_streamed = 0;
-  unsigned int epoch = 0;
   if (xg) {
     if (B > xg->max_batch || k > xg->max_k) return fail(RS_E_INVALID, "B=%d k=%d exceed the exchange buffer (%d, %d)", B, k, xg->max_batch, xg->max_k);
     for (int g = 0; g < xg->world; ++g)
       if (!xg->peer[g]) return fail(RS_E_STATE, "exchange buffer of rank %d has not been imported", g);
-    epoch = ++xg->epoch;
   }
   for (int pass = 0; pass < pl.passes; ++pass) {
     const int b0 = pass * pl.per_pass;
@@ -379,19 +417,21 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.corpus_scale_exp = corpus_scale_exp;
     p.n_work = n_work;
     p.tail_mode = fused_tail ? (xg ? 2 : 1) : 0;
-    p.sync = ix->sync;
-    p.dyn_sched = env_int("RS_DYN_SCHED", 1) != 0 ? 1 : 0;
-    if (p.dyn_sched && !fused_tail) RS_CUDA(cudaMemsetAsync(ix->sync + 4, 0, sizeof(unsigned int), stream));  // the tail resets it otherwise
+    p.pdl = pdl ? 1 : 0;
+    ix->launch_parity ^= 1u;
+    p.sync = ix->sync + 64 * ix->launch_parity;
+    p.dyn_sched = o.dyn_sched != 0 ? 1 : 0;
+    if (p.dyn_sched && !fused_tail) RS_CUDA(cudaMemsetAsync(p.sync + 4, 0, sizeof(unsigned int), stream));  // the tail resets it otherwise
     p.err_flag = ix->err_flag;
     p.out_score = out_score + (size_t)b0 * k;
     p.out_idx = out_idx + (size_t)b0 * k;
     p.idx_offset = ix->cfg.row_offset;
-    if (k > rs::fused_reg_k() && n_work >= k && env_int("RS_SHARED_BOUND", 1) != 0) {
+    if (shared_bound) {
       // 0xff bytes = NaN = "this CTA has not published a score for this query yet"
       RS_CUDA(cudaMemsetAsync(ix->g_best, 0xff, (size_t)n_work * pl.bpad * sizeof(float), stream));
       p.g_best = ix->g_best;
     }
-    if (env_int("RS_DEBUG_TS", 0)) {
+    if (o.debug_ts) {
       if (!ix->debug_ts) RS_CUDA(cudaMalloc(&ix->debug_ts, (size_t)ix->sm_count * 8 * sizeof(unsigned long long)));
       RS_CUDA(cudaMemsetAsync(ix->debug_ts, 0, (size_t)ix->sm_count * 8 * sizeof(unsigned long long), stream));
       p.debug_ts = ix->debug_ts;
@@ -419,26 +459,19 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.bufc = pl.bufc;
     p.lists_global = pl.lg;
     p.docm = docm ? 1 : 0;
-    p.qstages = 2 * terms;
+    p.qstages = pl.qstages;
     p.q_resident = pl.q_resident;
     p.sub = pl.sub;
     p.nbuf = pl.nbuf;
     p.mma_m = pl.mma_m;
-    p.debug_flags = env_int("RS_DEBUG_FLAGS", 0);
+    p.debug_flags = o.debug_flags;
     p.lo_coef = ix->plane_dtype == RS_DTYPE_FP16 ? ldexpf(1.0f, -RS_FP16_SPLIT_SHIFT) : 1.0f;
     rs::ExchangeArgs ea;
     memset(&ea, 0, sizeof(ea));
-    if (xg) ea = make_exchange_args(xg, epoch, B, k, b0, out_idx, out_score);
-    if (defer) {
-      // this launch pushes the rows of search `epoch` and final-merges the pending one
-      p.tail_mode = 3;
-      memset(&p.xp, 0, sizeof(p.xp));
-      if (xg->pending.valid)
-        p.xp = make_exchange_args(xg, xg->pending.epoch, xg->pending.B, xg->pending.k, 0, xg->pending.out_idx,
-                                  xg->pending.out_score);
-    }
+    if (xg) ea = make_exchange_args(xg, b0, pass == pl.passes - 1);
     p.x = ea;
-    if (!ix->record_events || env_int("RS_NO_EVENTS", 0)) {
+    // events around the launch would sit between two overlapped kernels and serialise them: not in that mode
+    if (ix->capturing || o.no_events || pdl) {
       RS_CUDA(rs::launch_fused_search(p, grid, stream));
     } else {
       const int slot = (int)(ix->ev_count % rs_index::kEventRing);
@@ -454,21 +487,84 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
       } else {
         // local merge + exchange + final merge in one kernel: rows go straight into every GPU's buffer
         RS_CUDA(rs::launch_exchange_merge(ix->cand_score, ix->cand_idx, n_work, nb, k, ix->cfg.row_offset,
-                                          out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, ea, stream));
+                                          out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, ea, ix->err_flag, stream));
       }
-    }
-    if (defer) {
-      xg->pending.valid = true;
-      xg->pending.epoch = epoch;
-      xg->pending.B = B;
-      xg->pending.k = k;
-      xg->pending.out_idx = out_idx;
-      xg->pending.out_score = out_score;
     }
     ix->stats.launches += 1 + (inline_prep ? 0 : 1) + (fused_tail ? 0 : 1);
     ix->stats.bytes_streamed += (int64_t)ix->corpus_bytes;
   }
   ix->stats.total_launches += ix->stats.launches;
+  return RS_OK;
+}
+
+// Host-buffer search on ix->stream: pinned H2D of the queries -> search -> ONE D2H of [indices][scores]; from the
+// second call of a shape on, the sequence is replayed from a captured CUDA graph.  out_idx == nullptr: this caller
+// does not need the result on the host (a non-root rank of a sharded search): no D2H, but still synchronous.
+int search_host_locked(rs_index* ix, rs_xchg* xg, const float* q_host, int B, int k, int metric, int terms,
+                       long long* out_idx, float* out_score) {
+  if (B <= 0 || B > ix->cfg.max_batch) return fail(RS_E_INVALID, "B=%d outside [1,%d]", B, ix->cfg.max_batch);
+  if (k <= 0 || k > ix->cfg.max_k) return fail(RS_E_INVALID, "k=%d outside [1,%d]", k, ix->cfg.max_k);
+  if (!ix->finalized) return fail(RS_E_STATE, "rs_finalize has not been called");
+  const size_t q_bytes = (size_t)B * ix->cfg.dim * sizeof(float);
+  const size_t n_out = (size_t)B * k;
+  char* pin = static_cast<char*>(ix->pinned);
+  long long* pin_idx = reinterpret_cast<long long*>(pin + ((q_bytes + 255) & ~size_t(255)));
+  float* pin_score = reinterpret_cast<float*>(pin_idx + n_out);
+  const int want_out = out_idx != nullptr ? 1 : 0;
+  if (ix->planes == 2) terms = 2;
+  auto enqueue = [&]() -> int {  // H2D -> (prep ->) fused (-> merge) -> D2H, all on ix->stream
+    RS_CUDA(cudaMemcpyAsync(ix->q_dev, pin, q_bytes, cudaMemcpyHostToDevice, ix->stream));
+    float* score_dev = reinterpret_cast<float*>(ix->out_idx_dev + n_out);  // right behind this call's indices
+    int rc = search_device_locked(ix, ix->q_dev, B, k, metric, terms, ix->out_idx_dev, score_dev, ix->stream, xg);
+    if (rc != RS_OK) return rc;
+    if (want_out)
+      RS_CUDA(cudaMemcpyAsync(pin_idx, ix->out_idx_dev, n_out * (sizeof(long long) + sizeof(float)), cudaMemcpyDeviceToHost,
+                              ix->stream));  // pin_score == pin_idx + n_out
+    return RS_OK;
+  };
+  int rc = take_device_error(ix, ix->stream);
+  if (rc != RS_OK) return rc;
+  rc = order_after_previous(ix, ix->stream);
+  if (rc != RS_OK) return rc;
+  memcpy(pin, q_host, q_bytes);
+  rs_index::GraphEntry* ge = nullptr;
+  if (ix->opt.graph) {
+    for (auto& g : ix->graphs)
+      if (g.B == B && g.k == k && g.metric == metric && g.terms == terms && g.xg == xg && g.want_out == want_out) ge = &g;
+    if (!ge && ix->graphs.size() < 64) {
+      ix->graphs.push_back({B, k, metric, terms, 0, xg, want_out, nullptr});
+      ge = &ix->graphs.back();
+    }
+  }
+  if (ge && !ge->exec && ge->uses >= 1) {
+    // second call with this shape: capture the sequence (the first, eager call set the kernels'
+    // shared-memory attributes and validated the arguments)
+    ix->capturing = true;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(ix->stream, cudaStreamCaptureModeThreadLocal);
+    int crc = ce == cudaSuccess ? enqueue() : RS_E_CUDA;
+    cudaError_t ee = cudaStreamEndCapture(ix->stream, &graph);
+    ix->capturing = false;
+    if (crc == RS_OK && ee == cudaSuccess && graph && cudaGraphInstantiate(&ge->exec, graph, 0) != cudaSuccess) ge->exec = nullptr;
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (!ge->exec) ge->uses = -1000000;  // capture not possible here: stay on the eager path
+  }
+  if (ge && ge->exec) {
+    RS_CUDA(cudaGraphLaunch(ge->exec, ix->stream));
+    ix->stats.total_launches += ix->stats.launches;
+  } else {
+    rc = enqueue();
+    if (rc != RS_OK) return rc;
+    if (ge) ++ge->uses;
+  }
+  RS_CUDA(cudaStreamSynchronize(ix->stream));
+  rc = take_device_error(ix, ix->stream);  // THIS call's result is invalid if a wait timed out
+  if (rc != RS_OK) return rc;
+  if (want_out) {
+    memcpy(out_idx, pin_idx, n_out * sizeof(long long));
+    memcpy(out_score, pin_score, n_out * sizeof(float));
+  }
   return RS_OK;
 }
 
@@ -502,6 +598,7 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   rs_index* ix = new (std::nothrow) rs_index();
   if (!ix) return fail(RS_E_INVALID, "out of host memory");
   ix->cfg = *cfg;
+  ix->opt = options_from_env();
   ix->sm_count = prop.multiProcessorCount;
   ix->kc = cfg->dim / RS_KCHUNK_ELEMS;
   ix->planes = cfg->dtype == RS_DTYPE_FP32 ? 2 : 1;
@@ -515,7 +612,7 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   ix->stats.corpus_bytes = (int64_t)ix->corpus_bytes;
 
   const int grid = std::min(ix->sm_count, ix->n_tiles);
-  const int cap1 = max_cap_rows(ix->kc, 1, 1, 3, 1, 0);
+  const int cap1 = max_cap_rows(ix->kc, 1, 1, 3, 1, 0, 2);
   if (cap1 <= 0) {
     delete ix;
     return fail(RS_E_UNSUPPORTED, "dim=%d does not fit the shared-memory pipeline", cfg->dim);
@@ -554,10 +651,11 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   // host-buffer searches write [indices int64][scores float] back to back so ONE copy brings both home
   RS_ALLOC(cudaMalloc(&ix->out_idx_dev, out_elems * (sizeof(long long) + sizeof(float))));
   RS_ALLOC(cudaMalloc(&ix->ingest_dev, kIngestChunkBytes));
-  RS_ALLOC(cudaMallocHost(&ix->pinned, ix->pinned_bytes));
+  RS_ALLOC(cudaHostAlloc(&ix->pinned, ix->pinned_bytes, cudaHostAllocPortable));
   RS_ALLOC(cudaMalloc(&ix->g_best, (size_t)prop.multiProcessorCount * 128 * sizeof(float)));
-  RS_ALLOC(cudaMalloc(&ix->sync, 256));
-  RS_ALLOC(cudaMemsetAsync(ix->sync, 0, 256, ix->stream));
+  RS_ALLOC(cudaMalloc(&ix->sync, 512));
+  RS_ALLOC(cudaMemsetAsync(ix->sync, 0, 512, ix->stream));
+  RS_ALLOC(cudaEventCreateWithFlags(&ix->order_ev, cudaEventDisableTiming));
   RS_ALLOC(cudaHostAlloc(&ix->err_flag, 64, cudaHostAllocMapped));
   *ix->err_flag = 0;
   for (int i = 0; i < 2; ++i) RS_ALLOC(cudaEventCreateWithFlags(&ix->ingest_done[i], cudaEventDisableTiming));
@@ -625,6 +723,7 @@ RS_API int rs_load_rows(rs_index* ix, const void* host_rows, int32_t src_dtype, 
     }
     RS_CUDA(cudaStreamSynchronize(ix->stream));
     ix->finalized = false;
+    drop_graphs(ix);
     return RS_OK;
   }
   const bool src_pinned = attr.type == cudaMemoryTypeHost;
@@ -651,6 +750,7 @@ RS_API int rs_load_rows(rs_index* ix, const void* host_rows, int32_t src_dtype, 
   }
   RS_CUDA(cudaStreamSynchronize(ix->stream));
   ix->finalized = false;
+  drop_graphs(ix);
   return RS_OK;
 }
 
@@ -667,6 +767,7 @@ RS_API int rs_fill_synthetic(rs_index* ix, uint64_t seed, int64_t global_row0) {
   }
   RS_CUDA(cudaStreamSynchronize(ix->stream));
   ix->finalized = false;
+  drop_graphs(ix);
   return RS_OK;
 }
 
@@ -695,59 +796,27 @@ RS_API int rs_search(rs_index* ix, const float* q_host, int32_t B, int32_t k, in
   if (!ix || !q_host || !out_idx || !out_score) return fail(RS_E_INVALID, "null argument");
   std::lock_guard<std::mutex> lock(ix->mu);
   RS_CUDA(cudaSetDevice(ix->cfg.device));
-  if (B <= 0 || B > ix->cfg.max_batch) return fail(RS_E_INVALID, "B=%d outside [1,%d]", B, ix->cfg.max_batch);
-  if (k <= 0 || k > ix->cfg.max_k) return fail(RS_E_INVALID, "k=%d outside [1,%d]", k, ix->cfg.max_k);
-  const size_t q_bytes = (size_t)B * ix->cfg.dim * sizeof(float);
-  const size_t n_out = (size_t)B * k;
-  char* pin = static_cast<char*>(ix->pinned);
-  long long* pin_idx = reinterpret_cast<long long*>(pin + ((q_bytes + 255) & ~size_t(255)));
-  float* pin_score = reinterpret_cast<float*>(pin_idx + n_out);
-  if (ix->planes == 2) query_terms = 2;
-  auto enqueue = [&]() -> int {  // H2D -> prep -> fused -> merge -> D2H, all on ix->stream
-    RS_CUDA(cudaMemcpyAsync(ix->q_dev, pin, q_bytes, cudaMemcpyHostToDevice, ix->stream));
-    float* score_dev = reinterpret_cast<float*>(ix->out_idx_dev + n_out);  // right behind this call's indices
-    int rc = search_device_locked(ix, ix->q_dev, B, k, metric, query_terms, ix->out_idx_dev, score_dev, ix->stream);
-    if (rc != RS_OK) return rc;
-    RS_CUDA(cudaMemcpyAsync(pin_idx, ix->out_idx_dev, n_out * (sizeof(long long) + sizeof(float)), cudaMemcpyDeviceToHost,
-                            ix->stream));  // pin_score == pin_idx + n_out
-    return RS_OK;
-  };
-  memcpy(pin, q_host, q_bytes);
-  rs_index::GraphEntry* ge = nullptr;
-  if (env_int("RS_GRAPH", 1)) {
-    for (auto& g : ix->graphs)
-      if (g.B == B && g.k == k && g.metric == metric && g.terms == query_terms) ge = &g;
-    if (!ge && ix->graphs.size() < 64) {
-      ix->graphs.push_back({B, k, metric, query_terms, 0, nullptr});
-      ge = &ix->graphs.back();
+  return search_host_locked(ix, nullptr, q_host, B, k, metric, query_terms, reinterpret_cast<long long*>(out_idx), out_score);
+}
+
+RS_API int rs_check(rs_index* ix) {
+  if (!ix) return fail(RS_E_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  return take_device_error(ix, ix->have_last ? ix->last_stream : ix->stream);
+}
+
+RS_API int rs_set_option(rs_index* ix, const char* name, int32_t value) {
+  if (!ix || !name) return fail(RS_E_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  for (const OptDef& d : kOptDefs)
+    if (strcmp(d.name, name) == 0) {
+      ix->opt.*(d.field) = value;
+      RS_CUDA(cudaSetDevice(ix->cfg.device));
+      drop_graphs(ix);  // captured launch sequences were planned with the old value
+      return RS_OK;
     }
-  }
-  if (ge && !ge->exec && ge->uses >= 1) {
-    // second call with this shape: capture the sequence (the first, eager call set the kernels'
-    // shared-memory attributes and validated the arguments)
-    ix->record_events = false;
-    cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamBeginCapture(ix->stream, cudaStreamCaptureModeThreadLocal);
-    int rc = ce == cudaSuccess ? enqueue() : RS_E_CUDA;
-    cudaError_t ee = cudaStreamEndCapture(ix->stream, &graph);
-    ix->record_events = true;
-    if (rc == RS_OK && ee == cudaSuccess && graph && cudaGraphInstantiate(&ge->exec, graph, 0) != cudaSuccess) ge->exec = nullptr;
-    if (graph) cudaGraphDestroy(graph);
-    cudaGetLastError();
-    if (!ge->exec) ge->uses = -1000000;  // capture not possible here: stay on the eager path
-  }
-  if (ge && ge->exec) {
-    RS_CUDA(cudaGraphLaunch(ge->exec, ix->stream));
-    ix->stats.total_launches += ix->stats.launches;
-  } else {
-    int rc = enqueue();
-    if (rc != RS_OK) return rc;
-    if (ge) ++ge->uses;
-  }
-  RS_CUDA(cudaStreamSynchronize(ix->stream));
-  memcpy(out_idx, pin_idx, n_out * sizeof(long long));
-  memcpy(out_score, pin_score, n_out * sizeof(float));
-  return RS_OK;
+  return fail(RS_E_INVALID, "unknown option %s", name);
 }
 
 RS_API int rs_merge_device(int32_t device, const float* scores_dev, const int64_t* idx_dev, int32_t n_lists, int32_t B,
@@ -778,12 +847,12 @@ RS_API int rs_xchg_create(int32_t device, int32_t world, int32_t rank, int32_t m
   x->rank = rank;
   x->max_batch = max_batch;
   x->max_k = max_k;
-  x->slot_bytes = (((size_t)max_batch * max_k * 12) + 255) & ~size_t(255);
-  x->parity_bytes = x->slot_bytes * world;
-  x->header_bytes = (((size_t)kXchgParities * rs::kMaxPeers * max_batch * sizeof(unsigned int)) + 255) & ~size_t(255);
-  x->total_bytes = x->header_bytes + kXchgParities * x->parity_bytes;
+  x->slot_entries = (((size_t)max_batch * max_k) + 15) & ~size_t(15);
+  x->total_bytes = kXchgHeaderBytes + 2 * x->slot_entries * world * sizeof(uint4);
   cudaError_t e = cudaMalloc(&x->local, x->total_bytes);
   if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->total_bytes);
+  const unsigned int one = 1u;  // epochs start at 1: zeroed entries never match
+  if (e == cudaSuccess) e = cudaMemcpy(x->local, &one, sizeof(one), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     cudaFree(x->local);
@@ -819,6 +888,25 @@ RS_API int rs_xchg_import(rs_xchg* x, int32_t peer_rank, const void* handle64) {
   return RS_OK;
 }
 
+RS_API int rs_xchg_attach(rs_xchg* x, rs_xchg* peer) {
+  if (!x || !peer) return fail(RS_E_INVALID, "null argument");
+  if (peer->world != x->world || peer->max_batch != x->max_batch || peer->max_k != x->max_k)
+    return fail(RS_E_INVALID, "exchange buffers of one group must share world, max_batch and max_k");
+  if (peer->rank == x->rank) return RS_OK;
+  RS_CUDA(cudaSetDevice(x->device));
+  if (peer->device != x->device) {
+    int can = 0;
+    RS_CUDA(cudaDeviceCanAccessPeer(&can, x->device, peer->device));
+    if (!can) return fail(RS_E_UNSUPPORTED, "device %d cannot access device %d's memory", x->device, peer->device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+      return fail(RS_E_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", peer->device, cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+  x->peer[peer->rank] = peer->local;
+  return RS_OK;
+}
+
 RS_API int rs_xchg_destroy(rs_xchg* x) {
   if (!x) return RS_OK;
   cudaSetDevice(x->device);
@@ -840,21 +928,177 @@ RS_API int rs_search_exchange(rs_index* ix, rs_xchg* x, const float* q_dev, int3
                               out_score_dev, static_cast<cudaStream_t>(stream), x);
 }
 
-RS_API int rs_search_exchange_async(rs_index* ix, rs_xchg* x, const float* q_dev, int32_t B, int32_t k, int32_t metric,
-                                    int32_t query_terms, int64_t* out_idx_dev, float* out_score_dev, void* stream) {
-  if (!ix || !x || !q_dev || !out_idx_dev || !out_score_dev) return fail(RS_E_INVALID, "null argument");
+RS_API int rs_search_exchange_host(rs_index* ix, rs_xchg* x, const float* q_host, int32_t B, int32_t k, int32_t metric,
+                                   int32_t query_terms, int64_t* out_idx, float* out_score) {
+  if (!ix || !x || !q_host || (out_idx == nullptr) != (out_score == nullptr)) return fail(RS_E_INVALID, "null argument");
   if (x->device != ix->cfg.device) return fail(RS_E_INVALID, "index and exchange buffer live on different devices");
   std::lock_guard<std::mutex> lock(ix->mu);
   RS_CUDA(cudaSetDevice(ix->cfg.device));
-  return search_device_locked(ix, q_dev, B, k, metric, query_terms, reinterpret_cast<long long*>(out_idx_dev),
-                              out_score_dev, static_cast<cudaStream_t>(stream), x, /*deferred=*/true);
+  return search_host_locked(ix, x, q_host, B, k, metric, query_terms, reinterpret_cast<long long*>(out_idx), out_score);
 }
 
-RS_API int rs_xchg_flush(rs_index* ix, rs_xchg* x, void* stream) {
-  if (!ix || !x) return fail(RS_E_INVALID, "null argument");
-  std::lock_guard<std::mutex> lock(ix->mu);
-  RS_CUDA(cudaSetDevice(ix->cfg.device));
-  return flush_pending(x, static_cast<cudaStream_t>(stream));
+// ---------------------------------------------------------------------------------------------------------
+// Single-process multi-GPU: what a service that constructs ONE retriever in ONE process gets (main.py:52-55).
+// The group owns one exchange buffer per shard (peer access inside the process) and drives every search from
+// the calling host thread: one pinned copy of the queries, an H2D + one fused kernel per GPU (the candidate
+// exchange and the final merge run inside those kernels, over NVLink), ONE D2H from the first GPU.  From the
+// second call of a shape on, the whole multi-device sequence is one captured CUDA graph = one launch call.
+// ---------------------------------------------------------------------------------------------------------
+struct rs_group {
+  int n = 0;
+  rs_index* ix[rs::kMaxPeers] = {};
+  rs_xchg* xg[rs::kMaxPeers] = {};
+  cudaEvent_t fork = nullptr, join[rs::kMaxPeers] = {};
+  struct GraphEntry {
+    int B, k, metric, terms, uses;
+    cudaGraphExec_t exec;
+  };
+  std::vector<GraphEntry> graphs;
+  int use_graph = 1;
+  std::mutex mu;
+};
+
+RS_API int rs_group_create(rs_index** shards, int32_t n, rs_group** out) {
+  if (!shards || !out) return fail(RS_E_INVALID, "null argument");
+  *out = nullptr;
+  if (n < 1 || n > rs::kMaxPeers) return fail(RS_E_INVALID, "a group holds 1..%d shards", rs::kMaxPeers);
+  for (int g = 0; g < n; ++g) {
+    if (!shards[g]) return fail(RS_E_INVALID, "null shard");
+    if (shards[g]->cfg.dim != shards[0]->cfg.dim || shards[g]->cfg.dtype != shards[0]->cfg.dtype ||
+        shards[g]->cfg.max_batch != shards[0]->cfg.max_batch || shards[g]->cfg.max_k != shards[0]->cfg.max_k)
+      return fail(RS_E_INVALID, "shards of one group must share dim, dtype, max_batch and max_k");
+    for (int h = 0; h < g; ++h)  // the in-kernel exchange needs every shard's grid resident at the same time
+      if (shards[h]->cfg.device == shards[g]->cfg.device) return fail(RS_E_INVALID, "two shards on device %d", shards[g]->cfg.device);
+  }
+  rs_group* gr = new (std::nothrow) rs_group();
+  if (!gr) return fail(RS_E_INVALID, "out of host memory");
+  gr->n = n;
+  gr->use_graph = shards[0]->opt.graph;
+  int rc = RS_OK;
+  for (int g = 0; g < n && rc == RS_OK; ++g) {
+    gr->ix[g] = shards[g];
+    rc = rs_xchg_create(shards[g]->cfg.device, n, g, shards[g]->cfg.max_batch, shards[g]->cfg.max_k, &gr->xg[g]);
+    if (rc == RS_OK && cudaEventCreateWithFlags(&gr->join[g], cudaEventDisableTiming) != cudaSuccess)
+      rc = fail(RS_E_CUDA, "event creation failed on device %d", shards[g]->cfg.device);
+  }
+  for (int g = 0; g < n && rc == RS_OK; ++g)
+    for (int h = 0; h < n && rc == RS_OK; ++h) rc = rs_xchg_attach(gr->xg[g], gr->xg[h]);
+  if (rc == RS_OK) {
+    cudaSetDevice(shards[0]->cfg.device);
+    if (cudaEventCreateWithFlags(&gr->fork, cudaEventDisableTiming) != cudaSuccess) rc = fail(RS_E_CUDA, "event creation failed");
+  }
+  if (rc != RS_OK) {
+    rs_group_destroy(gr);
+    return rc;
+  }
+  *out = gr;
+  return RS_OK;
+}
+
+RS_API int rs_group_destroy(rs_group* gr) {
+  if (!gr) return RS_OK;
+  for (auto& g : gr->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (int g = 0; g < gr->n; ++g) {
+    if (gr->ix[g]) {
+      cudaSetDevice(gr->ix[g]->cfg.device);
+      cudaDeviceSynchronize();
+    }
+  }
+  for (int g = 0; g < gr->n; ++g) {
+    if (gr->join[g]) cudaEventDestroy(gr->join[g]);
+    rs_xchg_destroy(gr->xg[g]);
+  }
+  if (gr->fork) cudaEventDestroy(gr->fork);
+  delete gr;
+  return RS_OK;
+}
+
+RS_API int rs_group_search(rs_group* gr, const float* q_host, int32_t B, int32_t k, int32_t metric, int32_t query_terms,
+                           int64_t* out_idx, float* out_score) {
+  if (!gr || !q_host || !out_idx || !out_score) return fail(RS_E_INVALID, "null argument");
+  std::lock_guard<std::mutex> glock(gr->mu);
+  std::unique_lock<std::mutex> locks[rs::kMaxPeers];
+  for (int g = 0; g < gr->n; ++g) locks[g] = std::unique_lock<std::mutex>(gr->ix[g]->mu);
+  rs_index* ix0 = gr->ix[0];
+  if (B <= 0 || B > ix0->cfg.max_batch) return fail(RS_E_INVALID, "B=%d outside [1,%d]", B, ix0->cfg.max_batch);
+  if (k <= 0 || k > ix0->cfg.max_k) return fail(RS_E_INVALID, "k=%d outside [1,%d]", k, ix0->cfg.max_k);
+  for (int g = 0; g < gr->n; ++g)
+    if (!gr->ix[g]->finalized) return fail(RS_E_STATE, "rs_finalize has not been called on shard %d", g);
+  if (ix0->planes == 2) query_terms = 2;
+  const size_t q_bytes = (size_t)B * ix0->cfg.dim * sizeof(float);
+  const size_t n_out = (size_t)B * k;
+  char* pin = static_cast<char*>(ix0->pinned);  // portable pinned memory: every GPU copies the queries from it
+  long long* pin_idx = reinterpret_cast<long long*>(pin + ((q_bytes + 255) & ~size_t(255)));
+  float* pin_score = reinterpret_cast<float*>(pin_idx + n_out);
+  cudaStream_t s0 = ix0->stream;
+  auto enqueue = [&]() -> int {
+    RS_CUDA(cudaSetDevice(ix0->cfg.device));
+    RS_CUDA(cudaEventRecord(gr->fork, s0));
+    for (int g = 0; g < gr->n; ++g) {
+      rs_index* ix = gr->ix[g];
+      RS_CUDA(cudaSetDevice(ix->cfg.device));
+      if (g > 0) RS_CUDA(cudaStreamWaitEvent(ix->stream, gr->fork, 0));
+      RS_CUDA(cudaMemcpyAsync(ix->q_dev, pin, q_bytes, cudaMemcpyHostToDevice, ix->stream));
+      float* score_dev = reinterpret_cast<float*>(ix->out_idx_dev + n_out);
+      int rc = search_device_locked(ix, ix->q_dev, B, k, metric, query_terms, ix->out_idx_dev, score_dev, ix->stream,
+                                    gr->n > 1 ? gr->xg[g] : nullptr);
+      if (rc != RS_OK) return rc;
+      if (g > 0) RS_CUDA(cudaEventRecord(gr->join[g], ix->stream));
+    }
+    RS_CUDA(cudaSetDevice(ix0->cfg.device));
+    for (int g = 1; g < gr->n; ++g) RS_CUDA(cudaStreamWaitEvent(s0, gr->join[g], 0));
+    RS_CUDA(cudaMemcpyAsync(pin_idx, ix0->out_idx_dev, n_out * (sizeof(long long) + sizeof(float)), cudaMemcpyDeviceToHost, s0));
+    return RS_OK;
+  };
+  for (int g = 0; g < gr->n; ++g) {
+    rs_index* ix = gr->ix[g];
+    RS_CUDA(cudaSetDevice(ix->cfg.device));
+    int rc = take_device_error(ix, ix->stream);
+    if (rc == RS_OK) rc = order_after_previous(ix, ix->stream);
+    if (rc != RS_OK) return rc;
+  }
+  memcpy(pin, q_host, q_bytes);
+  rs_group::GraphEntry* ge = nullptr;
+  if (gr->use_graph) {
+    for (auto& g : gr->graphs)
+      if (g.B == B && g.k == k && g.metric == metric && g.terms == query_terms) ge = &g;
+    if (!ge && gr->graphs.size() < 64) {
+      gr->graphs.push_back({B, k, metric, query_terms, 0, nullptr});
+      ge = &gr->graphs.back();
+    }
+  }
+  if (ge && !ge->exec && ge->uses >= 1) {
+    for (int g = 0; g < gr->n; ++g) gr->ix[g]->capturing = true;
+    cudaGraph_t graph = nullptr;
+    cudaSetDevice(ix0->cfg.device);
+    cudaError_t ce = cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal);
+    int crc = ce == cudaSuccess ? enqueue() : RS_E_CUDA;
+    cudaSetDevice(ix0->cfg.device);
+    cudaError_t ee = cudaStreamEndCapture(s0, &graph);
+    for (int g = 0; g < gr->n; ++g) gr->ix[g]->capturing = false;
+    if (crc == RS_OK && ee == cudaSuccess && graph && cudaGraphInstantiate(&ge->exec, graph, 0) != cudaSuccess) ge->exec = nullptr;
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (!ge->exec) ge->uses = -1000000;
+  }
+  RS_CUDA(cudaSetDevice(ix0->cfg.device));
+  if (ge && ge->exec) {
+    RS_CUDA(cudaGraphLaunch(ge->exec, s0));
+  } else {
+    int rc = enqueue();
+    if (rc != RS_OK) return rc;
+    if (ge) ++ge->uses;
+  }
+  RS_CUDA(cudaStreamSynchronize(s0));
+  for (int g = 0; g < gr->n; ++g) {
+    RS_CUDA(cudaSetDevice(gr->ix[g]->cfg.device));
+    int rc = take_device_error(gr->ix[g], gr->ix[g]->stream);
+    if (rc != RS_OK) return rc;
+  }
+  memcpy(out_idx, pin_idx, n_out * sizeof(long long));
+  memcpy(out_score, pin_score, n_out * sizeof(float));
+  return RS_OK;
 }
 
 RS_API int rs_get_rows(rs_index* ix, int64_t row0, int64_t nrows, float* out_host) {
@@ -871,6 +1115,21 @@ RS_API int rs_get_rows(rs_index* ix, int64_t row0, int64_t nrows, float* out_hos
     RS_CUDA(cudaMemcpyAsync(ix->pinned, ix->ingest_dev, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, ix->stream));
     RS_CUDA(cudaStreamSynchronize(ix->stream));
     memcpy(reinterpret_cast<char*>(out_host) + (size_t)r * row_bytes, ix->pinned, (size_t)n * row_bytes);
+    ix->stats.total_launches += 1;
+  }
+  return RS_OK;
+}
+
+RS_API int rs_get_rows_device(rs_index* ix, int64_t row0, int64_t nrows, float* out_dev, void* stream) {
+  if (!ix || !out_dev) return fail(RS_E_INVALID, "null argument");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > ix->cfg.n_rows) return fail(RS_E_INVALID, "row range out of bounds");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  const int64_t chunk_rows = 1 << 20;
+  for (int64_t r = 0; r < nrows; r += chunk_rows) {
+    const int64_t n = std::min(chunk_rows, nrows - r);
+    RS_CUDA(rs::launch_untile_rows(ix->corpus, row0 + r, (int)n, ix->cfg.dim, ix->cfg.dtype, ix->cfg.scale_exp,
+                                   out_dev + (size_t)r * ix->cfg.dim, static_cast<cudaStream_t>(stream)));
     ix->stats.total_launches += 1;
   }
   return RS_OK;
@@ -927,7 +1186,7 @@ RS_API int rs_debug_plan(int32_t dim, int32_t dtype, int32_t B, int32_t k, int32
   tmp.planes = dtype == RS_DTYPE_FP32 ? 2 : 1;
   if (tmp.planes == 2) query_terms = 2;
   Plan pl;
-  int rc = make_plan(&tmp, B, k, query_terms, &pl);
+  int rc = make_plan(&tmp, options_from_env(), B, k, query_terms, &pl);
   if (rc != RS_OK) return rc;
   const int v[9] = {pl.passes, pl.per_pass, pl.bpad, pl.stages, pl.q_resident, pl.sub, pl.nbuf, pl.mma_m, pl.cps};
   memcpy(out9, v, sizeof(v));

@@ -5,26 +5,24 @@
 
 namespace rs {
 
-// Arguments of the fused merge + exchange kernel (multi-GPU candidate exchange over peer memory).
+// Arguments of the in-kernel candidate exchange (multi-GPU, peer memory over NVLink).
+// Every GPU owns an exchange buffer of 16-byte entries {int64 global index, float score, uint32 epoch}:
+//   entries[parity][rank r][(q0 + q) * k + j]      parity = epoch & 1, one slot of slot_entries per rank
+// A rank stores its merged row of query q into ITS slot on every GPU with one 16-byte store per entry; the
+// epoch travels inside the entry, so there is no separate flag, no system-scope fence and no second round
+// trip: a reader polls the entry itself until it shows the search's epoch.
 constexpr int kMaxPeers = 8;
 struct ExchangeArgs {
   int world;                            // GPUs taking part
+  int rank;                             // this GPU
   int q0;                               // first query of this pass inside the search's batch
-  unsigned int epoch;                   // search counter; flags carry it
-  long long* dest_idx[kMaxPeers];       // GPU g: this rank's slot in g's exchange buffer, idx block  [B][k]
-  float* dest_score[kMaxPeers];         //        ... score block [B][k]
-  unsigned int* dest_flag[kMaxPeers];   // GPU g: flags[parity][this rank][0..max_batch)
-  const unsigned int* wait_flags;       // local flags[parity][0][0]; rank stride = flag_stride
-  int flag_stride;                      // = max_batch
-  const long long* local_idx;           // local exchange buffer, slot of rank 0 (idx block)
-  const float* local_score;             //                                      (score block)
-  long long idx_list_stride;            // elements between consecutive ranks' slots
-  long long score_list_stride;
-  // deferred mode: where the final rows of THIS search go once a later launch (or rs_xchg_flush) merges them
-  float* out_score;
-  long long* out_idx;
-  int n_queries;                        // queries of the search these arguments describe
-  int k;
+  int last_pass;                        // 1: the launch that completes the search bumps the epoch
+  unsigned int* epoch;                  // device words of the LOCAL buffer: [0] search counter (never 0; all ranks run
+                                        // in lockstep), [1] departures of the stand-alone exchange kernel
+  uint4* dest[kMaxPeers];               // GPU g: this rank's slot in g's buffer, parity 0 (peer pointer; dest[rank] local)
+  const uint4* local;                   // local buffer, slot of rank 0, parity 0
+  long long slot_entries;               // entries between consecutive ranks' slots
+  long long parity_entries;             // entries between the two parities
 };
 
 struct SearchParams {
@@ -63,16 +61,17 @@ struct SearchParams {
   int inline_prep;                   // 1: the CTA builds its own resident Q image (no query_prep_kernel launch)
   int corpus_scale_exp;              // power-of-two pre-scale of an fp32 corpus (folded into qscale)
   int n_work;                        // CTAs that own tiles and write candidate lists (= lists per query)
-  int tail_mode;                     // 0: candidates only; 1: + in-kernel merge; 2: + peer exchange and final merge;
-                                     // 3: deferred exchange - push this search's rows, final-merge the PREVIOUS search (xp)
-  unsigned int* sync;                // [0] arrivals of worker CTAs, [1] departures of merging CTAs, [4] next tile (dynamic scheduler)
+  int tail_mode;                     // 0: candidates only; 1: + in-kernel merge; 2: + peer exchange and final merge
+  int pdl;                           // launched with programmatic stream serialization: the scan may overlap the
+                                     // previous search's tail; shared workspaces are touched only after griddepcontrol.wait
+  unsigned int* sync;                // [0] arrivals of worker CTAs, [1] departures of merging CTAs, [4] next tile (dynamic
+                                     // scheduler); the host alternates between two such blocks from launch to launch
   int dyn_sched;                     // 1: supertiles after the first come from sync[4] (work stealing); 0: static round-robin
   unsigned int* err_flag;            // mapped host word, set to 1 if the arrival wait timed out
   float* out_score;                  // tail_mode != 0: final [n_queries][k]
   long long* out_idx;
   long long idx_offset;              // global index of this shard's row 0
-  ExchangeArgs x;                    // tail_mode >= 2
-  ExchangeArgs xp;                   // tail_mode == 3: the previous, still unmerged search (n_queries == 0: none)
+  ExchangeArgs x;                    // tail_mode == 2
   float* g_best;                     // k > 16: [n_work][bpad] best score seen per (CTA, query), NaN = none yet; null = off
   unsigned long long* debug_ts;      // null, or [grid][8] globaltimer stamps of the kernel's phases (RS_DEBUG_TS=1)
 };
@@ -89,8 +88,7 @@ cudaError_t launch_merge_i32(const float* cand_score, const int* cand_idx, int n
                              long long idx_offset, float* out_score, long long* out_idx, cudaStream_t stream);
 cudaError_t launch_exchange_merge(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int k,
                                   long long idx_offset, float* out_score, long long* out_idx, const ExchangeArgs& x,
-                                  cudaStream_t stream);
-cudaError_t launch_exchange_finalize(const ExchangeArgs& x, cudaStream_t stream);
+                                  unsigned int* err_flag, cudaStream_t stream);
 cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx, int n_lists, int n_queries, int kc,
                              int k, long long score_list_stride, long long idx_list_stride, float* out_score,
                              long long* out_idx, cudaStream_t stream);
@@ -98,6 +96,7 @@ cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx,
 // ingest (rs_ingest.cu)
 cudaError_t launch_tile_rows(const void* rows_dev, int src_dtype, long long row0, int nrows, int D, int dtype,
                              int scale_exp, uint8_t* corpus, float* dnorm, cudaStream_t stream);
+// out_rows_dev receives rows [row0, row0 + nrows) as float, row-major
 cudaError_t launch_untile_rows(const uint8_t* corpus, long long row0, int nrows, int D, int dtype, int scale_exp,
                                float* out_rows_dev, cudaStream_t stream);
 cudaError_t launch_synth_fill(unsigned long long seed, long long global_row0, long long local_row0, int nrows, int D,

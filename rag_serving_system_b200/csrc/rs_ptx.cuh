@@ -43,6 +43,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// no-ops unless the kernel was launched with cudaLaunchAttributeProgrammaticStreamSerialization
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- bulk async copy (TMA engine, 1-D)
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t pol;

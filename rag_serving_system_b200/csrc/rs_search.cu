@@ -15,8 +15,8 @@
 //                            query-major (everything else): queries are M (64 or 128 TMEM lanes, one per
 //                                        query), documents N = 128; a thread owns one query's top-k
 //   query_prep_kernel      stand-alone query prep (streamed-Q plans, B > 32, D > 1024, RS_INLINE_PREP=0)
-//   merge_local_kernel, exchange_merge_kernel, exchange_finalize_kernel, merge_topk_kernel
-//                          stand-alone merges: fallbacks of the tail, deferred-exchange flush, rs_merge_device
+//   merge_local_kernel, exchange_merge_kernel, merge_topk_kernel
+//                          stand-alone merges: fallbacks of the tail, rs_merge_device
 //
 // Query-major operand note: only Bpad A rows exist in shared memory; the remaining rows of the M=64/128
 // operand alias whatever follows in shared memory and produce garbage in TMEM lanes that are never read
@@ -703,53 +703,61 @@ __device__ __noinline__ void merge_query_local(const float* __restrict__ cand_sc
   __syncthreads();
 }
 
-// Candidate exchange + final merge of one query (multi-GPU): store the local row (m.res_*) into every
-// GPU's exchange buffer through peer pointers (NVLink), raise this rank's per-query flag there with
-// the search epoch, wait until every rank's flag for this query shows the epoch, then merge the
-// world lists from the local exchange buffer back into m.res_*.  A CTA only ever waits for the CTAs
-// of the same query on other GPUs.  Buffers are double-buffered by epoch parity (host side).
-// push: called by the whole CTA after the local merge left query q's row in m.res_*
-__device__ __forceinline__ void push_row(const ExchangeArgs& x, int q, int k, const MergeSmem& m) {
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x < 32) {
-    const size_t qg = (size_t)(x.q0 + q) * k;
-    for (int e = lane; e < k * x.world; e += 32) {
-      const int g = e / k, j = e - g * k;
-      x.dest_score[g][qg + j] = m.res_s[j];
-      x.dest_idx[g][qg + j] = m.res_i[j];
-    }
-    __threadfence_system();
-    __syncwarp();
-    if (lane < x.world) st_volatile_u32(x.dest_flag[lane] + x.q0 + q, x.epoch);
-  }
+// Candidate exchange + final merge of one query (multi-GPU).  The local row (m.res_*) is stored into this
+// rank's slot of EVERY GPU's exchange buffer through peer pointers (NVLink), one 16-byte entry
+// {index, score, epoch} per store; then the CTA polls the G x k entries of query q in its LOCAL buffer until
+// each shows this search's epoch, and merges the G world lists into m.res_*.  The epoch rides inside the
+// entry (a 16-byte store is one NVLink write, a 16-byte load one L2 sector read), so there is no flag, no
+// system-scope fence and no second round trip.  A CTA only ever waits for the CTAs of the same query on the
+// other GPUs.  Buffers are double-buffered by epoch parity (host side).  A peer that never shows up raises
+// err_flag (the host fails the call) and its slots are treated as empty.  Ends with a barrier.
+__device__ __forceinline__ void st_entry(uint4* p, long long idx, float sc, unsigned int epoch) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned int)((unsigned long long)idx & 0xffffffffull)),
+               "r"((unsigned int)((unsigned long long)idx >> 32)), "r"(__float_as_uint(sc)), "r"(epoch)
+               : "memory");
 }
-// finalize: wait until every rank's flag for query q shows x.epoch, then merge the world lists from the
-// local exchange buffer into m.res_*.  Ends with a barrier.
-__device__ __noinline__ void merge_world_lists(const float* __restrict__ local_score, const long long* __restrict__ local_idx,
-                                               long long score_list_stride, long long idx_list_stride, int world, size_t qoff,
-                                               int k, const MergeSmem m, int nthr);
-__device__ __forceinline__ void finalize_query(const ExchangeArgs& x, int q, int k, const MergeSmem& m, int nthr) {
-  if (threadIdx.x < x.world) {
-    long long spins = 0;
-    const unsigned int* f = x.wait_flags + (size_t)threadIdx.x * x.flag_stride + x.q0 + q;
-    while ((int)(ld_volatile_u32(f) - x.epoch) < 0 && ++spins < (1ll << 28)) {
-    }
-  }
-  __threadfence_system();
-  __syncthreads();
-  merge_world_lists(x.local_score, x.local_idx, x.score_list_stride, x.idx_list_stride, x.world, (size_t)(x.q0 + q) * k, k, m,
-                    nthr);
+__device__ __forceinline__ uint4 ld_entry(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
 }
-// merge of the G world lists of query q (already complete in the local exchange buffer) into m.res_*
-__device__ __noinline__ void merge_world_lists(const float* __restrict__ local_score, const long long* __restrict__ local_idx,
-                                               long long score_list_stride, long long idx_list_stride, int world, size_t qoff,
-                                               int k, const MergeSmem m, int nthr) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void bump_epoch(unsigned int* epoch) {  // never 0: zeroed buffers must not match
+  const unsigned int e = __ldcg(epoch) + 1u;
+  __stcg(epoch, e == 0u ? 1u : e);
+}
+__device__ __noinline__ void exchange_query(const ExchangeArgs& x, int q, int k, const MergeSmem m, int nthr,
+                                            unsigned int* err_flag) {
+  // the search counter lives in device memory (bumped by the last CTA of a search), so a captured CUDA graph
+  // can be replayed: nothing that changes from search to search is baked into the kernel arguments
+  const unsigned int epoch = __ldcg(x.epoch);
+  const size_t qe = (size_t)(epoch & 1u) * (size_t)x.parity_entries + (size_t)(x.q0 + q) * k;
+  const int total = k * x.world;
+  for (int e = threadIdx.x; e < total; e += nthr) {  // fan-out
+    const int g = e / k, j = e - g * k;
+    st_entry(x.dest[g] + qe + j, m.res_i[j], m.res_s[j], epoch);
+  }
   long long* s_idx = reinterpret_cast<long long*>(m.stage);
-  float* s_score = reinterpret_cast<float*>(m.stage + (size_t)world * k * sizeof(long long));
-  stage_lists<long long>(local_score, local_idx, world, k, score_list_stride, idx_list_stride, qoff, s_idx, s_score, nthr);
+  float* s_score = reinterpret_cast<float*>(m.stage + (size_t)total * sizeof(long long));
+  for (int e = threadIdx.x; e < total; e += nthr) {  // collect
+    const int r = e / k, j = e - r * k;
+    const uint4* src = x.local + (size_t)r * x.slot_entries + qe + j;
+    uint4 v = ld_entry(src);
+    long long spins = 0;
+    while (v.w != epoch) {
+      if (++spins > 64) __nanosleep(100);
+      if (spins > (1ll << 23)) {  // ~ seconds: the peer never pushed this search
+        *reinterpret_cast<volatile unsigned int*>(err_flag) = 2u;
+        v = make_uint4(0xffffffffu, 0xffffffffu, 0xff800000u, epoch);  // (-1, -inf)
+        break;
+      }
+      v = ld_entry(src);
+    }
+    s_idx[e] = (long long)(((unsigned long long)v.y << 32) | (unsigned long long)v.x);
+    s_score[e] = __uint_as_float(v.z);
+  }
+  __syncthreads();  // staged; every thread is done reading the local row out of m.res_*
+  const int world = x.world;
   if (k <= kParMaxK) {
-    // the local row was consumed by the fan-out above (same warp 0 lanes) before the flags were raised
     for (int j = threadIdx.x; j < k; j += nthr) {
       m.res_s[j] = -CUDART_INF_F;
       m.res_i[j] = -1;
@@ -772,14 +780,9 @@ __device__ __noinline__ void merge_world_lists(const float* __restrict__ local_s
       sc = s_score[l * k + j];
       id = s_idx[l * k + j];
     };
-    select_rounds(load, world, k, k, 0, m.res_s, m.res_i, lane);
+    select_rounds(load, world, k, k, 0, m.res_s, m.res_i, threadIdx.x & 31);
   }
   __syncthreads();
-}
-
-__device__ __forceinline__ void exchange_query(const ExchangeArgs& x, int q, int k, const MergeSmem& m, int nthr) {
-  push_row(x, q, k, m);
-  finalize_query(x, q, k, m, nthr);
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
@@ -1494,6 +1497,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
         }
       }
       // per-CTA candidates, best first; dot scores leave raw units here
+      griddep_wait();  // (overlapped launches) the previous search is done with cand_*
       if (live && worker) {
         float* cs = p.cand_score + ((size_t)row * p.n_work + blockIdx.x) * k;   // [query][cta][k]
         int* ci = p.cand_idx + ((size_t)row * p.n_work + blockIdx.x) * k;
@@ -1518,13 +1522,21 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
     }
   }
 
-  if (p.tail_mode != 0) __threadfence();  // this thread's candidate stores are visible GPU-wide before the arrival
+  if (!DOCM && p.tail_mode != 0) __threadfence();  // this thread's candidate stores are visible GPU-wide before the arrival
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+
+  // Overlapped launches (p.pdl): from here on this CTA only publishes and merges, so the NEXT search's grid may
+  // start filling the SMs that worker CTAs are about to leave.  Every thread first waits for the previous
+  // search to be complete (its merging CTAs read the workspaces this one is about to reuse); a CTA therefore
+  // releases its dependents only after its own predecessor has finished, which keeps at most two searches in
+  // flight (the two blocks of sync counters alternate).  Without the launch attribute both are no-ops.
+  griddep_wait();
+  griddep_launch_dependents();
 
   if constexpr (DOCM) {
     // the four warps' lists of query q (best first, shared memory) -> the CTA's one list in cand_*
@@ -1556,39 +1568,24 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
         for (int w = 0; w < 4; ++w)
           if (w == bw) ++h[w];
       }
+      if (p.tail_mode != 0) __threadfence();
     }
-    if (p.tail_mode != 0) __threadfence();
     __syncthreads();
   }
-
   // ===================== tail: candidate merge (+ multi-GPU exchange) inside the same launch ============
   // Worker CTAs publish their lists and arrive on a device counter; CTA q (q < n_queries) waits for all
   // n_work arrivals, merges query q's lists out of L2 (ring/Q shared memory is free by now) and - multi-GPU
   // - exchanges the row with the peer GPUs and merges the world lists.  Every CTA of the grid is resident
   // (grid <= SM count, one CTA per SM), so the wait cannot starve a CTA that has not started.  The last
-  // merging CTA to leave resets the counters for the next launch (launches on one index are stream-ordered).
+  // merging CTA to leave resets the counters for the launch after the next one (launches on one index are
+  // stream-ordered and alternate between two counter blocks).
   if (p.tail_mode != 0) {
     if (threadIdx.x == 0 && worker) {
       __threadfence();
       atomicAdd(p.sync, 1u);
       stamp(p.debug_ts, 4);  // candidates published, arrived
     }
-    // tail_mode 3 (deferred exchange): this launch also final-merges the PREVIOUS search, whose rows the
-    // peers pushed one search ago - it does so before waiting for its own grid, i.e. while slower CTAs of
-    // this GPU are still scanning, and it never waits for a peer's current search: every rank runs at its
-    // own pace (one search of slack), and the NVLink round trip leaves the critical path.
-    const int prev_nq = p.tail_mode == 3 ? p.xp.n_queries : 0;
-    const int duty = max(p.n_queries, prev_nq);
-    if ((int)blockIdx.x < duty) {
-      for (int q = blockIdx.x; q < prev_nq; q += gridDim.x) {
-        const MergeSmem mp = merge_smem_at(smem, p.xp.k);
-        finalize_query(p.xp, q, p.xp.k, mp, kThreads);
-        for (int j = threadIdx.x; j < p.xp.k; j += kThreads) {
-          p.xp.out_score[(size_t)q * p.xp.k + j] = mp.res_s[j];
-          p.xp.out_idx[(size_t)q * p.xp.k + j] = mp.res_i[j];
-        }
-        __syncthreads();
-      }
+    if ((int)blockIdx.x < p.n_queries) {
       if (threadIdx.x == 0) {
         long long spins = 0;
         while (ld_acquire_gpu_u32(p.sync) < (unsigned int)p.n_work) {
@@ -1605,24 +1602,21 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
       const MergeSmem m = merge_smem_at(smem, p.k);
       for (int q = blockIdx.x; q < ((p.debug_flags & 4) ? 0 : p.n_queries); q += gridDim.x) {
         merge_query_local(p.cand_score, p.cand_idx, p.n_work, p.k, p.idx_offset, q, m, kThreads, p.debug_ts);
-        if (p.tail_mode == 3) {
-          push_row(p.x, q, p.k, m);  // the final merge of this search happens in the next launch / the flush
-        } else {
-          if (p.tail_mode == 2) exchange_query(p.x, q, p.k, m, kThreads);
-          for (int j = threadIdx.x; j < p.k; j += kThreads) {
-            p.out_score[(size_t)q * p.k + j] = m.res_s[j];
-            p.out_idx[(size_t)q * p.k + j] = m.res_i[j];
-          }
+        if (p.tail_mode == 2) exchange_query(p.x, q, p.k, m, kThreads, p.err_flag);
+        for (int j = threadIdx.x; j < p.k; j += kThreads) {
+          p.out_score[(size_t)q * p.k + j] = m.res_s[j];
+          p.out_idx[(size_t)q * p.k + j] = m.res_i[j];
         }
         __syncthreads();
       }
       if (threadIdx.x == 0) {
         stamp(p.debug_ts, 6);  // this CTA's queries merged and written
-        const unsigned int mergers = (unsigned int)min((int)gridDim.x, duty);
+        const unsigned int mergers = (unsigned int)min((int)gridDim.x, p.n_queries);
         if (atomicAdd(p.sync + 1, 1u) == mergers - 1u) {
           atomicExch(p.sync, 0u);
           atomicExch(p.sync + 1, 0u);
           atomicExch(p.sync + 4, 0u);  // tile counter of the dynamic scheduler
+          if (p.tail_mode == 2 && p.x.last_pass) bump_epoch(p.x.epoch);  // every query of this search is exchanged
         }
       }
     }
@@ -1704,27 +1698,19 @@ __global__ void __launch_bounds__(kMergeThreads) exchange_merge_kernel(const flo
                                                                        int k, long long idx_offset,
                                                                        float* __restrict__ out_score,
                                                                        long long* __restrict__ out_idx,
-                                                                       const ExchangeArgs x) {
+                                                                       const ExchangeArgs x, unsigned int* err_flag) {
   extern __shared__ __align__(16) uint8_t merge_smem[];
   const int q = blockIdx.x;  // query inside this pass
   const MergeSmem m = merge_smem_at(merge_smem, k);
   merge_query_local(cand_score, cand_idx, n_lists, k, idx_offset, q, m, kMergeThreads);
-  exchange_query(x, q, k, m, kMergeThreads);
+  exchange_query(x, q, k, m, kMergeThreads, err_flag);
   for (int j = threadIdx.x; j < k; j += kMergeThreads) {
     out_score[(size_t)q * k + j] = m.res_s[j];
     out_idx[(size_t)q * k + j] = m.res_i[j];
   }
-}
-
-// Deferred exchange, last step: final merge of a search whose rows have already been pushed (rs_xchg_flush).
-__global__ void __launch_bounds__(kMergeThreads) exchange_finalize_kernel(const ExchangeArgs x) {
-  extern __shared__ __align__(16) uint8_t merge_smem[];
-  const int q = blockIdx.x;
-  const MergeSmem m = merge_smem_at(merge_smem, x.k);
-  finalize_query(x, q, x.k, m, kMergeThreads);
-  for (int j = threadIdx.x; j < x.k; j += kMergeThreads) {
-    x.out_score[(size_t)q * x.k + j] = m.res_s[j];
-    x.out_idx[(size_t)q * x.k + j] = m.res_i[j];
+  if (threadIdx.x == 0 && atomicAdd(x.epoch + 1, 1u) == gridDim.x - 1u) {  // last CTA of the pass
+    atomicExch(x.epoch + 1, 0u);
+    if (x.last_pass) bump_epoch(x.epoch);
   }
 }
 
@@ -1746,8 +1732,20 @@ static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t 
   const int bytes = (int)map.total + 1024;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kThreads, bytes, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = (size_t)bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (p.pdl) {  // programmatic dependent launch: this grid may start while the previous kernel of the stream drains
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages, int bufc,
@@ -1824,7 +1822,7 @@ cudaError_t launch_merge_i64(const float* cand_score, const long long* cand_idx,
 
 cudaError_t launch_exchange_merge(const float* cand_score, const int* cand_idx, int n_lists, int n_queries, int k,
                                   long long idx_offset, float* out_score, long long* out_idx, const ExchangeArgs& x,
-                                  cudaStream_t stream) {
+                                  unsigned int* err_flag, cudaStream_t stream) {
   if (n_lists > 32 * kMergeMaxOwn || x.world > kMaxPeers) return cudaErrorInvalidValue;
   const size_t res_bytes = merge_res_bytes(k);
   const size_t stage_bytes = std::max((size_t)n_lists * k * 8, (size_t)x.world * k * 12);
@@ -1835,14 +1833,7 @@ cudaError_t launch_exchange_merge(const float* cand_score, const int* cand_idx, 
     if (e != cudaSuccess) return e;
   }
   exchange_merge_kernel<<<n_queries, kMergeThreads, bytes, stream>>>(cand_score, cand_idx, n_lists, k, idx_offset,
-                                                                     out_score, out_idx, x);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_exchange_finalize(const ExchangeArgs& x, cudaStream_t stream) {
-  if (x.world > kMaxPeers || x.n_queries <= 0) return cudaErrorInvalidValue;
-  const size_t bytes = merge_res_bytes(x.k) + (size_t)x.world * x.k * 12;
-  exchange_finalize_kernel<<<x.n_queries, kMergeThreads, bytes, stream>>>(x);
+                                                                     out_score, out_idx, x, err_flag);
   return cudaGetLastError();
 }
 

@@ -146,6 +146,7 @@ class B200Retriever:
         self._max_batch, self._max_k = int(max_batch), int(max_k)
         self._query_terms = query_terms
         self._shards: List[_cabi.Index] = []
+        self._group: Optional[_cabi.Group] = None
         self._lock = threading.Lock()
 
     def _create_shards(self, scale_exp: int):
@@ -158,8 +159,16 @@ class B200Retriever:
                 self._shards.append(_cabi.Index(hi - lo, self.D, self._dtype, device=dev, row_offset=lo,
                                                 max_batch=self._max_batch, max_k=self._max_k,
                                                 scale_exp=scale_exp))
+        if len(self._shards) > 1:
+            # one process, several GPUs (main.py:52-55 constructs ONE retriever): the C ABI's group drives all
+            # shards from the calling thread - one H2D + one fused kernel per GPU with the candidate exchange
+            # inside the kernels (NVLink peer memory), one D2H; replayed from ONE multi-device CUDA graph
+            self._group = _cabi.Group(self._shards)
 
     def close(self):
+        if getattr(self, "_group", None) is not None:
+            self._group.close()
+            self._group = None
         for ix in getattr(self, "_shards", []):
             ix.close()
         self._shards = []
@@ -175,44 +184,24 @@ class B200Retriever:
             raise ValueError(f"queries must be [B, {self.D}]")
         if k <= 0:
             raise ValueError("k must be positive")
+        if k > self._max_k:
+            raise ValueError(f"k={k} exceeds max_k={self._max_k} given at construction")
         metric = metric or self._metric
         terms = query_terms or self._query_terms or _auto_query_terms(q, self._dtype)
         B = q.shape[0]
-        kk = min(k, self._max_k)
-        if kk < k:
-            raise ValueError(f"k={k} exceeds max_k={self._max_k} given at construction")
-        if B <= self._max_batch and len(self._shards) == 1:      # the serving case: one call, fresh arrays
+        backend = self._group if self._group is not None else self._shards[0]
+        if B <= self._max_batch:                                  # the serving case: one call, fresh arrays
             with self._lock:
-                return self._shards[0].search(q, k, metric, terms)
+                return backend.search(q, k, metric, terms)
         out_i = np.full((B, k), -1, dtype=np.int64)
         out_s = np.full((B, k), -np.inf, dtype=np.float32)
         with self._lock:
             for b0 in range(0, B, self._max_batch):
                 qb = q[b0:b0 + self._max_batch]
-                if len(self._shards) == 1:
-                    i, s = self._shards[0].search(qb, k, metric, terms)
-                else:
-                    i, s = self._search_multi(qb, k, metric, terms)
+                i, s_ = backend.search(qb, k, metric, terms)
                 out_i[b0:b0 + len(qb)] = i
-                out_s[b0:b0 + len(qb)] = s
+                out_s[b0:b0 + len(qb)] = s_
         return out_i, out_s
-
-    def _search_multi(self, q, k, metric, terms):
-        """Single-process multi-GPU: every shard searches concurrently (ctypes drops the GIL), the
-        B x k candidates of each GPU are gathered on the first device and merged there."""
-        import torch
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(len(self._shards)) as ex:
-            parts = list(ex.map(lambda ix: ix.search(q, k, metric, terms), self._shards))
-        dev = torch.device("cuda", self._shards[0].device)
-        B = q.shape[0]
-        ci = torch.from_numpy(np.stack([p[0] for p in parts])).to(dev)
-        cs = torch.from_numpy(np.stack([p[1] for p in parts])).to(dev)
-        oi = torch.empty((B, k), dtype=torch.int64, device=dev)
-        os_ = torch.empty((B, k), dtype=torch.float32, device=dev)
-        _cabi.merge_device(dev.index, cs.data_ptr(), ci.data_ptr(), len(parts), B, k, k, oi.data_ptr(),
-                           os_.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
-        return oi.cpu().numpy(), os_.cpu().numpy()
 
     def search_tensor(self, queries, k: int, metric: Optional[str] = None, query_terms: Optional[int] = None):
         """Zero-copy hand-off from the embedder: ``queries`` is a float32 CUDA tensor
@@ -265,6 +254,9 @@ class B200Retriever:
             if actual_k <= 0:                                             # :644-646
                 log.warning("Requested k=%s results in actual_k=%s. Returning empty list.", k, actual_k)
                 return []
+            if actual_k > self._max_k:        # behavioural difference, INTEGRATION.md: the kernels keep <= max_k hits
+                log.warning("k=%d exceeds max_k=%d; returning the best %d documents", actual_k, self._max_k, self._max_k)
+                actual_k = self._max_k
             idx, _ = self.search(query_emb.reshape(1, self.D), actual_k)
             return _gather(self.documents, idx[0][idx[0] >= 0])           # :675
         except Exception as e:                                            # :681-683
@@ -303,6 +295,13 @@ class B200Retriever:
         if max_k <= 0:                                                    # :731-732
             return [[] for _ in ks]
         try:
+            if max_k > self._max_k:
+                # behavioural difference: the kernels keep at most max_k hits per query.  One
+                # oversized request must not cost the other requests of its batch their contexts (the reference
+                # serves any k <= N), so that row gets the best max_k documents and a warning.
+                log.warning("batch_retrieve: k=%d exceeds max_k=%d; rows asking for more get the best %d documents",
+                            max_k, self._max_k, self._max_k)
+                max_k = self._max_k
             idx, _ = self.search(query_embeddings, max_k)                 # :736-773
             return _rows_to_docs(self.documents, idx, ks)                 # :776-790
         except Exception as e:                                            # :796-799

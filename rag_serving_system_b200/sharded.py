@@ -5,8 +5,8 @@ Each rank owns a contiguous row shard behind one ``_cabi.Index``.  A search is
     local fused score+select  ->  B x k (score, global index) candidates per rank
     exchange of the candidates over NVLink (B*k*12 bytes per rank), either
       exchange="nccl": ONE all-gather of the packed candidates (north_star (c)), or
-      exchange="p2p" : the local merge kernel itself stores each row into every GPU's buffer
-                       through CUDA-IPC peer pointers and raises an epoch flag (no collective call)
+      exchange="p2p" : the tail of the scan kernel itself stores each row into every GPU's buffer through
+                       CUDA-IPC peer pointers as 16-byte {index, score, epoch} entries (no collective call)
     on-device merge of the G sorted lists per query on every rank
 
 The path has exactly one exchange step.  The reference has no multi-GPU search at all (it scales
@@ -131,55 +131,41 @@ class ShardedSearcher:
                            stream, score_list_stride=nb // 4, idx_list_stride=nb // 8)
         return out_i, out_s
 
-    def search_async(self, q_dev: torch.Tensor, k: int, metric: str = "dot", query_terms: int = 1):
-        """Pipelined form for back-to-back searches (p2p exchange): the launch pushes this search's rows to
-        the peers and never waits for them; the final merge of search i runs in the tail of search i+1 (or
-        in ``flush``).  The returned tensors are therefore valid, in stream order, after the NEXT
-        ``search_async`` / ``flush``; three output sets rotate, so keep at most two searches un-flushed
-        before reading.  Falls back to ``search`` when there is nothing to pipeline."""
-        if self.xchg is None:
-            return self.search(q_dev, k, metric, query_terms)
-        assert q_dev.is_cuda and q_dev.dtype == torch.float32 and q_dev.is_contiguous()
-        B = q_dev.shape[0]
-        key = ("async", B, k)
-        if key not in self._bufs:
-            dev = torch.device("cuda", self.device)
-            self._bufs[key] = [0] + [(torch.empty((B, k), dtype=torch.int64, device=dev),
-                                      torch.empty((B, k), dtype=torch.float32, device=dev)) for _ in range(3)]
-        ring = self._bufs[key]
-        ring[0] = (ring[0] + 1) % 3
-        out_i, out_s = ring[1 + ring[0]]
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        self.xchg.search_async(self.index, q_dev.data_ptr(), B, k, out_i.data_ptr(), out_s.data_ptr(), metric,
-                               query_terms, stream)
-        return out_i, out_s
+    def set_overlap(self, on: bool):
+        """Let consecutive ``search`` calls on one stream overlap (RS_OVERLAP, programmatic dependent launch):
+        the scan of search i+1 runs while the merge / exchange tail of search i drains.  The queries of a
+        search must then not be produced by the kernel that immediately precedes it on the stream."""
+        self.index.set_option("RS_OVERLAP", 1 if on else 0)
 
-    def flush(self):
-        """Final merge of the last ``search_async`` (no-op when nothing is pending)."""
+    def search_host(self, q_host, k: int, metric: str = "dot", query_terms: int = 1, want_result: bool = True):
+        """End-to-end call with HOST buffers (a NumPy array or a CPU torch tensor): H2D of the queries from the
+        library's pinned staging, search (+ exchange), D2H of the result, one synchronisation - all inside the C
+        ABI (rs_search / rs_search_exchange_host), replayed from a CUDA graph.  ``want_result=False`` on ranks
+        that only take part (no D2H).  The NCCL exchange keeps the torch-level sequence."""
+        q_np = q_host.numpy() if isinstance(q_host, torch.Tensor) else q_host
+        if self.world == 1:
+            return self.index.search(q_np, k, metric, query_terms)
         if self.xchg is not None:
-            self.xchg.flush(self.index, torch.cuda.current_stream(self.device).cuda_stream)
-
-    def search_host(self, q_host: torch.Tensor, k: int, metric: str = "dot", query_terms: int = 1):
-        """End-to-end call with HOST buffers: pinned H2D of the queries, search, D2H of the result into
-        pinned host tensors (reused by the next call with the same B and k), one synchronisation."""
+            return self.xchg.search_host(self.index, q_np, k, metric, query_terms, want_result)
         dev = torch.device("cuda", self.device)
-        B = q_host.shape[0]
+        B = q_np.shape[0]
         key = ("host", B, k)
         if key not in self._bufs:
-            self._bufs[key] = (torch.empty((B, q_host.shape[1]), dtype=torch.float32, device=dev),
+            self._bufs[key] = (torch.empty((B, q_np.shape[1]), dtype=torch.float32).pin_memory(),
+                               torch.empty((B, q_np.shape[1]), dtype=torch.float32, device=dev),
                                torch.empty((B, k), dtype=torch.int64).pin_memory(),
                                torch.empty((B, k), dtype=torch.float32).pin_memory())
-        q_dev, pin_i, pin_s = self._bufs[key]
-        q_dev.copy_(q_host, non_blocking=True)
+        q_pin, q_dev, pin_i, pin_s = self._bufs[key]
+        q_pin.numpy()[...] = q_np
+        q_dev.copy_(q_pin, non_blocking=True)
         oi, os_ = self.search(q_dev, k, metric, query_terms)
         pin_i.copy_(oi, non_blocking=True)
         pin_s.copy_(os_, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return pin_i, pin_s
+        return pin_i.numpy(), pin_s.numpy()
 
     def close(self):
         if self.xchg is not None:
-            self.flush()
             torch.cuda.synchronize(self.device)
             if dist.is_initialized():
                 dist.barrier(group=self.group)      # nobody unmaps a buffer a peer may still write

@@ -26,8 +26,9 @@ def main():
     ok = True
     for dtype, metric, k, B, exch in (("bf16", "dot", 10, 32, "p2p"), ("bf16", "dot", 10, 32, "nccl"),
                                       ("fp32", "cosine", 5, 7, "p2p"), ("fp16", "dot", 100, 3, "nccl"),
-                                      ("bf16", "dot", 17, 100, "p2p")):
-        s = ShardedSearcher(N, D, dtype, max_batch=128, max_k=128, scale_exp=4 if dtype == "fp32" else 0,
+                                      ("bf16", "dot", 17, 100, "p2p"), ("fp16", "dot", 100, 256, "p2p"),
+                                      ("fp16", "cosine", 100, 256, "p2p")):
+        s = ShardedSearcher(N, D, dtype, max_batch=256, max_k=128, scale_exp=4 if dtype == "fp32" else 0,
                             exchange=exch)
         s.fill_synthetic(1234)
         Q, src = o.synth_queries(9, N, B, D, dtype=o.DTYPE_NAMES[dtype])
@@ -36,9 +37,13 @@ def main():
         for _ in range(3):                      # repeated calls exercise both parities of the exchange buffer
             idx, sc = s.search(q_dev, k, metric, terms)
         torch.cuda.synchronize()
+        s.index.check()
         idx, sc = idx.cpu().numpy(), sc.cpu().numpy()
-        hidx, hsc = s.search_host(torch.from_numpy(Q).pin_memory(), k, metric, terms)
-        assert np.array_equal(hidx.numpy(), idx) and np.array_equal(hsc.numpy(), sc)
+        # host-buffer call (C ABI, CUDA-graph replay from the 2nd call on); only rank 0 asks for the result
+        for _ in range(3):
+            hidx, hsc = s.search_host(Q, k, metric, terms, want_result=(rank == 0 or exch == "nccl"))
+        if rank == 0 or exch == "nccl":
+            assert np.array_equal(hidx, idx) and np.array_equal(hsc, sc)
         # every rank must hold the same answer
         gathered = [None] * world
         dist.all_gather_object(gathered, (idx.tobytes(), sc.tobytes()))
@@ -51,30 +56,28 @@ def main():
             assert (idx[:, 0] == src).all()
             print(f"multi-gpu ok world={world} {dtype} {metric} k={k} B={B} exchange={exch} near-tie swaps={sw}", flush=True)
         if exch == "p2p":
-            # pipelined (deferred) exchange: the final merge of search i runs in the tail of search i+1 or in
-            # flush(); every result must equal the synchronous search of the same queries, also when B and k
-            # change between calls and when synchronous searches are interleaved
-            seq = [(Q, k), (Q[::-1].copy(), k), (Q[: max(1, B // 2)].copy(), max(1, k // 2)), (Q, k), (Q[::-1].copy(), k)]
+            # overlapped launches (RS_OVERLAP, programmatic dependent launch): the scan of search i+1 runs while the
+            # exchange tail of search i drains; every result must equal the serial search of the same queries, also
+            # when B and k change between calls
+            seq = [(Q, k), (Q[::-1].copy(), k), (Q[: max(1, B // 2)].copy(), max(1, k // 2)), (Q, k), (Q[::-1].copy(), k)] * 2
+            qs = [torch.from_numpy(Qi).cuda() for Qi, _ in seq]
             want = []
-            for Qi, ki in seq:
-                wi, ws = s.search(torch.from_numpy(Qi).cuda(), ki, metric, terms)
+            for qd, (Qi, ki) in zip(qs, seq):
+                wi, ws = s.search(qd, ki, metric, terms)
                 want.append((wi.clone(), ws.clone()))
-            got, prev = [], None
-            for Qi, ki in seq:
-                cur = s.search_async(torch.from_numpy(Qi).cuda(), ki, metric, terms)
-                if prev is not None:
-                    got.append((prev[0].clone(), prev[1].clone()))      # valid after the NEXT call (stream order)
-                prev = cur
-            s.flush()
-            got.append((prev[0].clone(), prev[1].clone()))
-            mid_i, mid_s = s.search_async(q_dev, k, metric, terms)          # pending search, then a synchronous one
-            si, ss = s.search(q_dev, k, metric, terms)
             torch.cuda.synchronize()
-            assert torch.equal(mid_i, si) and torch.equal(mid_s, ss)
+            s.set_overlap(True)
+            got = []
+            for qd, (Qi, ki) in zip(qs, seq):
+                gi, gs = s.search(qd, ki, metric, terms)
+                got.append((gi.clone(), gs.clone()))      # clone: a kernel of torch's between two searches is allowed
+            torch.cuda.synchronize()
+            s.index.check()
+            s.set_overlap(False)
             for n, ((gi, gs), (wi, ws)) in enumerate(zip(got, want)):
-                assert torch.equal(gi, wi) and torch.equal(gs, ws), f"deferred exchange: search {n} differs"
+                assert torch.equal(gi, wi) and torch.equal(gs, ws), f"overlapped launches: search {n} differs"
             if rank == 0:
-                print(f"deferred exchange ok world={world} {dtype} {metric} k={k} B={B}", flush=True)
+                print(f"overlapped launches ok world={world} {dtype} {metric} k={k} B={B}", flush=True)
         s.close()
     dist.barrier()
     dist.destroy_process_group()

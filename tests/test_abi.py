@@ -26,7 +26,7 @@ def test_library_builds_and_loads():
     path = build.build()
     assert os.path.exists(path)
     lib = _cabi.load()
-    assert lib.rs_version() == 1
+    assert lib.rs_version() == _cabi.ABI_VERSION == 2
 
 
 def test_every_declared_symbol_is_exported():
@@ -41,7 +41,7 @@ def test_every_declared_symbol_is_exported():
 def test_struct_layouts_match_header():
     # sizes the C side checks via struct_size
     assert C.sizeof(_cabi.rs_config) == 48
-    assert C.sizeof(_cabi.rs_stats) == 72
+    assert C.sizeof(_cabi.rs_stats) == 80
 
 
 def test_build_targets_sm100a_only():

@@ -37,9 +37,24 @@ class FakeIndex:
         pass
 
 
+class FakeGroup:
+    """Test double for _cabi.Group: per-shard oracle searches merged with the oracle's candidate merge."""
+
+    def __init__(self, shards):
+        self.shards = list(shards)
+
+    def search(self, q, k, metric="dot", query_terms=1):
+        parts = [ix.search(q, k, metric, query_terms) for ix in self.shards]
+        return o.merge_candidates(np.stack([p[1] for p in parts]), np.stack([p[0] for p in parts]), k)
+
+    def close(self):
+        pass
+
+
 @pytest.fixture()
 def fake_backend(monkeypatch):
     monkeypatch.setattr(_cabi, "Index", FakeIndex)
+    monkeypatch.setattr(_cabi, "Group", FakeGroup)
 
 
 def test_class_surface_matches_reference(fake_backend, short_facts):
@@ -81,6 +96,23 @@ def test_retrieve_with_scores_triple_and_multi_shard(fake_backend, squad):
         r.search(g.Q, 0)
     with pytest.raises(ValueError):
         r.search(g.Q[:, :3], 1)
+
+
+def test_multi_device_class_and_k_above_max_k(fake_backend, squad):
+    """devices=[...] splits the corpus into contiguous row shards behind one group (same answers as one shard);
+    a request with k > max_k gets the best max_k documents and does not empty the other rows of its batch
+    (the reference serves any k <= N, retriever.py:729-730; documented difference)."""
+    g = squad
+    one = retriever.SimpleRetriever(g.E, g.contexts, max_k=16)
+    multi = retriever.SimpleRetriever(g.E, g.contexts, max_k=16, devices=[0, 1, 2])
+    assert [ix.row_offset for ix in multi._shards] == [0, 334, 668] and multi._group is not None
+    ks = [g.k] * len(g.Q)
+    assert multi.batch_retrieve(g.Q, ks) == one.batch_retrieve(g.Q, ks) == g.texts
+    ks[5] = 99
+    out = one.batch_retrieve(g.Q, ks)
+    assert [row for i, row in enumerate(out) if i != 5] == [row for i, row in enumerate(g.texts) if i != 5]
+    assert len(out[5]) == 16 and out[5][:g.k] == g.texts[5]
+    assert len(one.retrieve(g.Q[0], 40)) == 16 and one.retrieve(g.Q[0], 3) == g.texts[0][:3]
 
 
 def test_gather_and_source_dtype_helpers():

@@ -1,10 +1,14 @@
 """CPU tests: the oracle against the reference-generated golden vectors (tests/golden, written by
 oracle/make_golden.py from the UNMODIFIED reference SimpleRetriever) and its own invariants."""
+import os
+
 import numpy as np
 import pytest
 from hypothesis import given, settings, strategies as st
 
 from oracle import retrieval_oracle as o
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 # ---------------------------------------------------------------- pinned to the reference
@@ -208,3 +212,32 @@ def test_stored_values_roundtrip():
     x = o.synth_rows(9, np.arange(10))
     assert np.array_equal(o.stored_values(x, o.DTYPE_BF16), o.round_to_bf16(x).astype(np.float64))
     assert np.abs(o.stored_values(x, o.DTYPE_FP32, 4) - x).max() < 1e-8
+
+
+def test_native_synth_rows_equal_numpy():
+    """oracle/synth_native.c (the C restatement bench.py's CPU legs use for >= 1M-row samples) is bit-identical to
+    the NumPy generator, for any row range and dimension."""
+    from oracle import build_oracle
+    if build_oracle.build_native() is None:
+        pytest.skip("gcc not available")
+    for seed, row0, n, D in ((1234, 0, 300, 1024), (7, 999_999_000, 129, 64), (1234, 12_345_678, 50, 2048)):
+        a = build_oracle.synth_rows_native(seed, row0, n, D)
+        assert a.dtype == np.float32 and np.array_equal(a, o.synth_rows(seed, np.arange(row0, row0 + n), D))
+
+
+def test_reference_copy_recipe_and_port_agree():
+    """oracle/_ref holds an UNMODIFIED copy of the reference module (made by oracle/build_oracle.py when
+    /root/reference exists); its SimpleRetriever and the oracle port return the same documents."""
+    import hashlib
+    from oracle import build_oracle
+    mod = build_oracle.load_reference_module()
+    if mod is None:
+        pytest.skip("no /root/reference and no oracle/_ref copy on this box")
+    if os.path.exists(build_oracle.REF_SRC):
+        assert (hashlib.sha256(open(build_oracle.REF_SRC, "rb").read()).hexdigest()
+                == hashlib.sha256(open(build_oracle.REF_COPY, "rb").read()).hexdigest())
+    g = np.load(os.path.join(GOLD, "squad_golden.npz"))
+    E = np.load(os.path.join(GOLD, "squad_embeddings.npy"))
+    docs = [str(i) for i in range(len(E))]
+    ks = [int(g["k"])] * len(g["queries"])
+    assert mod.SimpleRetriever(E, docs).batch_retrieve(g["queries"], ks) == o.SimpleRetrieverPort(E, docs).batch_retrieve(g["queries"], ks)

@@ -50,6 +50,7 @@ for rep in range(reps):
         for key in KEYS:
             os.environ.pop(key, None)
         os.environ.update({k_: str(v) for k_, v in env.items() if not k_.startswith("_")})
+        ix.reload_env_options()
         B, k = int(env.get("_B", B0)), int(env.get("_k", k0))      # "_B" / "_k" override the batch / k per variant
         name = json.dumps(env)
         try:

@@ -15,6 +15,7 @@ st = torch.cuda.current_stream().cuda_stream
 for env in ({}, {"RS_NO_EVENTS": "1"}):
     for k_ in ("RS_NO_EVENTS",): os.environ.pop(k_, None)
     os.environ.update(env)
+    ix.reload_env_options()
     for _ in range(10): ix.search_device(q.data_ptr(), 32, 10, oi.data_ptr(), os_.data_ptr(), "dot", 1, st)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -46,6 +46,7 @@ def run(ix, q_dev, B, k, metric, terms, steps, env, label, out):
     for key in ("RS_MMA_M", "RS_QRESIDENT", "RS_SUB", "RS_NBUF", "RS_CPS", "RS_INLINE_PREP", "RS_FUSED_TAIL", "RS_DEBUG_FLAGS", "RS_SHARED_BOUND", "RS_DOCM", "RS_QLO_STREAM", "RS_LISTS_GLOBAL", "RS_DYN_SCHED", "RS_BUFC", "RS_LEAN"):
         os.environ.pop(key, None)
     os.environ.update({k_: str(v) for k_, v in env.items()})
+    ix.reload_env_options()
     oi = torch.empty((B, k), dtype=torch.int64, device="cuda")
     os_ = torch.empty((B, k), dtype=torch.float32, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
