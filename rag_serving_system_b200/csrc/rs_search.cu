@@ -721,6 +721,7 @@ __device__ __forceinline__ uint4 ld_entry(const uint4* p) {
   asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
+constexpr unsigned long long kPeerTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;  // 30 s
 __device__ __forceinline__ void bump_epoch(unsigned int* epoch) {  // never 0: zeroed buffers must not match
   const unsigned int e = __ldcg(epoch) + 1u;
   __stcg(epoch, e == 0u ? 1u : e);
@@ -742,13 +743,21 @@ __device__ __noinline__ void exchange_query(const ExchangeArgs& x, int q, int k,
     const int r = e / k, j = e - r * k;
     const uint4* src = x.local + (size_t)r * x.slot_entries + qe + j;
     uint4 v = ld_entry(src);
-    long long spins = 0;
+    // A peer process may legitimately be late by seconds (its host thread was busy); only a peer that does not
+    // show up for kPeerTimeoutNs is treated as gone.
+    unsigned long long t0 = 0;
+    int spins = 0;
     while (v.w != epoch) {
-      if (++spins > 64) __nanosleep(100);
-      if (spins > (1ll << 23)) {  // ~ seconds: the peer never pushed this search
-        *reinterpret_cast<volatile unsigned int*>(err_flag) = 2u;
-        v = make_uint4(0xffffffffu, 0xffffffffu, 0xff800000u, epoch);  // (-1, -inf)
-        break;
+      if (++spins > 64) {
+        __nanosleep(200);
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (now - t0 > kPeerTimeoutNs) {
+          *reinterpret_cast<volatile unsigned int*>(err_flag) = 2u;
+          v = make_uint4(0xffffffffu, 0xffffffffu, 0xff800000u, epoch);  // (-1, -inf)
+          break;
+        }
       }
       v = ld_entry(src);
     }

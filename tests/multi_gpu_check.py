@@ -55,6 +55,7 @@ def main():
             sw = o.check_topk(idx, sc, S, k, rtol=1e-5 if dtype == "fp32" else 2e-3, atol=1e-6)
             assert (idx[:, 0] == src).all()
             print(f"multi-gpu ok world={world} {dtype} {metric} k={k} B={B} exchange={exch} near-tie swaps={sw}", flush=True)
+        dist.barrier()
         if exch == "p2p":
             # overlapped launches (RS_OVERLAP, programmatic dependent launch): the scan of search i+1 runs while the
             # exchange tail of search i drains; every result must equal the serial search of the same queries, also
