@@ -417,7 +417,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.corpus_scale_exp = corpus_scale_exp;
     p.n_work = n_work;
     p.tail_mode = fused_tail ? (xg ? 2 : 1) : 0;
-    p.pdl = pdl ? 1 : 0;
+    p.pdl = pdl ? (grid == ix->sm_count && n_work == grid ? 2 : 1) : 0;
     ix->launch_parity ^= 1u;
     p.sync = ix->sync + 64 * ix->launch_parity;
     p.dyn_sched = o.dyn_sched != 0 ? 1 : 0;

@@ -63,7 +63,8 @@ struct SearchParams {
   int n_work;                        // CTAs that own tiles and write candidate lists (= lists per query)
   int tail_mode;                     // 0: candidates only; 1: + in-kernel merge; 2: + peer exchange and final merge
   int pdl;                           // launched with programmatic stream serialization: the scan may overlap the
-                                     // previous search's tail; shared workspaces are touched only after griddepcontrol.wait
+                                     // previous search's tail; shared workspaces are touched only after griddepcontrol.wait.
+                                     // 1: dependents released after the scan; 2 (grid == SM count): at kernel entry
   unsigned int* sync;                // [0] arrivals of worker CTAs, [1] departures of merging CTAs, [4] next tile (dynamic
                                      // scheduler); the host alternates between two such blocks from launch to launch
   int dyn_sched;                     // 1: supertiles after the first come from sync[4] (work stealing); 0: static round-robin

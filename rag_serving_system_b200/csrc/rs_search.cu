@@ -1000,6 +1000,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   float* s_qnorm = reinterpret_cast<float*>(smem + map.bar_off + 1024);
   float* s_qscale = s_qnorm + 128;
 
+  // Overlapped launches, full-machine grids (p.pdl == 2): release the dependent grid right away.  It can only
+  // become resident as this grid's CTAs leave their SMs (one CTA per SM), so the next search's CTAs start
+  // one by one the moment a worker CTA of this search exits - no wait for the slowest scanner, no launch
+  // latency - and since its CTAs release THEIR dependents only once all of them are resident, i.e. once every
+  // CTA of this grid has exited, at most two searches are ever in flight.
+  if (p.pdl == 2) griddep_launch_dependents();
   if (threadIdx.x == 0) {
     stamp(p.debug_ts, 0);  // kernel entry
     for (int s = 0; s < p.stages; ++s) {
@@ -1545,7 +1551,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
   // releases its dependents only after its own predecessor has finished, which keeps at most two searches in
   // flight (the two blocks of sync counters alternate).  Without the launch attribute both are no-ops.
   griddep_wait();
-  griddep_launch_dependents();
+  if (p.pdl != 2) griddep_launch_dependents();
 
   if constexpr (DOCM) {
     // the four warps' lists of query q (best first, shared memory) -> the CTA's one list in cand_*

@@ -626,11 +626,13 @@ def test_config5_shape_b256_k100_fp16(metric):
         ix.close()
 
 
-def test_overlapped_launches_equal_serial_searches():
+@pytest.mark.parametrize("N", [300_000, 9_000])
+def test_overlapped_launches_equal_serial_searches(N):
     """RS_OVERLAP=1 (programmatic dependent launch): back-to-back device searches whose scans overlap the previous
-    search's tail give bit-identical results to serial searches, also with alternating queries and k."""
+    search's tail give bit-identical results to serial searches, also with alternating queries, B and k.  300k rows:
+    full-machine grids (dependents released at kernel entry); 9k rows: 71 CTAs (released after the scan)."""
     import torch
-    N, D = 300_000, 1024
+    D = 1024
     ix = _cabi.Index(N, D, "bf16", max_batch=64, max_k=16)
     try:
         ix.fill_synthetic(1234, 0)
@@ -653,9 +655,11 @@ def test_overlapped_launches_equal_serial_searches():
             return [(a.cpu().numpy(), b.cpu().numpy()) for a, b in outs]
 
         want = run()
+        assert ix.stats()["overlapped"] == 0
         ix.set_option("RS_OVERLAP", 1)
         for _ in range(3):
             got = run()
+            assert ix.stats()["overlapped"] == 1
             for (gi, gs), (wi, ws) in zip(got, want):
                 assert np.array_equal(gi, wi) and np.array_equal(gs, ws)
         S = o.scores_dot(Qa.astype(np.float64), o.round_to_bf16(o.synth_rows(1234, np.arange(N), D)).astype(np.float64), np.float64)
