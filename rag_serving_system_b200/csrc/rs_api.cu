@@ -55,6 +55,7 @@ struct Plan {
   int bufc;        // k > 16: candidate-buffer entries per query (32; 16 when that saves a pass)
   int lg;          // k > 16: sorted lists in global memory (L2) instead of shared memory
   int qstages;     // streamed Q: slots of the private Q ring
+  int wide;        // one-pass wide-batch kernel (128 < B <= 256 per pass)
 };
 
 int env_int(const char* name, int dflt) {
@@ -74,6 +75,8 @@ struct Options {
   int qlo_stream = 0;    // RS_QLO_STREAM   two-term searches: 1/2 = stream the lo query term
   int graph = 1;         // RS_GRAPH        0: host-buffer searches enqueue eagerly instead of replaying a CUDA graph
   int no_events = 0;     // RS_NO_EVENTS    1: no CUDA events around the fused launch
+  int wide = 1;          // RS_WIDE         batches above 128: 2 = one pass, CTA-pair kernel (cta_group::2); 1 = one pass, one CTA
+                         //                 per SM; 0 = split into passes of 128
   int overlap = 0;       // RS_OVERLAP      1: consecutive device-buffer searches on one stream may overlap (PDL)
   int debug_flags = 0;   // RS_DEBUG_FLAGS  timing experiments: skip MMAs (1) / the epilogue (2) / the tail merge (4)
   int debug_ts = 0;      // RS_DEBUG_TS     per-CTA %globaltimer phase stamps
@@ -88,7 +91,7 @@ const OptDef kOptDefs[] = {
     {"RS_DOCM", &Options::docm}, {"RS_INLINE_PREP", &Options::inline_prep}, {"RS_FUSED_TAIL", &Options::fused_tail},
     {"RS_DYN_SCHED", &Options::dyn_sched}, {"RS_SHARED_BOUND", &Options::shared_bound},
     {"RS_LISTS_GLOBAL", &Options::lists_global}, {"RS_QLO_STREAM", &Options::qlo_stream}, {"RS_GRAPH", &Options::graph},
-    {"RS_NO_EVENTS", &Options::no_events}, {"RS_OVERLAP", &Options::overlap}, {"RS_DEBUG_FLAGS", &Options::debug_flags},
+    {"RS_NO_EVENTS", &Options::no_events}, {"RS_WIDE", &Options::wide}, {"RS_OVERLAP", &Options::overlap}, {"RS_DEBUG_FLAGS", &Options::debug_flags},
     {"RS_DEBUG_TS", &Options::debug_ts}, {"RS_QRESIDENT", &Options::qresident}, {"RS_CPS", &Options::cps},
     {"RS_SUB", &Options::sub}, {"RS_BUFC", &Options::bufc}, {"RS_LEAN", &Options::lean}, {"RS_MMA_M", &Options::mma_m},
     {"RS_NBUF", &Options::nbuf}, {"RS_QSTAGES", &Options::qstages},
@@ -126,7 +129,9 @@ struct rs_index {
   cudaStream_t stream = nullptr;
   unsigned int* sync = nullptr;      // two blocks of 64 counters (arrivals, departures, next tile); launches alternate
   unsigned int launch_parity = 0;
-  float* g_best = nullptr;           // shared bound table [sm_count][128] (k > 16 searches)
+  float* g_best = nullptr;           // shared bound table [sm_count][256] (k > 16 and wide searches)
+  void* cbuf = nullptr;              // wide searches: candidate buffers [256][grid][32] x 8 B
+  int pair_clusters = -1;            // CTA pairs of the pair kernel this device keeps resident at once (-1: not queried)
   unsigned long long* debug_ts = nullptr;  // RS_DEBUG_TS=1: [grid][8] phase stamps of the last fused launch
   unsigned int* err_flag = nullptr;  // mapped pinned word a kernel raises when a wait times out (1: own CTAs, 2: a peer GPU)
   // searches share the workspaces above, so a search on another stream than the previous one is ordered after it
@@ -205,6 +210,34 @@ int make_plan(const rs_index* ix, const Options& o, int B, int k, int terms, Pla
   const int lg = lists_in_smem && o.lists_global != 0 ? 1 : 0;
   const int qstages = o.qstages > 0 ? o.qstages : 2 * terms;
   pl->qstages = qstages;
+  pl->wide = 0;
+  if (o.wide != 0 && B > 128 && terms == 1 && ix->planes == 1 && rs::fused_wide_smem_bytes(k) <= kMaxSmem) {
+    // Wide batches (BASELINE config 5: B=256): both 128-row halves of the batch share ONE pass over the shard;
+    // the general kernel would stream the shard once per 128 queries.
+    pl->passes = (B + 255) / 256;
+    pl->per_pass = (B + pl->passes - 1) / pl->passes;
+    pl->bpad = 256;
+    pl->q_resident = 0;
+    pl->sub = 2;
+    pl->cps = 1;
+    pl->bufc = rs::fused_wide_bufc();
+    pl->lg = 1;
+    if (o.wide == 2 && ix->pair_clusters != 0 && rs::fused_pair_smem_bytes(k) <= kMaxSmem) {
+      // CTA pairs (fused_search_pair_kernel): M=256 x N=256 MMAs across two SMs, two TMEM accumulators
+      pl->wide = 2;
+      pl->qstages = 0;
+      pl->stages = 6;
+      pl->nbuf = 2;
+      pl->mma_m = 256;
+      return RS_OK;
+    }
+    pl->wide = 1;  // fused_search_wide_kernel: one CTA per SM, one accumulator
+    pl->qstages = (o.qstages >= 2 && o.qstages <= rs::fused_wide_slots() - 2) ? o.qstages : 2;  // Q k-chunks come from L2 (short
+    pl->stages = rs::fused_wide_slots() - pl->qstages;  // latency), document k-chunks from HBM: the ring's 6 slots go 2 : 4
+    pl->nbuf = 1;
+    pl->mma_m = 128;
+    return RS_OK;
+  }
   long long best_cost = -1;
   for (int resident = 1; resident >= 0; --resident) {
     if (o.qresident >= 0 && resident != o.qresident) continue;
@@ -305,6 +338,7 @@ void free_all(rs_index* ix) {
   cudaFree(ix->ingest_dev);
   cudaFree(ix->sync);
   cudaFree(ix->g_best);
+  cudaFree(ix->cbuf);
   cudaFree(ix->debug_ts);
   if (ix->err_flag) cudaFreeHost(ix->err_flag);
   if (ix->pinned) cudaFreeHost(ix->pinned);
@@ -368,26 +402,34 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   }
   // doc-major kernel variant (documents on the MMA's M): half the tensor work and a quarter of the Q-operand reads
   // at B=32; for B <= 32, k <= 16, resident Q (RS_DOCM=0: off; RS_DOCM=2: only one-term 16-bit searches)
-  const bool docm = pl.q_resident == 1 && (o.docm == 1 ? true : (terms == 1 && ix->planes == 1)) &&
+  const bool docm = !pl.wide && pl.q_resident == 1 && (o.docm == 1 ? true : (terms == 1 && ix->planes == 1)) &&
                     k <= rs::fused_reg_k() && pl.bpad <= 32 && pl.sub == 1 && o.docm != 0 &&
                     rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, 1, pl.qstages, pl.bufc, pl.lg, 1) <= kMaxSmem;
   if (docm) pl.nbuf = 8;
-  const int n_work = std::min(ix->sm_count, ix->n_tiles);  // CTAs that own tiles = candidate lists per query
+  // CTAs that own tiles.  Pair kernel: both CTAs of every pair that owns a supertile (two tiles)
+  const int n_work = pl.wide == 2 ? 2 * std::min(ix->pair_clusters, (ix->n_tiles + 1) / 2) : std::min(ix->sm_count, ix->n_tiles);
+  const int n_lists = pl.wide == 2 ? n_work / 2 : n_work;  // candidate lists per query
   // single-launch search (default): query prep in the fused kernel's prologue (resident-Q plans) and the
   // candidate merge (+ exchange) in its tail.  RS_INLINE_PREP=0 / RS_FUSED_TAIL=0 fall back to the
   // separate query_prep_kernel / merge kernels.
-  const bool inline_prep = pl.q_resident == 1 && ix->cfg.dim <= 1024 && pl.bpad <= 32 && o.inline_prep != 0;
-  const int tail_cap = rs::fused_tail_smem_capacity(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, pl.qstages);
-  const bool fused_tail = o.fused_tail != 0 && rs::fused_tail_smem_bytes(n_work, k, xg ? xg->world : 1) <= (size_t)tail_cap;
-  const int grid = fused_tail ? std::max(n_work, std::min(pl.per_pass, ix->sm_count)) : n_work;
+  const bool inline_prep = !pl.wide && pl.q_resident == 1 && ix->cfg.dim <= 1024 && pl.bpad <= 32 && o.inline_prep != 0;
+  const int tail_cap = pl.wide == 2 ? rs::fused_pair_tail_capacity(k) : pl.wide ? rs::fused_wide_tail_capacity(k)
+                               : rs::fused_tail_smem_capacity(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, pl.qstages);
+  const bool fused_tail = o.fused_tail != 0 && rs::fused_tail_smem_bytes(n_lists, k, xg ? xg->world : 1) <= (size_t)tail_cap;
+  // pair kernel: whole pairs; every resident pair when the tail needs merging CTAs for up to 256 queries
+  const int grid = pl.wide == 2 ? (fused_tail ? 2 * ix->pair_clusters : n_work)
+                                : fused_tail ? std::max(n_work, std::min(pl.per_pass, ix->sm_count)) : n_work;
   // overlapped launches (RS_OVERLAP=1): the scan of this search may run while the previous search's tail drains.
   // Only for plans that touch no shared workspace before the tail (register lists, Q image built in shared memory).
   const bool pdl = o.overlap != 0 && !ix->capturing && inline_prep && fused_tail && pl.passes == 1 &&
                    k <= rs::fused_reg_k() && !o.debug_ts;
-  const bool shared_bound = k > rs::fused_reg_k() && n_work >= k && o.shared_bound != 0;
+  // bound shared between CTAs: needs (lists x published rank) >= k documents known to reach it
+  const int bound_rank = pl.wide == 2 && n_lists < k ? 2 : 1;
+  const bool shared_bound = (k > rs::fused_reg_k() || pl.wide) && n_lists * bound_rank >= k && o.shared_bound != 0;
   ix->stats.grid = grid;
   ix->stats.stages = pl.stages;
-  ix->stats.smem_bytes = rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, pl.qstages, pl.bufc, pl.lg, docm);
+  ix->stats.smem_bytes = pl.wide == 2 ? rs::fused_pair_smem_bytes(k) : pl.wide ? rs::fused_wide_smem_bytes(k)
+                                 : rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, pl.qstages, pl.bufc, pl.lg, docm);
   ix->stats.q_resident = pl.q_resident;
   ix->stats.sub = pl.sub;
   ix->stats.nbuf = pl.nbuf;
@@ -416,6 +458,8 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.inline_prep = inline_prep ? 1 : 0;
     p.corpus_scale_exp = corpus_scale_exp;
     p.n_work = n_work;
+    p.n_lists = n_lists;
+    p.bound_rank = bound_rank;
     p.tail_mode = fused_tail ? (xg ? 2 : 1) : 0;
     p.pdl = pdl ? (grid == ix->sm_count && n_work == grid ? 2 : 1) : 0;
     ix->launch_parity ^= 1u;
@@ -428,7 +472,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.idx_offset = ix->cfg.row_offset;
     if (shared_bound) {
       // 0xff bytes = NaN = "this CTA has not published a score for this query yet"
-      RS_CUDA(cudaMemsetAsync(ix->g_best, 0xff, (size_t)n_work * pl.bpad * sizeof(float), stream));
+      RS_CUDA(cudaMemsetAsync(ix->g_best, 0xff, (size_t)n_lists * pl.bpad * sizeof(float), stream));
       p.g_best = ix->g_best;
     }
     if (o.debug_ts) {
@@ -459,6 +503,8 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.bufc = pl.bufc;
     p.lists_global = pl.lg;
     p.docm = docm ? 1 : 0;
+    p.wide = pl.wide;
+    p.cbuf = reinterpret_cast<uint2*>(ix->cbuf);
     p.qstages = pl.qstages;
     p.q_resident = pl.q_resident;
     p.sub = pl.sub;
@@ -482,11 +528,11 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     }
     if (!fused_tail) {
       if (!xg) {
-        RS_CUDA(rs::launch_merge_i32(ix->cand_score, ix->cand_idx, n_work, nb, k, k, ix->cfg.row_offset,
+        RS_CUDA(rs::launch_merge_i32(ix->cand_score, ix->cand_idx, n_lists, nb, k, k, ix->cfg.row_offset,
                                      out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, stream));
       } else {
         // local merge + exchange + final merge in one kernel: rows go straight into every GPU's buffer
-        RS_CUDA(rs::launch_exchange_merge(ix->cand_score, ix->cand_idx, n_work, nb, k, ix->cfg.row_offset,
+        RS_CUDA(rs::launch_exchange_merge(ix->cand_score, ix->cand_idx, n_lists, nb, k, ix->cfg.row_offset,
                                           out_score + (size_t)b0 * k, out_idx + (size_t)b0 * k, ea, ix->err_flag, stream));
       }
     }
@@ -617,7 +663,7 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
     delete ix;
     return fail(RS_E_UNSUPPORTED, "dim=%d does not fit the shared-memory pipeline", cfg->dim);
   }
-  const size_t pass_rows = 128;
+  const size_t pass_rows = 256;  // queries per fused launch: up to 128 (general kernel) or 256 (wide kernel)
   const size_t qimg_bytes = (size_t)2 * ix->kc * pass_rows * RS_KCHUNK_BYTES;
   const size_t cand_elems = (size_t)grid * pass_rows * cfg->max_k;
   const size_t q_bytes = (size_t)cfg->max_batch * cfg->dim * sizeof(float);
@@ -652,7 +698,11 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   RS_ALLOC(cudaMalloc(&ix->out_idx_dev, out_elems * (sizeof(long long) + sizeof(float))));
   RS_ALLOC(cudaMalloc(&ix->ingest_dev, kIngestChunkBytes));
   RS_ALLOC(cudaHostAlloc(&ix->pinned, ix->pinned_bytes, cudaHostAllocPortable));
-  RS_ALLOC(cudaMalloc(&ix->g_best, (size_t)prop.multiProcessorCount * 128 * sizeof(float)));
+  RS_ALLOC(cudaMalloc(&ix->g_best, (size_t)prop.multiProcessorCount * pass_rows * sizeof(float)));
+  if (cfg->max_batch > 128) {
+    RS_ALLOC(cudaMalloc(&ix->cbuf, (size_t)grid * pass_rows * rs::fused_wide_bufc() * sizeof(uint2)));
+    ix->pair_clusters = ix->planes == 1 ? std::min(rs::fused_pair_max_clusters(cfg->max_k), prop.multiProcessorCount / 2) : 0;
+  }
   RS_ALLOC(cudaMalloc(&ix->sync, 512));
   RS_ALLOC(cudaMemsetAsync(ix->sync, 0, 512, ix->stream));
   RS_ALLOC(cudaEventCreateWithFlags(&ix->order_ev, cudaEventDisableTiming));

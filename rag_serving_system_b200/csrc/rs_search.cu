@@ -361,10 +361,10 @@ __device__ __forceinline__ float cosine_raw_bound(float thr_cos, float nq, float
 // All four pointers address ONE query's arrays (unit stride).  Candidate scores are multiplied by `scale` (an
 // exact power of two, or 1) on the way in, so a list may be kept in final units while the filter runs in raw
 // accumulator units; the returned k-th best is in list units.
-__device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs, const int* Bi, int n, int k, int lane,
-                                                  float scale = 1.0f) {
-  float cs = lane < n ? Bs[lane] * scale : -CUDART_INF_F;
-  int ci = lane < n ? Bi[lane] : 0x7fffffff;
+// merge_sorted_candidates: the same merge with the (at most 32) candidates handed in as registers, one per lane
+// (lanes >= n: (-inf, 0x7fffffff)); Bs is a 32-float scratch for the sorted candidate scores.
+__device__ __forceinline__ float merge_sorted_candidates(float* Ls, int* Li, float* Bs, float cs, int ci, int n, int k,
+                                                         int lane) {
 #pragma unroll
   for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
@@ -422,6 +422,12 @@ __device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs,
   }
   __syncwarp();
   return Ls[k - 1];
+}
+__device__ __forceinline__ float flush_candidates(float* Ls, int* Li, float* Bs, const int* Bi, int n, int k, int lane,
+                                                  float scale = 1.0f) {
+  const float cs = lane < n ? Bs[lane] * scale : -CUDART_INF_F;
+  const int ci = lane < n ? Bi[lane] : 0x7fffffff;
+  return merge_sorted_candidates(Ls, Li, Bs, cs, ci, n, k, lane);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -800,6 +806,59 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
   return v;
 }
 
+// ===================== tail of a fused search: candidate merge (+ multi-GPU exchange) inside the same launch ====
+// Called by every thread of every CTA once the CTA's candidate lists are in cand_* (and fenced).
+__device__ __forceinline__ void fused_tail(const SearchParams& p, uint8_t* smem, const bool worker) {
+  // Worker CTAs publish their lists and arrive on a device counter; CTA q (q < n_queries) waits for all
+  // n_work arrivals, merges query q's lists out of L2 (ring/Q shared memory is free by now) and - multi-GPU
+  // - exchanges the row with the peer GPUs and merges the world lists.  Every CTA of the grid is resident
+  // (grid <= SM count, one CTA per SM), so the wait cannot starve a CTA that has not started.  The last
+  // merging CTA to leave resets the counters for the launch after the next one (launches on one index are
+  // stream-ordered and alternate between two counter blocks).
+  if (p.tail_mode != 0) {
+    if (threadIdx.x == 0 && worker) {
+      __threadfence();
+      atomicAdd(p.sync, 1u);
+      stamp(p.debug_ts, 4);  // candidates published, arrived
+    }
+    if ((int)blockIdx.x < p.n_queries) {
+      if (threadIdx.x == 0) {
+        long long spins = 0;
+        while (ld_acquire_gpu_u32(p.sync) < (unsigned int)p.n_work) {
+          __nanosleep(40);
+          if (++spins > (1ll << 24)) {  // ~1 s: a CTA of this grid never ran; flag it instead of hanging the GPU
+            *reinterpret_cast<volatile unsigned int*>(p.err_flag) = 1u;  // mapped host memory
+            break;
+          }
+        }
+        __threadfence();
+        stamp(p.debug_ts, 5);  // every worker CTA has arrived
+      }
+      __syncthreads();
+      const MergeSmem m = merge_smem_at(smem, p.k);
+      for (int q = blockIdx.x; q < ((p.debug_flags & 4) ? 0 : p.n_queries); q += gridDim.x) {
+        merge_query_local(p.cand_score, p.cand_idx, p.n_lists, p.k, p.idx_offset, q, m, kThreads, p.debug_ts);
+        if (p.tail_mode == 2) exchange_query(p.x, q, p.k, m, kThreads, p.err_flag);
+        for (int j = threadIdx.x; j < p.k; j += kThreads) {
+          p.out_score[(size_t)q * p.k + j] = m.res_s[j];
+          p.out_idx[(size_t)q * p.k + j] = m.res_i[j];
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {
+        stamp(p.debug_ts, 6);  // this CTA's queries merged and written
+        const unsigned int mergers = (unsigned int)min((int)gridDim.x, p.n_queries);
+        if (atomicAdd(p.sync + 1, 1u) == mergers - 1u) {
+          atomicExch(p.sync, 0u);
+          atomicExch(p.sync + 1, 0u);
+          atomicExch(p.sync + 4, 0u);  // tile counter of the dynamic scheduler
+          if (p.tail_mode == 2 && p.x.last_pass) bump_epoch(p.x.epoch);  // every query of this search is exchanged
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Doc-major variant (B <= 32, k <= 16, resident Q; any storage type, one or two query terms, dot or cosine): DOCUMENTS are the
 // MMA's M (128 per tile, one TMEM lane each) and the QUERIES its N (16 or 32 columns).  Against the
@@ -955,7 +1014,7 @@ __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars&
 // is outermost: for every 64-element k-chunk the (optional) Q blocks arrive once and are reused
 // by the MMAs of all p.sub document blocks, each accumulating into its own TMEM columns.
 template <int NACC, bool REGLIST, bool QRES, bool DOCM = false>
-__global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const __grid_constant__ SearchParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned shared memory; the launcher over-allocates by 1 KiB
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -1587,55 +1646,868 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const SearchP
     }
     __syncthreads();
   }
-  // ===================== tail: candidate merge (+ multi-GPU exchange) inside the same launch ============
-  // Worker CTAs publish their lists and arrive on a device counter; CTA q (q < n_queries) waits for all
-  // n_work arrivals, merges query q's lists out of L2 (ring/Q shared memory is free by now) and - multi-GPU
-  // - exchanges the row with the peer GPUs and merges the world lists.  Every CTA of the grid is resident
-  // (grid <= SM count, one CTA per SM), so the wait cannot starve a CTA that has not started.  The last
-  // merging CTA to leave resets the counters for the launch after the next one (launches on one index are
-  // stream-ordered and alternate between two counter blocks).
-  if (p.tail_mode != 0) {
-    if (threadIdx.x == 0 && worker) {
-      __threadfence();
-      atomicAdd(p.sync, 1u);
-      stamp(p.debug_ts, 4);  // candidates published, arrived
+  fused_tail(p, smem, worker);
+}
+
+// ==========================================================================================
+// Wide-batch variant: 128 < B <= 256 queries share ONE pass over the shard (one query term, 16-bit storage;
+// BASELINE config 5: B=256, k=100, the tensor-bound regime).  Query-major like the general kernel, but
+//   * the batch is two HALVES of 128 query rows.  Both halves multiply the same document blocks: a document
+//     block is read from HBM once and stays in shared memory for the two MMA chains (the two-pass plan read
+//     the shard twice);
+//   * documents travel as tile PAIRS: a ring stage holds the same k-chunk of two consecutive tiles back to back
+//     (256 rows, 32 KiB), which is exactly one N=256 K-major SWIZZLE_128B operand, so one M=128 x N=256 MMA per
+//     16 k-elements and half replaces four M=128 x N=128 ones (12 KiB of operand reads per 128 tensor cycles
+//     instead of 8 KiB per 64);
+//   * Q k-chunks (256 rows x 64 columns = 32 KiB) stream through a ring of 3 slots - one slot is reused by both
+//     tiles of the pair - so the L2->SM traffic of Q equals the document traffic instead of twice it;
+//   * TMEM: [half][tile of the pair][128 columns] = all 512 columns, single-buffered.  The epilogue therefore
+//     only FILTERS while it holds the accumulator (scores -> threshold compare -> passing candidates appended to
+//     a per-(query, CTA) buffer); the expensive part - merging a full buffer into the query's sorted list - is
+//     deferred until the accumulator is back with the MMA warp and overlaps the next supertile's MMAs;
+//   * selection state lives in global memory (L2): the sorted lists are the per-CTA candidate arrays the tail
+//     merges anyway (cand_*, final units), the 32-entry candidate buffers are cbuf.  Shared memory is all ring.
+// An epilogue thread owns query rows r and 128 + r.  Prologue (query_prep_kernel, bpad = 256) and tail (merge,
+// exchange) are the general kernel's.
+// ==========================================================================================
+constexpr int kWideSlots = 6;      // 32 KiB ring slots in all: p.qstages of them hold Q k-chunks, p.stages document k-chunks
+constexpr int kWideBufC = 32;     // candidate-buffer entries per (query, CTA)
+constexpr int kWideFlushAt = 20;  // deferred flush once a buffer holds this many (a full one is flushed on the spot)
+constexpr uint32_t kWideSlotBytes = 2u * RS_BLOCK_BYTES;  // 32 KiB
+
+struct WideSmem {
+  uint32_t q_off, d_off, bar_off, dump_off, scratch_off, total;
+};
+__host__ __device__ inline WideSmem make_wide_smem(int k, int qslots = 2) {
+  WideSmem m;
+  m.q_off = 0;
+  m.d_off = (uint32_t)qslots * kWideSlotBytes;
+  m.bar_off = (uint32_t)kWideSlots * kWideSlotBytes;
+  m.dump_off = m.bar_off + 1024u;                                 // barriers, scheduler queue, TMEM address
+  m.scratch_off = m.dump_off + 4u * 32u * 32u * 4u;               // rare-path chunk per warp: [32 columns][32 lanes]
+  m.total = m.scratch_off + 4u * (2u * (uint32_t)k + 64u) * 4u;   // per warp: list scores k, list ids k, 32 sorted candidates
+  return m;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) fused_search_wide_kernel(const __grid_constant__ SearchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kWideQSlots = p.qstages, kWideDStages = p.stages;  // kWideQSlots + kWideDStages == kWideSlots
+  const WideSmem map = make_wide_smem(p.k, kWideQSlots);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t q_smem = smem_base + map.q_off, d_smem = smem_base + map.d_off, bar_base = smem_base + map.bar_off;
+  auto dfull = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto dempty = [&](int s) { return bar_base + 8u * (uint32_t)(kWideDStages + s); };
+  auto qfull = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kWideDStages + s); };
+  auto qempty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kWideDStages + kWideQSlots + s); };
+  const uint32_t tfull = bar_base + 8u * (uint32_t)(2 * kWideSlots);
+  const uint32_t tempty = tfull + 8u;
+  constexpr int kSched = 8;
+  auto sched_full = [&](int s) { return tempty + 8u + 8u * (uint32_t)s; };
+  auto sched_empty = [&](int s) { return tempty + 8u + 8u * (uint32_t)(kSched + s); };
+  volatile int* tile_u = reinterpret_cast<volatile int*>(smem + map.bar_off + 512);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + map.bar_off + 512 + 4 * kSched);
+  const bool worker = (int)blockIdx.x < p.n_work;
+  const int n_super = (p.n_tiles + 1) / 2;
+  const size_t tile_bytes = (size_t)p.kc * RS_BLOCK_BYTES;
+  constexpr uint32_t kTmemCols = 512;
+
+  if (threadIdx.x == 0) {
+    stamp(p.debug_ts, 0);
+    for (int s = 0; s < kWideDStages; ++s) {
+      mbar_init(dfull(s), 1);
+      mbar_init(dempty(s), 1);
     }
-    if ((int)blockIdx.x < p.n_queries) {
-      if (threadIdx.x == 0) {
-        long long spins = 0;
-        while (ld_acquire_gpu_u32(p.sync) < (unsigned int)p.n_work) {
-          __nanosleep(40);
-          if (++spins > (1ll << 24)) {  // ~1 s: a CTA of this grid never ran; flag it instead of hanging the GPU
-            *reinterpret_cast<volatile unsigned int*>(p.err_flag) = 1u;  // mapped host memory
-            break;
+    for (int s = 0; s < kWideQSlots; ++s) {
+      mbar_init(qfull(s), 1);
+      mbar_init(qempty(s), 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, kNumEpiWarps);
+    for (int s = 0; s < kSched; ++s) {
+      mbar_init(sched_full(s), 1);
+      mbar_init(sched_empty(s), 1 + kNumEpiWarps);
+    }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(smem_u32((const void*)tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    // ===================== bulk-copy producer + dynamic scheduler =====================
+    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_keep = l2_policy_evict_last();
+    int ds = 0, qs = 0, sslot = 0;
+    uint32_t dph = 0, qph = 0, sph = 0;
+    int u = (worker && (int)blockIdx.x < n_super) ? (int)blockIdx.x : -1;
+    while (true) {
+      mbar_wait(sched_empty(sslot), sph ^ 1u);
+      if (lane == 0) {
+        tile_u[sslot] = u;
+        mbar_arrive(sched_full(sslot));
+      }
+      if (++sslot == kSched) {
+        sslot = 0;
+        sph ^= 1u;
+      }
+      if (u < 0) break;
+      int nxt = u + (int)gridDim.x;
+      if (p.dyn_sched && lane == 0) nxt = (int)atomicAdd(p.sync + 4, 1u) + (int)gridDim.x;
+      const int nsub = min(2, p.n_tiles - 2 * u);
+      const uint8_t* src = p.corpus + (size_t)u * 2 * tile_bytes;
+      for (int kc = 0; kc < p.kc; ++kc) {
+        mbar_wait(qempty(qs), qph ^ 1u);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(qfull(qs), kWideSlotBytes);
+          bulk_g2s(q_smem + (uint32_t)qs * kWideSlotBytes, p.qimg + (size_t)kc * kWideSlotBytes, kWideSlotBytes, qfull(qs), pol_keep);
+        }
+        if (++qs == kWideQSlots) {
+          qs = 0;
+          qph ^= 1u;
+        }
+        mbar_wait(dempty(ds), dph ^ 1u);
+        if (lane == 0) {
+          const uint32_t dst = d_smem + (uint32_t)ds * kWideSlotBytes;
+          mbar_arrive_expect_tx(dfull(ds), (uint32_t)nsub * RS_BLOCK_BYTES);
+          bulk_g2s(dst, src + (size_t)kc * RS_BLOCK_BYTES, RS_BLOCK_BYTES, dfull(ds), pol_stream);
+          if (nsub == 2) bulk_g2s(dst + RS_BLOCK_BYTES, src + tile_bytes + (size_t)kc * RS_BLOCK_BYTES, RS_BLOCK_BYTES, dfull(ds), pol_stream);
+        }
+        if (++ds == kWideDStages) {
+          ds = 0;
+          dph ^= 1u;
+        }
+      }
+      nxt = __shfl_sync(0xffffffffu, nxt, 0);
+      u = nxt < n_super ? nxt : -1;
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer: per k-chunk 2 halves x 4 MMAs of M=128 x N=256 x K=16 =====================
+    const uint32_t idesc = umma_idesc_f16(p.dtype == RS_DTYPE_BF16, 128, 256);
+    const bool skip_mma = (p.debug_flags & 1) != 0;
+    int ds = 0, qs = 0, sslot = 0;
+    uint32_t dph = 0, qph = 0, sph = 0, acc_ph = 0;
+    while (true) {
+      mbar_wait(sched_full(sslot), sph);
+      const int u = tile_u[sslot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sched_empty(sslot));
+      if (++sslot == kSched) {
+        sslot = 0;
+        sph ^= 1u;
+      }
+      if (u < 0) break;
+      mbar_wait(tempty, acc_ph ^ 1u);
+      tc_fence_after();
+      for (int kc = 0; kc < p.kc; ++kc) {
+        mbar_wait(qfull(qs), qph);
+        mbar_wait(dfull(ds), dph);
+        tc_fence_after();
+        if (lane == 0 && !skip_mma) {
+          const uint32_t qa = q_smem + (uint32_t)qs * kWideSlotBytes;
+          const uint64_t a0 = umma_smem_desc(qa), a1 = umma_smem_desc(qa + RS_BLOCK_BYTES);
+          const uint64_t b = umma_smem_desc(d_smem + (uint32_t)ds * kWideSlotBytes);
+#pragma unroll
+          for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
+            umma_f16(tmem_base, a0 + 2u * ks, b + 2u * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+#pragma unroll
+          for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
+            umma_f16(tmem_base + 256u, a1 + 2u * ks, b + 2u * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          umma_commit(dempty(ds));
+          umma_commit(qempty(qs));
+        }
+        if (++ds == kWideDStages) {
+          ds = 0;
+          dph ^= 1u;
+        }
+        if (++qs == kWideQSlots) {
+          qs = 0;
+          qph ^= 1u;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) umma_commit(tfull);
+      acc_ph ^= 1u;
+    }
+  } else {
+    // ===================== epilogue: a thread owns query rows r and 128 + r =====================
+    const int quarter = warp & 3;
+    const int k = p.k;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool cosine = p.metric == RS_METRIC_COSINE;
+    int row[2];
+    bool live[2];
+    float qs[2], inv_qs[2], nq[2], thr[2], thr_raw[2], best_seen[2], gbound[2];
+    int cnt[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      row[h] = h * 128 + quarter * 32 + lane;
+      live[h] = row[h] < p.n_queries;
+      qs[h] = live[h] ? p.qscale[row[h]] : 1.f;
+      inv_qs[h] = 1.0f / qs[h];
+      nq[h] = live[h] ? p.qnorm[row[h]] : 0.f;
+      thr[h] = live[h] ? -CUDART_INF_F : CUDART_INF_F;
+      thr_raw[h] = thr[h];
+      best_seen[h] = -CUDART_INF_F;
+      gbound[h] = -CUDART_INF_F;
+      cnt[h] = 0;
+    }
+    float* dump = reinterpret_cast<float*>(smem + map.dump_off) + (size_t)quarter * 32 * 32;
+    float* Ws = reinterpret_cast<float*>(smem + map.scratch_off) + (size_t)quarter * (2 * k + 64);
+    int* Wi = reinterpret_cast<int*>(Ws + k);
+    float* Bs = Ws + 2 * k;
+    auto glist_s = [&](int qrow) { return p.cand_score + ((size_t)qrow * p.n_work + blockIdx.x) * k; };
+    auto glist_i = [&](int qrow) { return p.cand_idx + ((size_t)qrow * p.n_work + blockIdx.x) * k; };
+    auto gbuf = [&](int qrow) { return p.cbuf + ((size_t)qrow * p.n_work + blockIdx.x) * kWideBufC; };
+    if (worker) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (live[h]) {
+          float* l0 = glist_s(row[h]);
+          int* i0 = glist_i(row[h]);
+          for (int j = 0; j < k; ++j) {
+            l0[j] = -CUDART_INF_F;
+            i0[j] = -1;
           }
         }
-        __threadfence();
-        stamp(p.debug_ts, 5);  // every worker CTA has arrived
+    }
+    __syncwarp();
+    const bool shared_bound = p.g_best != nullptr && worker;
+    int tiles_done = 0, next_refresh = 1;
+    // merge query ql (of half h) of this warp: its n buffered candidates -> its sorted list; returns the new k-th
+    // best in FILTER units (raw accumulator units for dot).  Whole warp, converged.
+    auto flush_query = [&](const float qs_h, const float inv_qs_h, int h, int ql, int n) -> float {
+      const int qrow = h * 128 + quarter * 32 + ql;
+      const float unit = cosine ? 1.0f : __shfl_sync(0xffffffffu, qs_h, ql);  // list units = final units
+      float* gs = glist_s(qrow);
+      int* gi = glist_i(qrow);
+      float cs = -CUDART_INF_F;
+      int ci = 0x7fffffff;
+      if (lane < n) {
+        const uint2 c = __ldcg(gbuf(qrow) + lane);
+        cs = __uint_as_float(c.x) * unit;
+        ci = (int)c.y;
       }
-      __syncthreads();
-      const MergeSmem m = merge_smem_at(smem, p.k);
-      for (int q = blockIdx.x; q < ((p.debug_flags & 4) ? 0 : p.n_queries); q += gridDim.x) {
-        merge_query_local(p.cand_score, p.cand_idx, p.n_work, p.k, p.idx_offset, q, m, kThreads, p.debug_ts);
-        if (p.tail_mode == 2) exchange_query(p.x, q, p.k, m, kThreads, p.err_flag);
-        for (int j = threadIdx.x; j < p.k; j += kThreads) {
-          p.out_score[(size_t)q * p.k + j] = m.res_s[j];
-          p.out_idx[(size_t)q * p.k + j] = m.res_i[j];
-        }
-        __syncthreads();
+      for (int j = lane; j < k; j += 32) {
+        Ws[j] = __ldcg(gs + j);
+        Wi[j] = __ldcg(gi + j);
       }
-      if (threadIdx.x == 0) {
-        stamp(p.debug_ts, 6);  // this CTA's queries merged and written
-        const unsigned int mergers = (unsigned int)min((int)gridDim.x, p.n_queries);
-        if (atomicAdd(p.sync + 1, 1u) == mergers - 1u) {
-          atomicExch(p.sync, 0u);
-          atomicExch(p.sync + 1, 0u);
-          atomicExch(p.sync + 4, 0u);  // tile counter of the dynamic scheduler
-          if (p.tail_mode == 2 && p.x.last_pass) bump_epoch(p.x.epoch);  // every query of this search is exchanged
+      __syncwarp();
+      const float nt = merge_sorted_candidates(Ws, Wi, Bs, cs, ci, n, k, lane);
+      for (int j = lane; j < k; j += 32) {
+        __stcg(gs + j, Ws[j]);
+        __stcg(gi + j, Wi[j]);
+      }
+      __syncwarp();
+      if (p.debug_ts && lane == 0) atomicAdd(p.debug_ts + (size_t)blockIdx.x * 8 + 7, 1ull << 32);  // flushes
+      return cosine ? nt : nt * __shfl_sync(0xffffffffu, inv_qs_h, ql);  // exact: qs is a power of two
+    };
+
+    int sslot = 0;
+    uint32_t sph = 0, acc_ph = 0;
+    // RS_DEBUG_TS: cycles this warp spent waiting for an accumulator / holding it / merging afterwards (slots 1-3)
+    const bool prof = p.debug_ts != nullptr && threadIdx.x == kFirstEpiWarp * 32;
+    long long t_wait = 0, t_hold = 0, t_merge = 0, tc0 = 0, tc1 = 0, tc2 = 0;
+    while (true) {
+      mbar_wait(sched_full(sslot), sph);
+      const int u = tile_u[sslot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sched_empty(sslot));
+      if (++sslot == kSched) {
+        sslot = 0;
+        sph ^= 1u;
+      }
+      if (u < 0) break;
+      const int nsub = min(2, p.n_tiles - 2 * u);
+      if (prof) tc0 = clock64();
+      mbar_wait(tfull, acc_ph);
+      tc_fence_after();
+      if (prof) tc1 = clock64();
+      if (shared_bound && tiles_done >= next_refresh) {  // after 1, 2, 4, ... tiles, then every 64 (see the general kernel)
+        next_refresh = tiles_done < 64 ? 2 * tiles_done : tiles_done + 64;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (live[h]) {
+            float mn = CUDART_INF_F;
+#pragma unroll 8
+            for (int c = 0; c < p.n_work; ++c) {
+              const float v = __ldcg(p.g_best + (size_t)c * p.bpad + row[h]);
+              mn = fminf(mn, v == v ? v : -CUDART_INF_F);  // NaN = that CTA has not published yet
+            }
+            if (mn > -CUDART_INF_F && mn < CUDART_INF_F) {
+              gbound[h] = __uint_as_float(__float_as_uint(mn) + (mn > 0.f ? -1 : (mn < 0.f ? 1 : 0)));  // next float below
+              if (mn == 0.f) gbound[h] = -1.401298464e-45f;
+              if (gbound[h] > thr[h]) {
+                thr[h] = gbound[h];
+                thr_raw[h] = cosine ? CUDART_INF_F : thr[h];  // cosine: recomputed per tile just below
+              }
+            }
+          }
         }
+      }
+      tiles_done += nsub;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h * 128 + quarter * 32 >= p.n_queries || (p.debug_flags & 2)) continue;  // no live row of this warp in the half
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int t = 2 * u + sub;
+          float ndmin = 1.f, ndmax = 1.f;
+          if (cosine) {
+            const float2 mm = p.tile_norm_minmax[t];
+            ndmin = mm.x;
+            ndmax = mm.y;
+            thr_raw[h] = live[h] ? cosine_raw_bound(thr[h], nq[h], inv_qs[h], ndmin, ndmax) : CUDART_INF_F;
+          }
+          const uint32_t tacc = lane_base + (uint32_t)(h * 256 + sub * 128);
+          const int tile_row0 = t * RS_TILE_ROWS;
+#pragma unroll 1
+          for (int c0 = 0; c0 < RS_TILE_ROWS; c0 += 32) {
+            float v[32];
+            {
+              uint32_t r0[32];
+              tmem_ld_x32(tacc + c0, r0);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+            }
+            const float m = max32(v);
+            if (__any_sync(0xffffffffu, m > thr_raw[h])) {
+              uint32_t pm = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                pm |= (v[j] > thr_raw[h]) ? (1u << j) : 0u;
+                dump[j * 32 + lane] = v[j];
+              }
+              if (tile_row0 + c0 + 32 > p.n_rows) {  // ragged last tile: mask padded rows
+                const int valid = p.n_rows - (tile_row0 + c0);
+                pm = valid <= 0 ? 0u : (pm & (0xffffffffu >> (32 - valid)));
+              }
+              __syncwarp();
+              while (__any_sync(0xffffffffu, pm != 0u)) {
+                if (pm != 0u) {
+                  const int j = __ffs(pm) - 1;
+                  pm &= pm - 1;
+                  const float s = dump[j * 32 + lane];
+                  const int idx = tile_row0 + c0 + j;
+                  float x = s;  // dot: compare and buffer raw units (exact power-of-two scale)
+                  if (cosine) {
+                    const float nd = p.dnorm[idx];
+                    const float denom = __fadd_rn(__fmul_rn(nq[h], nd), 1e-8f);  // retriever.py:605,607
+                    x = __fdiv_rn(s * qs[h], denom);
+                    x = fminf(fmaxf(x, -1.0f), 1.0f);                            // retriever.py:609
+                  }
+                  if (x > thr[h]) {
+                    __stcg(gbuf(row[h]) + cnt[h], make_uint2(__float_as_uint(x), (unsigned int)idx));
+                    ++cnt[h];
+                    if (p.debug_ts) atomicAdd(p.debug_ts + (size_t)blockIdx.x * 8 + 7, 1ull);  // appends (low word)
+                    if (shared_bound && x > best_seen[h]) {
+                      best_seen[h] = x;
+                      __stcg(p.g_best + (size_t)blockIdx.x * p.bpad + row[h], x);
+                    }
+                  }
+                }
+                uint32_t full = __ballot_sync(0xffffffffu, cnt[h] == kWideBufC);  // (rare: flushes normally happen below)
+                while (full) {
+                  const int ql = __ffs(full) - 1;
+                  full &= full - 1;
+                  const float nt = flush_query(qs[h], inv_qs[h], h, ql, kWideBufC);
+                  if (lane == ql) {
+                    thr[h] = fmaxf(nt, gbound[h]);
+                    cnt[h] = 0;
+                    thr_raw[h] = cosine ? cosine_raw_bound(thr[h], nq[h], inv_qs[h], ndmin, ndmax) : thr[h];
+                  }
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+      // every TMEM read of this supertile is complete (wait::ld above): hand the accumulator back, THEN merge
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+      acc_ph ^= 1u;
+      if (prof) tc2 = clock64();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t due = __ballot_sync(0xffffffffu, cnt[h] >= kWideFlushAt);
+        while (due) {
+          const int ql = __ffs(due) - 1;
+          due &= due - 1;
+          const int n = __shfl_sync(0xffffffffu, cnt[h], ql);
+          const float nt = flush_query(qs[h], inv_qs[h], h, ql, n);
+          if (lane == ql) {
+            thr[h] = fmaxf(nt, gbound[h]);
+            cnt[h] = 0;
+            thr_raw[h] = cosine ? CUDART_INF_F : thr[h];  // cosine: recomputed per tile
+          }
+        }
+      }
+      if (prof) {
+        t_wait += tc1 - tc0;
+        t_hold += tc2 - tc1;
+        t_merge += clock64() - tc2;
+      }
+    }
+    if (prof) {
+      p.debug_ts[(size_t)blockIdx.x * 8 + 1] = (unsigned long long)t_wait;
+      p.debug_ts[(size_t)blockIdx.x * 8 + 2] = (unsigned long long)t_hold;
+      p.debug_ts[(size_t)blockIdx.x * 8 + 3] = (unsigned long long)t_merge;
+    }
+    // drain the partially filled buffers; the lists already sit in cand_* in final units
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t rem = __ballot_sync(0xffffffffu, cnt[h] > 0);
+      while (rem) {
+        const int ql = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const int n = __shfl_sync(0xffffffffu, cnt[h], ql);
+        flush_query(qs[h], inv_qs[h], h, ql, n);
       }
     }
   }
+
+  if (p.tail_mode != 0) __threadfence();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+  fused_tail(p, smem, worker);
+}
+
+// ==========================================================================================
+// CTA-pair variant of the wide-batch kernel (the default for 128 < B <= 256 per pass): the two SMs of a TPC run
+// as a thread-block cluster of 2 and share ONE document stream through tcgen05.mma.cta_group::2.
+//   * CTA rank r of a pair owns query rows 128r .. 128r+127 (its half of the MMA's M = 256) and loads ONE tile
+//     of the pair's supertile (tiles 2u and 2u+1 = the two halves of the MMA's N = 256): per k-chunk a CTA
+//     brings 16 KiB of documents from HBM and 16 KiB of its own query rows from L2 into one 32 KiB ring slot;
+//     the tensor cores read the other CTA's document half through the pair link.  L2->SM traffic of Q equals the
+//     document traffic, as in the single-CTA wide kernel.
+//   * One thread of the leader (rank 0) issues M=256 x N=256 x K=16 MMAs (128 tensor cycles each, the full rate
+//     of both SMs; 8 KiB of shared-memory operand reads per CTA per MMA = half the limit).  Each CTA's TMEM
+//     receives ITS 128 query rows x 256 documents = 256 columns, so the 512 columns hold TWO accumulators and
+//     the epilogue of supertile i overlaps the MMAs of supertile i+1 (the single-CTA wide kernel needs all 512
+//     columns for one supertile and serialises the two).
+//   * Barriers: full[s] of the leader counts its own bulk copies AND a relay arrive from the peer's (otherwise
+//     idle) MMA warp once the peer's copies have landed; empty[s] and tfull[b] are signalled in both CTAs by
+//     multicast tcgen05.commit; the epilogue warps of both CTAs arrive on the leader's tempty[b].
+//   * Static schedule: pair P takes supertiles P, P + n_pairs, ... (ascending document order per CTA, which the
+//     tie rule needs).  An odd tile count leaves the last supertile with one tile: rank 1 re-reads tile 2u and
+//     nobody looks at columns 128-255.
+//   * Epilogue: a thread owns ONE query; selection state as in the wide kernel (sorted list in cand_*, 32-entry
+//     candidate buffer in cbuf, both L2-resident; filter while holding the accumulator, merge after releasing
+//     it); TMEM loads are software-pipelined (the next 32 columns are in flight while these are compared).
+//     Candidate lists per query = number of worker pairs (p.n_lists).  Shared bound: a CTA publishes its
+//     bound_rank-th best score (1 or 2), so that bound_rank * n_lists >= k documents are known to reach the bound.
+// Every wait has a watchdog (a few seconds of wall clock, then the error word is raised and the kernel traps):
+// a protocol bug or a lost peer must never hang the GPU.
+// ==========================================================================================
+constexpr int kPairSlots = 6;
+constexpr uint32_t kPairSlotBytes = 2u * RS_BLOCK_BYTES;  // [16 KiB query rows of this CTA][16 KiB documents of this CTA's tile]
+struct PairSmem {
+  uint32_t bar_off, dump_off, scratch_off, total;
+};
+__host__ __device__ inline PairSmem make_pair_smem(int k) {
+  PairSmem m;
+  m.bar_off = (uint32_t)kPairSlots * kPairSlotBytes;
+  m.dump_off = m.bar_off + 1024u;
+  m.scratch_off = m.dump_off + 4u * 32u * 32u * 4u;
+  m.total = m.scratch_off + 4u * (2u * (uint32_t)k + 64u) * 4u;
+  return m;
+}
+
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity, unsigned int* err_flag) {
+  unsigned int polls = 0;
+  unsigned long long t0 = 0;
+  while (!(CLUSTER ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity))) {
+    if ((++polls & 0xfffu) == 0u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) {  // 4 s
+        *reinterpret_cast<volatile unsigned int*>(err_flag) = 3u;
+        __threadfence_system();
+        __trap();
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __grid_constant__ SearchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = (int)blockIdx.x >> 1;
+  const int n_pairs = (int)gridDim.x >> 1;
+  const PairSmem map = make_pair_smem(p.k);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + map.bar_off;
+  auto slot_addr = [&](int s) { return smem_base + (uint32_t)s * kPairSlotBytes; };
+  auto full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty = [&](int s) { return bar_base + 8u * (uint32_t)(kPairSlots + s); };
+  auto tfull = [&](int b) { return bar_base + 8u * (uint32_t)(2 * kPairSlots + b); };
+  auto tempty = [&](int b) { return bar_base + 8u * (uint32_t)(2 * kPairSlots + 2 + b); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + map.bar_off + 512);
+  const int n_super = (p.n_tiles + 1) / 2;
+  const bool worker = pair < n_super && (int)blockIdx.x < p.n_work;
+  const size_t tile_bytes = (size_t)p.kc * RS_BLOCK_BYTES;
+  constexpr uint32_t kTmemCols = 512;
+
+  if (threadIdx.x == 0) {
+    stamp(p.debug_ts, 0);
+    for (int s = 0; s < kPairSlots; ++s) {
+      mbar_init(full(s), rank == 0 ? 2u : 1u);  // leader: its own copies + the peer's relay
+      mbar_init(empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull(b), 1);
+      mbar_init(tempty(b), 2 * kNumEpiWarps);   // used in the leader only: the epilogue warps of both CTAs
+    }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc_pair(smem_u32((const void*)tmem_slot), kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before anybody signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    // ===================== bulk-copy producer (both CTAs) =====================
+    if (worker) {
+      const uint64_t pol_stream = l2_policy_evict_first();
+      const uint64_t pol_keep = l2_policy_evict_last();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int u = pair; u < n_super; u += n_pairs) {
+        const int nsub = min(2, p.n_tiles - 2 * u);
+        const int tile = 2 * u + ((int)rank < nsub ? (int)rank : 0);
+        const uint8_t* dsrc = p.corpus + (size_t)tile * tile_bytes;
+        const uint8_t* qsrc = p.qimg + (size_t)rank * RS_BLOCK_BYTES;
+        for (int kc = 0; kc < p.kc; ++kc) {
+          mbar_wait_guarded<false>(empty(s), ph ^ 1u, p.err_flag);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(full(s), kPairSlotBytes);
+            bulk_g2s(slot_addr(s), qsrc + (size_t)kc * kPairSlotBytes, RS_BLOCK_BYTES, full(s), pol_keep);
+            bulk_g2s(slot_addr(s) + RS_BLOCK_BYTES, dsrc + (size_t)kc * RS_BLOCK_BYTES, RS_BLOCK_BYTES, full(s), pol_stream);
+          }
+          if (++s == kPairSlots) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+      // drain: the last multicast commits must have landed in this CTA's empty barriers before the pair may part
+      for (int i = 0; i < kPairSlots; ++i) {
+        mbar_wait_guarded<false>(empty(s), ph ^ 1u, p.err_flag);
+        if (++s == kPairSlots) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (worker && rank == 0) {
+      // ===================== MMA issuer (leader): per k-chunk 4 MMAs of M=256 x N=256 x K=16 across the pair =====================
+      const uint32_t idesc = umma_idesc_f16(p.dtype == RS_DTYPE_BF16, 256, 256);
+      const bool skip_mma = (p.debug_flags & 1) != 0;
+      int s = 0, b = 0;
+      uint32_t ph = 0, acc_ph = 0;  // bit b of acc_ph = phase of accumulator b
+      for (int u = pair; u < n_super; u += n_pairs) {
+        mbar_wait_guarded<true>(tempty(b), ((acc_ph >> b) & 1u) ^ 1u, p.err_flag);
+        tc_fence_after();
+        for (int kc = 0; kc < p.kc; ++kc) {
+          mbar_wait_guarded<true>(full(s), ph, p.err_flag);
+          tc_fence_after();
+          if (lane == 0) {
+            if (!skip_mma) {
+              const uint64_t a = umma_smem_desc(slot_addr(s)), bd = umma_smem_desc(slot_addr(s) + RS_BLOCK_BYTES);
+#pragma unroll
+              for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
+                umma_f16_pair(tmem_base + (uint32_t)b * 256u, a + 2u * ks, bd + 2u * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+            }
+            umma_commit_pair(empty(s));
+          }
+          __syncwarp();
+          if (++s == kPairSlots) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        if (lane == 0) umma_commit_pair(tfull(b));
+        __syncwarp();
+        acc_ph ^= 1u << b;
+        b ^= 1;
+      }
+    } else if (worker) {
+      // ===================== relay (peer): tell the leader when this CTA's half of a slot has landed =====================
+      int s = 0;
+      uint32_t ph = 0;
+      for (int u = pair; u < n_super; u += n_pairs) {
+        for (int kc = 0; kc < p.kc; ++kc) {
+          mbar_wait_guarded<false>(full(s), ph, p.err_flag);
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(full(s), 0));
+          __syncwarp();
+          if (++s == kPairSlots) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs): a thread owns query row 128*rank + 32*quarter + lane =====================
+    const int quarter = warp & 3;
+    const int k = p.k;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool cosine = p.metric == RS_METRIC_COSINE;
+    const int row = (int)rank * 128 + quarter * 32 + lane;
+    const bool live = row < p.n_queries;
+    const bool warp_live = (int)rank * 128 + quarter * 32 < p.n_queries && !(p.debug_flags & 2);
+    const float qs = live ? p.qscale[row] : 1.f;
+    const float inv_qs = 1.0f / qs;
+    const float nq = live ? p.qnorm[row] : 0.f;
+    float thr = live ? -CUDART_INF_F : CUDART_INF_F, thr_raw = thr;
+    float best1 = -CUDART_INF_F, best2 = -CUDART_INF_F, gbound = -CUDART_INF_F;
+    int cnt = 0;
+    const int n_lists = p.n_lists;
+    float* dump = reinterpret_cast<float*>(smem + map.dump_off) + (size_t)quarter * 32 * 32;
+    float* Ws = reinterpret_cast<float*>(smem + map.scratch_off) + (size_t)quarter * (2 * k + 64);
+    int* Wi = reinterpret_cast<int*>(Ws + k);
+    float* Bs = Ws + 2 * k;
+    auto glist_s = [&](int qrow) { return p.cand_score + ((size_t)qrow * n_lists + pair) * k; };
+    auto glist_i = [&](int qrow) { return p.cand_idx + ((size_t)qrow * n_lists + pair) * k; };
+    auto gbuf = [&](int qrow) { return p.cbuf + ((size_t)qrow * n_lists + pair) * kWideBufC; };
+    if (worker && live) {
+      float* l0 = glist_s(row);
+      int* i0 = glist_i(row);
+      for (int j = 0; j < k; ++j) {
+        l0[j] = -CUDART_INF_F;
+        i0[j] = -1;
+      }
+    }
+    __syncwarp();
+    const bool shared_bound = p.g_best != nullptr && worker;
+    const int bound_rank = p.bound_rank;
+    int tiles_done = 0, next_refresh = 1;
+    // merge query ql of this warp: its n buffered candidates -> its sorted list; returns the new k-th best in FILTER
+    // units (raw accumulator units for dot).  Whole warp, converged.
+    auto flush_query = [&](int ql, int n) -> float {
+      const int qrow = (int)rank * 128 + quarter * 32 + ql;
+      const float unit = cosine ? 1.0f : __shfl_sync(0xffffffffu, qs, ql);  // list units = final units
+      float* gs = glist_s(qrow);
+      int* gi = glist_i(qrow);
+      float cs = -CUDART_INF_F;
+      int ci = 0x7fffffff;
+      if (lane < n) {
+        const uint2 c = __ldcg(gbuf(qrow) + lane);
+        cs = __uint_as_float(c.x) * unit;
+        ci = (int)c.y;
+      }
+      for (int j = lane; j < k; j += 32) {
+        Ws[j] = __ldcg(gs + j);
+        Wi[j] = __ldcg(gi + j);
+      }
+      __syncwarp();
+      const float nt = merge_sorted_candidates(Ws, Wi, Bs, cs, ci, n, k, lane);
+      for (int j = lane; j < k; j += 32) {
+        __stcg(gs + j, Ws[j]);
+        __stcg(gi + j, Wi[j]);
+      }
+      __syncwarp();
+      if (p.debug_ts && lane == 0) atomicAdd(p.debug_ts + (size_t)blockIdx.x * 8 + 7, 1ull << 32);  // flushes
+      return cosine ? nt : nt * __shfl_sync(0xffffffffu, inv_qs, ql);  // exact: qs is a power of two
+    };
+    // compare 32 scores of this thread's query (columns c0..c0+31 of tile t) with its threshold; rare path: append
+    auto filter32 = [&](const uint32_t (&r)[32], int t, int c0, float ndmin, float ndmax) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      const float m = max32(v);
+      if (!__any_sync(0xffffffffu, m > thr_raw)) return;
+      const int row0 = t * RS_TILE_ROWS + c0;
+      uint32_t pm = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        pm |= (v[j] > thr_raw) ? (1u << j) : 0u;
+        dump[j * 32 + lane] = v[j];
+      }
+      if (row0 + 32 > p.n_rows) {  // ragged last tile: mask padded rows
+        const int valid = p.n_rows - row0;
+        pm = valid <= 0 ? 0u : (pm & (0xffffffffu >> (32 - valid)));
+      }
+      __syncwarp();
+      while (__any_sync(0xffffffffu, pm != 0u)) {
+        if (pm != 0u) {
+          const int j = __ffs(pm) - 1;
+          pm &= pm - 1;
+          const float s = dump[j * 32 + lane];
+          const int idx = row0 + j;
+          float x = s;  // dot: compare and buffer raw units (exact power-of-two scale)
+          if (cosine) {
+            const float nd = p.dnorm[idx];
+            const float denom = __fadd_rn(__fmul_rn(nq, nd), 1e-8f);  // retriever.py:605,607
+            x = __fdiv_rn(s * qs, denom);
+            x = fminf(fmaxf(x, -1.0f), 1.0f);                         // retriever.py:609
+          }
+          if (x > thr) {
+            __stcg(gbuf(row) + cnt, make_uint2(__float_as_uint(x), (unsigned int)idx));
+            ++cnt;
+            if (p.debug_ts) atomicAdd(p.debug_ts + (size_t)blockIdx.x * 8 + 7, 1ull);  // appends (low word)
+            if (shared_bound) {  // publish this CTA's bound_rank-th best score of the query
+              float pub = -CUDART_INF_F;
+              if (x > best1) {
+                best2 = best1;
+                best1 = x;
+                pub = bound_rank == 1 ? best1 : best2;
+              } else if (x > best2) {
+                best2 = x;
+                if (bound_rank == 2) pub = best2;
+              }
+              if (pub > -CUDART_INF_F) __stcg(p.g_best + (size_t)pair * p.bpad + row, pub);
+            }
+          }
+        }
+        uint32_t fullm = __ballot_sync(0xffffffffu, cnt == kWideBufC);  // (rare: flushes normally happen after the release)
+        while (fullm) {
+          const int ql = __ffs(fullm) - 1;
+          fullm &= fullm - 1;
+          const float nt = flush_query(ql, kWideBufC);
+          if (lane == ql) {
+            thr = fmaxf(nt, gbound);
+            cnt = 0;
+            thr_raw = cosine ? cosine_raw_bound(thr, nq, inv_qs, ndmin, ndmax) : thr;
+          }
+        }
+      }
+      __syncwarp();
+    };
+
+    if (worker) {
+      int b = 0;
+      uint32_t acc_ph = 0;  // bit b = phase of accumulator b
+      const bool prof = p.debug_ts != nullptr && threadIdx.x == kFirstEpiWarp * 32;
+      long long t_wait = 0, t_hold = 0, t_merge = 0, tc0 = 0, tc1 = 0, tc2 = 0;
+      const uint32_t tempty_leader = mapa_u32(tempty(0), 0);  // tempty(b) = tempty(0) + 8 b in the leader's window
+      for (int u = pair; u < n_super; u += n_pairs) {
+        const int nsub = min(2, p.n_tiles - 2 * u);
+        if (prof) tc0 = clock64();
+        mbar_wait_guarded<false>(tfull(b), (acc_ph >> b) & 1u, p.err_flag);
+        tc_fence_after();
+        if (prof) tc1 = clock64();
+        if (shared_bound && live && tiles_done >= next_refresh) {  // after 1, 2, 4, ... tiles, then every 64
+          next_refresh = tiles_done < 64 ? 2 * tiles_done : tiles_done + 64;
+          float mn = CUDART_INF_F;
+#pragma unroll 8
+          for (int c = 0; c < n_lists; ++c) {
+            const float v = __ldcg(p.g_best + (size_t)c * p.bpad + row);
+            mn = fminf(mn, v == v ? v : -CUDART_INF_F);  // NaN = that pair has not published yet
+          }
+          if (mn > -CUDART_INF_F && mn < CUDART_INF_F) {
+            gbound = __uint_as_float(__float_as_uint(mn) + (mn > 0.f ? -1 : (mn < 0.f ? 1 : 0)));  // next float below
+            if (mn == 0.f) gbound = -1.401298464e-45f;
+            if (gbound > thr) {
+              thr = gbound;
+              thr_raw = cosine ? CUDART_INF_F : thr;  // cosine: recomputed per tile just below
+            }
+          }
+        }
+        tiles_done += nsub;
+        if (warp_live) {
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int t = 2 * u + sub;
+            float ndmin = 1.f, ndmax = 1.f;
+            if (cosine) {
+              const float2 mm = p.tile_norm_minmax[t];
+              ndmin = mm.x;
+              ndmax = mm.y;
+              thr_raw = live ? cosine_raw_bound(thr, nq, inv_qs, ndmin, ndmax) : CUDART_INF_F;
+            }
+            const uint32_t tacc = lane_base + (uint32_t)(b * 256 + sub * 128);
+            uint32_t ra[32], rb[32];
+            tmem_ld_x32(tacc, ra);
+#pragma unroll 1
+            for (int c0 = 0; c0 < RS_TILE_ROWS; c0 += 64) {
+              tmem_wait_ld_regs(ra);
+              tmem_ld_x32(tacc + c0 + 32, rb);
+              filter32(ra, t, c0, ndmin, ndmax);
+              tmem_wait_ld_regs(rb);
+              if (c0 + 64 < RS_TILE_ROWS) tmem_ld_x32(tacc + c0 + 64, ra);
+              filter32(rb, t, c0 + 32, ndmin, ndmax);
+            }
+          }
+        }
+        // every TMEM read of this supertile is complete: hand the accumulator back to the leader's issuer, THEN merge
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader + 8u * (uint32_t)b);
+        acc_ph ^= 1u << b;
+        b ^= 1;
+        if (prof) tc2 = clock64();
+        uint32_t due = __ballot_sync(0xffffffffu, cnt >= kWideFlushAt);
+        while (due) {
+          const int ql = __ffs(due) - 1;
+          due &= due - 1;
+          const int n = __shfl_sync(0xffffffffu, cnt, ql);
+          const float nt = flush_query(ql, n);
+          if (lane == ql) {
+            thr = fmaxf(nt, gbound);
+            cnt = 0;
+            thr_raw = cosine ? CUDART_INF_F : thr;  // cosine: recomputed per tile
+          }
+        }
+        if (prof) {
+          t_wait += tc1 - tc0;
+          t_hold += tc2 - tc1;
+          t_merge += clock64() - tc2;
+        }
+      }
+      if (prof) {
+        p.debug_ts[(size_t)blockIdx.x * 8 + 1] = (unsigned long long)t_wait;
+        p.debug_ts[(size_t)blockIdx.x * 8 + 2] = (unsigned long long)t_hold;
+        p.debug_ts[(size_t)blockIdx.x * 8 + 3] = (unsigned long long)t_merge;
+      }
+      // drain the partially filled buffers; the lists already sit in cand_* in final units
+      uint32_t rem = __ballot_sync(0xffffffffu, cnt > 0);
+      while (rem) {
+        const int ql = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const int n = __shfl_sync(0xffffffffu, cnt, ql);
+        flush_query(ql, n);
+      }
+    }
+  }
+
+  if (p.tail_mode != 0) __threadfence();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no signal crosses the pair after this point; both CTAs are done with TMEM
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+  fused_tail(p, smem, worker);
 }
 
 // smem bytes the tail needs at offset 0 (result row + staged lists of one query)
@@ -1713,7 +2585,7 @@ __global__ void __launch_bounds__(kMergeThreads) exchange_merge_kernel(const flo
                                                                        int k, long long idx_offset,
                                                                        float* __restrict__ out_score,
                                                                        long long* __restrict__ out_idx,
-                                                                       const ExchangeArgs x, unsigned int* err_flag) {
+                                                                       const __grid_constant__ ExchangeArgs x, unsigned int* err_flag) {
   extern __shared__ __align__(16) uint8_t merge_smem[];
   const int q = blockIdx.x;  // query inside this pass
   const MergeSmem m = merge_smem_at(merge_smem, k);
@@ -1777,7 +2649,75 @@ static cudaError_t launch_fused_q(const SearchParams& p, int grid, cudaStream_t 
                       : launch_fused_t<NACC, REGLIST, false>(p, grid, stream);
 }
 
+int fused_wide_smem_bytes(int k) { return (int)make_wide_smem(k).total + 1024; }
+int fused_wide_tail_capacity(int k) { return (int)make_wide_smem(k).bar_off; }
+int fused_wide_slots() { return kWideSlots; }
+int fused_wide_bufc() { return kWideBufC; }
+
+static cudaError_t launch_fused_wide(const SearchParams& p, int grid, cudaStream_t stream) {
+  if (p.bpad != 256 || p.terms != 1 || p.planes != 1 || p.n_queries > 256 || p.k > kMaxListK || p.cbuf == nullptr ||
+      p.qstages < 2 || p.stages < 2 || p.qstages + p.stages != kWideSlots)
+    return cudaErrorInvalidValue;
+  const int bytes = fused_wide_smem_bytes(p.k);
+  cudaError_t e = cudaFuncSetAttribute(fused_search_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  fused_search_wide_kernel<<<grid, kThreads, bytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+int fused_pair_smem_bytes(int k) { return (int)make_pair_smem(k).total + 1024; }
+int fused_pair_tail_capacity(int k) { return (int)make_pair_smem(k).bar_off; }
+
+static void pair_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int grid, int bytes, cudaStream_t stream) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->gridDim = dim3((unsigned)grid);
+  cfg->blockDim = dim3(kThreads);
+  cfg->dynamicSmemBytes = (size_t)bytes;
+  cfg->stream = stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
+}
+
+int fused_pair_max_clusters(int k) {
+  const int bytes = fused_pair_smem_bytes(k);
+  if (cudaFuncSetAttribute(fused_search_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  pair_launch_config(&cfg, attr, sms & ~1, bytes, nullptr);
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, fused_search_pair_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+static cudaError_t launch_fused_pair(const SearchParams& p, int grid, cudaStream_t stream) {
+  if (p.bpad != 256 || p.terms != 1 || p.planes != 1 || p.n_queries > 256 || p.k > kMaxListK || p.cbuf == nullptr ||
+      (grid & 1) || (p.n_work & 1) || p.n_lists * 2 != p.n_work || (p.g_best && p.bound_rank != 1 && p.bound_rank != 2))
+    return cudaErrorInvalidValue;
+  const int bytes = fused_pair_smem_bytes(p.k);
+  cudaError_t e = cudaFuncSetAttribute(fused_search_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  pair_launch_config(&cfg, attr, grid, bytes, stream);
+  return cudaLaunchKernelEx(&cfg, fused_search_pair_kernel, p);
+}
+
 cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t stream) {
+  if (p.wide == 2) return launch_fused_pair(p, grid, stream);
+  if (p.wide) return launch_fused_wide(p, grid, stream);
   const bool reglist = p.k <= kRegK;
   const int nacc = (p.terms == 2 || p.planes == 2) ? 2 : 1;
   if (p.docm) {

@@ -332,7 +332,7 @@ def test_large_batches_stream_queries_single_pass(squad, B, dtype, terms):
     try:
         idx, sc = ix.search(Q, 10, "dot", terms)
         st = ix.stats()
-        assert st["passes"] == (1 if B <= 128 else 2) and st["q_resident"] == 0
+        assert st["passes"] == 1 and st["q_resident"] == 0      # B = 256: the wide-batch kernel, still one pass
         S = exact_scores(Q, E, dtype, "dot", terms, 4 if dtype == "fp32" else 0)
         o.check_topk(idx, sc, S, 10, rtol=RTOL[dtype], atol=1e-6)
     finally:
@@ -620,8 +620,40 @@ def test_config5_shape_b256_k100_fp16(metric):
         sw = o.check_topk_candidates(idx, sc, ci, cs, exact(idx), k, rtol=2e-3, atol=1e-6)
         print(f"B=256 k=100 fp16 {metric}: passes {st['passes']}, bytes streamed / corpus bytes "
               f"{st['bytes_streamed'] / st['corpus_bytes']:.1f}, near-tie substitutions {sw}")
+        assert st["passes"] == 1 and st["bytes_streamed"] == st["corpus_bytes"]      # ONE pass for 256 queries
         idx2, sc2 = ix.search(Q, k, metric, 1)
         assert np.array_equal(idx, idx2) and np.array_equal(sc, sc2)
+    finally:
+        ix.close()
+
+
+@pytest.mark.parametrize("dtype,metric,B,k,N", [
+    ("bf16", "dot", 256, 100, 128 * 148 * 2 + 300), ("fp16", "cosine", 129, 10, 128 * 148 + 1), ("bf16", "dot", 200, 1, 128 * 7),
+    ("fp16", "dot", 256, 128, 128 * 301 + 5), ("bf16", "cosine", 255, 17, 900), ("fp16", "dot", 300, 16, 128 * 40 + 77),
+    ("bf16", "dot", 512, 33, 128 * 149)])
+def test_wide_batch_kernel_sweep(dtype, metric, B, k, N):
+    """fused_search_wide_kernel (128 < B <= 256 per pass, ONE pass over the shard): odd and even tile counts, fewer
+    supertiles than CTAs, ragged last tile, partly filled second half, every k range, both metrics, batches above
+    256 (several wide passes) - against the oracle, and bit-identical to the two-pass plan (RS_WIDE=0)."""
+    E = o.synth_rows(13, np.arange(N))
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, N, B)
+    src[:2] = [0, N - 1]
+    Q = o.round_to_dtype(E[src] + 0.02 * rng.standard_normal((B, 1024)).astype(np.float32), DT[dtype])
+    ix = make_index(E, dtype, max_batch=512, max_k=128)
+    try:
+        idx, sc = ix.search(Q, k, metric, 1)
+        st = ix.stats()
+        assert st["passes"] == -(-B // 256) and st["bytes_streamed"] == st["passes"] * st["corpus_bytes"]
+        S = exact_scores(Q, E, dtype, metric, 1)
+        o.check_topk(idx, sc, S, k, rtol=RTOL[dtype], atol=1e-6)
+        assert (idx[:, 0] == src).all()
+        i2, s2 = ix.search(Q, k, metric, 1)                 # deterministic
+        assert np.array_equal(idx, i2) and np.array_equal(sc, s2)
+        ix.set_option("RS_WIDE", 0)                         # the general kernel, 128 queries per pass
+        i3, s3 = ix.search(Q, k, metric, 1)
+        assert ix.stats()["passes"] == -(-B // 128)
+        assert np.array_equal(idx, i3) and np.array_equal(sc, s3)
     finally:
         ix.close()
 

@@ -13,8 +13,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 from rag_serving_system_b200 import _cabi
 from perf_sweep import Power
 
-KEYS = ("RS_MMA_M", "RS_QRESIDENT", "RS_SUB", "RS_NBUF", "RS_CPS", "RS_INLINE_PREP", "RS_FUSED_TAIL", "RS_DEBUG_FLAGS", "RS_SHARED_BOUND", "RS_DOCM", "RS_QLO_STREAM", "RS_LISTS_GLOBAL", "RS_DYN_SCHED",
-        "RS_STAGES", "RS_NO_EVENTS")
+KEYS = tuple(_cabi.OPTION_DEFAULTS)
 rows, B, k = (int(x) for x in sys.argv[1:4])
 dtype = sys.argv[4]
 envs = json.loads(sys.argv[5])
