@@ -75,7 +75,7 @@ struct Options {
   int qlo_stream = 0;    // RS_QLO_STREAM   two-term searches: 1/2 = stream the lo query term
   int graph = 1;         // RS_GRAPH        0: host-buffer searches enqueue eagerly instead of replaying a CUDA graph
   int no_events = 0;     // RS_NO_EVENTS    1: no CUDA events around the fused launch
-  int wide = 1;          // RS_WIDE         batches above 128: 2 = one pass, CTA-pair kernel (cta_group::2); 1 = one pass, one CTA
+  int wide = 2;          // RS_WIDE         batches above 128: 2 = one pass, CTA-pair kernel (cta_group::2); 1 = one pass, one CTA
                          //                 per SM; 0 = split into passes of 128
   int overlap = 0;       // RS_OVERLAP      1: consecutive device-buffer searches on one stream may overlap (PDL)
   int debug_flags = 0;   // RS_DEBUG_FLAGS  timing experiments: skip MMAs (1) / the epilogue (2) / the tail merge (4)

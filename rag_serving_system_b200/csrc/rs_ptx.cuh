@@ -137,6 +137,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// the same with the default semantics (.release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id) does
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // wait on a LOCAL mbarrier whose arrivals may come from the other CTA (acquire at cluster scope)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;

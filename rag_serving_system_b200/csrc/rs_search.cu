@@ -2264,10 +2264,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
       // ===================== relay (peer): tell the leader when this CTA's half of a slot has landed =====================
       int s = 0;
       uint32_t ph = 0;
+      const uint32_t full_leader = mapa_u32(full(0), 0);
       for (int u = pair; u < n_super; u += n_pairs) {
         for (int kc = 0; kc < p.kc; ++kc) {
           mbar_wait_guarded<false>(full(s), ph, p.err_flag);
-          if (lane == 0) mbar_arrive_cluster(mapa_u32(full(s), 0));
+          // (a .release.cluster arrive here costs ~1 us each and serialises the relay: 3.2 ms instead of 1.2 ms for
+          // the bare stream of 4M rows; the bulk copies' completion on full(s) already orders the data)
+          if (lane == 0) mbar_arrive_remote(full_leader + 8u * (uint32_t)s);
           __syncwarp();
           if (++s == kPairSlots) {
             s = 0;
@@ -2310,6 +2313,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
     __syncwarp();
     const bool shared_bound = p.g_best != nullptr && worker;
     const int bound_rank = p.bound_rank;
+    const int flush_at = (p.debug_flags >> 8) ? (p.debug_flags >> 8) : kWideFlushAt;  // (experiments)
     int tiles_done = 0, next_refresh = 1;
     // merge query ql of this warp: its n buffered candidates -> its sorted list; returns the new k-th best in FILTER
     // units (raw accumulator units for dot).  Whole warp, converged.
@@ -2344,14 +2348,26 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      const float m = max32(v);
+      float gm[4];  // maxima of the four groups of 8 consecutive columns
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        gm[g] = fmaxf(fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3])),
+                      fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7])));
+      const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
       if (!__any_sync(0xffffffffu, m > thr_raw)) return;
+      // rare path: only the groups in which some lane passes are parked in shared memory (8 stores per group instead of
+      // 32 per chunk: the ring fills and the MMAs' operand reads already use the shared-memory bandwidth)
       const int row0 = t * RS_TILE_ROWS + c0;
       uint32_t pm = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        pm |= (v[j] > thr_raw) ? (1u << j) : 0u;
-        dump[j * 32 + lane] = v[j];
+      for (int g = 0; g < 4; ++g) {
+        if (__any_sync(0xffffffffu, gm[g] > thr_raw)) {
+#pragma unroll
+          for (int j = 8 * g; j < 8 * g + 8; ++j) {
+            pm |= (v[j] > thr_raw) ? (1u << j) : 0u;
+            dump[j * 32 + lane] = v[j];
+          }
+        }
       }
       if (row0 + 32 > p.n_rows) {  // ragged last tile: mask padded rows
         const int valid = p.n_rows - row0;
@@ -2461,11 +2477,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
         // every TMEM read of this supertile is complete: hand the accumulator back to the leader's issuer, THEN merge
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tempty_leader + 8u * (uint32_t)b);
+        if (lane == 0) mbar_arrive_remote(tempty_leader + 8u * (uint32_t)b);
         acc_ph ^= 1u << b;
         b ^= 1;
         if (prof) tc2 = clock64();
-        uint32_t due = __ballot_sync(0xffffffffu, cnt >= kWideFlushAt);
+        uint32_t due = __ballot_sync(0xffffffffu, cnt >= flush_at);
         while (due) {
           const int ql = __ffs(due) - 1;
           due &= due - 1;

@@ -632,9 +632,10 @@ def test_config5_shape_b256_k100_fp16(metric):
     ("fp16", "dot", 256, 128, 128 * 301 + 5), ("bf16", "cosine", 255, 17, 900), ("fp16", "dot", 300, 16, 128 * 40 + 77),
     ("bf16", "dot", 512, 33, 128 * 149)])
 def test_wide_batch_kernel_sweep(dtype, metric, B, k, N):
-    """fused_search_wide_kernel (128 < B <= 256 per pass, ONE pass over the shard): odd and even tile counts, fewer
-    supertiles than CTAs, ragged last tile, partly filled second half, every k range, both metrics, batches above
-    256 (several wide passes) - against the oracle, and bit-identical to the two-pass plan (RS_WIDE=0)."""
+    """Wide batches (128 < B <= 256 per pass, ONE pass over the shard): the CTA-pair kernel (fused_search_pair_kernel,
+    tcgen05 cta_group::2 - the default) and the one-CTA-per-SM kernel (fused_search_wide_kernel, RS_WIDE=1).  Odd and
+    even tile counts, fewer supertiles than pairs, ragged last tile, partly filled second half, every k range, both
+    metrics, batches above 256 (several wide passes) - against the oracle, and all three plans bit-identical."""
     E = o.synth_rows(13, np.arange(N))
     rng = np.random.default_rng(3)
     src = rng.integers(0, N, B)
@@ -645,11 +646,17 @@ def test_wide_batch_kernel_sweep(dtype, metric, B, k, N):
         idx, sc = ix.search(Q, k, metric, 1)
         st = ix.stats()
         assert st["passes"] == -(-B // 256) and st["bytes_streamed"] == st["passes"] * st["corpus_bytes"]
+        assert st["mma_m"] == 256 and st["nbuf"] == 2 and st["grid"] % 2 == 0       # the pair kernel ran
         S = exact_scores(Q, E, dtype, metric, 1)
         o.check_topk(idx, sc, S, k, rtol=RTOL[dtype], atol=1e-6)
         assert (idx[:, 0] == src).all()
-        i2, s2 = ix.search(Q, k, metric, 1)                 # deterministic
-        assert np.array_equal(idx, i2) and np.array_equal(sc, s2)
+        for _ in range(3):                                  # deterministic, and the pair protocol survives repeats
+            i2, s2 = ix.search(Q, k, metric, 1)
+            assert np.array_equal(idx, i2) and np.array_equal(sc, s2)
+        ix.set_option("RS_WIDE", 1)                         # one CTA per SM, single accumulator
+        i4, s4 = ix.search(Q, k, metric, 1)
+        assert ix.stats()["passes"] == -(-B // 256) and ix.stats()["mma_m"] == 128
+        assert np.array_equal(idx, i4) and np.array_equal(sc, s4)
         ix.set_option("RS_WIDE", 0)                         # the general kernel, 128 queries per pass
         i3, s3 = ix.search(Q, k, metric, 1)
         assert ix.stats()["passes"] == -(-B // 128)

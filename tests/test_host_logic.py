@@ -147,9 +147,9 @@ def test_launch_planner_is_consistent():
                         assert dim >= 2048 or k > 16, (dim, dtype, B, k)      # only big shapes may be refused
                         continue
                     nacc = 2 if (terms == 2 or dtype == "fp32") else 1
-                    if B > 128 and nacc == 1:            # wide-batch kernel: both 128-row halves share ONE pass
+                    if B > 128 and nacc == 1:            # wide-batch (CTA-pair) kernel: both 128-row halves share ONE pass
                         assert (pl["passes"], pl["bpad"], pl["sub"], pl["nbuf"], pl["mma_m"], pl["cps"], pl["q_resident"]) == \
-                            (1, 256, 2, 1, 128, 1, 0), (dim, dtype, B, k, pl)
+                            (1, 256, 2, 2, 256, 1, 0), (dim, dtype, B, k, pl)
                         continue
                     assert pl["passes"] * pl["per_pass"] >= B and pl["bpad"] % 8 == 0 and pl["bpad"] <= 128
                     assert pl["bpad"] >= pl["per_pass"] and pl["stages"] >= 2
