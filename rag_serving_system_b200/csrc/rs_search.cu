@@ -2291,7 +2291,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
     const float qs = live ? p.qscale[row] : 1.f;
     const float inv_qs = 1.0f / qs;
     const float nq = live ? p.qnorm[row] : 0.f;
-    float thr = live ? -CUDART_INF_F : CUDART_INF_F, thr_raw = thr;
+    float thr = (live && !(p.debug_flags & 32)) ? -CUDART_INF_F : CUDART_INF_F, thr_raw = thr;  // flag 32: nothing ever passes (timing)
     float best1 = -CUDART_INF_F, best2 = -CUDART_INF_F, gbound = -CUDART_INF_F;
     int cnt = 0;
     const int n_lists = p.n_lists;
@@ -2314,7 +2314,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
     const bool shared_bound = p.g_best != nullptr && worker;
     const int bound_rank = p.bound_rank;
     const int flush_at = (p.debug_flags >> 8) ? (p.debug_flags >> 8) : kWideFlushAt;  // (experiments)
-    int tiles_done = 0, next_refresh = 1;
+    int supers_done = 0, next_refresh = 1;
+    bool count_bound = true;  // false while the first supertile is filtered: the sample pass has counted its documents
     // merge query ql of this warp: its n buffered candidates -> its sorted list; returns the new k-th best in FILTER
     // units (raw accumulator units for dot).  Whole warp, converged.
     auto flush_query = [&](int ql, int n) -> float {
@@ -2391,7 +2392,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
             __stcg(gbuf(row) + cnt, make_uint2(__float_as_uint(x), (unsigned int)idx));
             ++cnt;
             if (p.debug_ts) atomicAdd(p.debug_ts + (size_t)blockIdx.x * 8 + 7, 1ull);  // appends (low word)
-            if (shared_bound) {  // publish this CTA's bound_rank-th best score of the query
+            if (shared_bound && count_bound) {  // publish this CTA's bound_rank-th best score of the query
               float pub = -CUDART_INF_F;
               if (x > best1) {
                 best2 = best1;
@@ -2432,10 +2433,71 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
         mbar_wait_guarded<false>(tfull(b), (acc_ph >> b) & 1u, p.err_flag);
         tc_fence_after();
         if (prof) tc1 = clock64();
-        if (shared_bound && live && tiles_done >= next_refresh) {  // after 1, 2, 4, ... tiles, then every 64
-          next_refresh = tiles_done < 64 ? 2 * tiles_done : tiles_done + 64;
-          float mn = CUDART_INF_F;
+        if (shared_bound && u == pair) {
+          // ---- sample pass over the FIRST accumulator: before a query has k candidates its own k-th best filters
+          // nothing, and every document of the first supertile would be appended and merged (measured: 194 of a
+          // query's 265 appends per pair, the epilogue far behind the MMAs).  So the first supertile is scanned twice
+          // while its accumulator is held: pass A only tracks the query's two best scores in registers and publishes
+          // the bound; once every pair has published (all are resident and publish within their first supertile),
+          // the filter below runs against a bound that already rejects > 99 % of the documents.
+          if (warp_live) {
+            for (int sub = 0; sub < nsub; ++sub) {
+              const uint32_t tacc = lane_base + (uint32_t)(b * 256 + sub * 128);
+              const int trow0 = (2 * u + sub) * RS_TILE_ROWS;
+#pragma unroll 1
+              for (int c0 = 0; c0 < RS_TILE_ROWS; c0 += 32) {
+                uint32_t r0[32];
+                tmem_ld_x32(tacc + c0, r0);
+                tmem_wait_ld_regs(r0);
+                const int valid = p.n_rows - (trow0 + c0);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  float x = __uint_as_float(r0[j]);
+                  if (cosine) {
+                    const float nd = p.dnorm[min(trow0 + c0 + j, p.n_rows - 1)];
+                    const float denom = __fadd_rn(__fmul_rn(nq, nd), 1e-8f);  // retriever.py:605,607
+                    x = fminf(fmaxf(__fdiv_rn(x * qs, denom), -1.0f), 1.0f);   // retriever.py:609
+                  }
+                  if (j >= valid) x = -CUDART_INF_F;  // padded rows of a ragged last tile
+                  best2 = fmaxf(best2, fminf(best1, x));
+                  best1 = fmaxf(best1, x);
+                }
+              }
+            }
+          }
+          if (live) {
+            __stcg(p.g_best + (size_t)pair * p.bpad + row, bound_rank == 1 ? best1 : best2);  // -inf: nothing to offer
+            unsigned int polls = 0;
+            unsigned long long t0 = 0;
+            while (true) {
+              bool all = true;
 #pragma unroll 8
+              for (int c = 0; c < n_lists; ++c) {
+                const float v = __ldcg(p.g_best + (size_t)c * p.bpad + row);
+                all = all && (v == v);
+              }
+              if (all) break;
+              __nanosleep(100);
+              if ((++polls & 0xffu) == 0u) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                if (now - t0 > 2000000000ull) {  // 2 s: a pair of this grid never ran; give up on the bound, not on the search
+                  *reinterpret_cast<volatile unsigned int*>(p.err_flag) = 1u;
+                  break;
+                }
+              }
+            }
+          }
+          count_bound = false;
+        } else {
+          count_bound = true;
+        }
+        if (shared_bound && live && supers_done >= next_refresh - (u == pair ? 1 : 0)) {
+          // bound refresh: after the sample, then after 1, 2, 3, 4 supertiles, then at 1.5x intervals, then every 32
+          if (u != pair) next_refresh = next_refresh < 4 ? next_refresh + 1 : (next_refresh < 64 ? next_refresh + next_refresh / 2 : next_refresh + 32);
+          float mn = CUDART_INF_F;
+#pragma unroll 16
           for (int c = 0; c < n_lists; ++c) {
             const float v = __ldcg(p.g_best + (size_t)c * p.bpad + row);
             mn = fminf(mn, v == v ? v : -CUDART_INF_F);  // NaN = that pair has not published yet
@@ -2449,7 +2511,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
             }
           }
         }
-        tiles_done += nsub;
+        ++supers_done;
         if (warp_live) {
           for (int sub = 0; sub < nsub; ++sub) {
             const int t = 2 * u + sub;
