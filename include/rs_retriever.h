@@ -186,6 +186,19 @@ RS_API int rs_group_search(rs_group* g, const float* q_host, int32_t B, int32_t 
                     int64_t* out_idx, float* out_score);
 RS_API int rs_group_destroy(rs_group* g);
 
+/* Document arena (host side).  Replaces the B*k Python list lookups of retriever.py:776-790 /
+ * :789 / :675 and the per-query joins of batch_processor.py:100 (`"\n---\n".join(docs)`): the documents live ONCE in
+ * a UTF-8 byte arena (document i = arena[offsets[i], offsets[i+1])), copied by rs_docs_create; rs_docs_join writes,
+ * for every query i, its first min(ks[i], stride) VALID hits (idx >= 0; -1 is the padding of retriever.py:767-769)
+ * joined with `sep` into `out` - one memcpy per hit, no Python objects - and out_offsets[B+1] delimits the rows.
+ * ks[i] <= 0 gives an empty row (retriever.py:778-780).  *need receives the total bytes; when out_cap < *need (or
+ * out == NULL) only the sizes are computed and the caller calls again with a large enough buffer. */
+typedef struct rs_docs rs_docs;
+RS_API int rs_docs_create(const char* arena, const int64_t* offsets, int64_t n_docs, rs_docs** out);
+RS_API int rs_docs_destroy(rs_docs* d);
+RS_API int rs_docs_join(const rs_docs* d, const int64_t* idx, int32_t B, int32_t stride, const int32_t* ks, const char* sep,
+                 int32_t sep_len, char* out, int64_t out_cap, int64_t* out_offsets, int64_t* need);
+
 /* Read back the represented values of rows [row0,row0+nrows) as float (inverse of the tiling);
  * used by the tests (ingest round trip) and by the CPU-baseline sampler. */
 RS_API int rs_get_rows(rs_index* ix, int64_t row0, int64_t nrows, float* out_host);

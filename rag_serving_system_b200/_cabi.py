@@ -23,12 +23,13 @@ EXPORTS = (
     "rs_debug_plan", "rs_debug_timestamps", "rs_xchg_create", "rs_xchg_export", "rs_xchg_import", "rs_xchg_attach",
     "rs_xchg_destroy", "rs_search_exchange", "rs_search_exchange_host", "rs_check", "rs_set_option",
     "rs_get_rows_device", "rs_group_create", "rs_group_search", "rs_group_destroy",
+    "rs_docs_create", "rs_docs_destroy", "rs_docs_join",
 )
 ABI_VERSION = 2          # include/rs_retriever.h: RS_ABI_VERSION
 # switches of an index and their defaults (csrc/rs_api.cu: Options); rs_create reads the environment once
 OPTION_DEFAULTS = {
     "RS_DOCM": 1, "RS_INLINE_PREP": 1, "RS_FUSED_TAIL": 1, "RS_DYN_SCHED": 1, "RS_SHARED_BOUND": 1,
-    "RS_LISTS_GLOBAL": 1, "RS_QLO_STREAM": 0, "RS_GRAPH": 1, "RS_NO_EVENTS": 0, "RS_WIDE": 2, "RS_OVERLAP": 0,
+    "RS_LISTS_GLOBAL": 1, "RS_QLO_STREAM": 0, "RS_GRAPH": 1, "RS_NO_EVENTS": 0, "RS_WIDE": 2, "RS_DMPAIR": 1, "RS_OVERLAP": 0,
     "RS_DEBUG_FLAGS": 0, "RS_DEBUG_TS": 0, "RS_QRESIDENT": -1, "RS_CPS": 0, "RS_SUB": 0, "RS_BUFC": 0,
     "RS_LEAN": -1, "RS_MMA_M": 0, "RS_NBUF": 0, "RS_QSTAGES": 0,
 }
@@ -108,6 +109,9 @@ def load() -> C.CDLL:
         "rs_group_create": [C.POINTER(vp), i32, C.POINTER(vp)],
         "rs_group_search": [vp, vp, i32, i32, i32, i32, vp, vp],
         "rs_group_destroy": [vp],
+        "rs_docs_create": [vp, vp, i64, C.POINTER(vp)],
+        "rs_docs_destroy": [vp],
+        "rs_docs_join": [vp, vp, i32, i32, vp, C.c_char_p, i32, vp, i64, vp, vp],
         "rs_get_rows": [vp, i64, i64, vp],
         "rs_get_norms": [vp, i64, i64, vp],
         "rs_get_image": [vp, i64, i64, vp],
@@ -311,6 +315,52 @@ class Group:
     def close(self):
         if getattr(self, "h", None):
             self.lib.rs_group_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class DocArena:
+    """UTF-8 byte arena of the documents + native gather/join (rs_docs_*; host code of the C ABI, no GPU needed).
+
+    ``join(idx, ks, sep)`` returns, per query, the documents of its first k_i valid hits joined with ``sep`` -
+    what ``sep.join(batch_retrieve(...)[i])`` gives (retriever.py:776-790 + batch_processor.py:100) - with one
+    memcpy per hit in C and ONE ``bytes.decode`` per query instead of B*k list lookups and B joins."""
+
+    def __init__(self, documents):
+        self.lib = load()
+        enc = [d.encode("utf-8") for d in documents]
+        off = np.zeros(len(enc) + 1, dtype=np.int64)
+        if enc:
+            np.cumsum(np.fromiter((len(e) for e in enc), dtype=np.int64, count=len(enc)), out=off[1:])
+        arena = b"".join(enc)
+        h = C.c_void_p()
+        check(self.lib.rs_docs_create(arena, off.ctypes.data, len(enc), C.byref(h)), "rs_docs_create")
+        self.h, self.n = h, len(enc)
+
+    def join_bytes(self, idx: np.ndarray, ks, sep: str = "\n---\n"):
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        B, stride = idx.shape
+        ks_a = np.ascontiguousarray(np.clip(np.asarray(ks, dtype=np.int64), 0, stride), dtype=np.int32)
+        assert ks_a.shape == (B,)
+        sep_b = sep.encode("utf-8")
+        offs = np.empty(B + 1, dtype=np.int64)
+        need = C.c_int64(0)
+        check(self.lib.rs_docs_join(self.h, idx.ctypes.data, B, stride, ks_a.ctypes.data, sep_b, len(sep_b), None, 0,
+                                    offs.ctypes.data, C.byref(need)), "rs_docs_join")
+        buf = C.create_string_buffer(max(1, need.value))
+        check(self.lib.rs_docs_join(self.h, idx.ctypes.data, B, stride, ks_a.ctypes.data, sep_b, len(sep_b), buf, need.value,
+                                    offs.ctypes.data, C.byref(need)), "rs_docs_join")
+        return buf.raw[:need.value], offs
+
+    def join(self, idx: np.ndarray, ks, sep: str = "\n---\n"):
+        raw, offs = self.join_bytes(idx, ks, sep)
+        o = offs.tolist()
+        return [raw[o[i]:o[i + 1]].decode("utf-8") for i in range(len(o) - 1)]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rs_docs_destroy(self.h)
             self.h = None
 
     __del__ = close

@@ -75,6 +75,7 @@ struct Options {
   int qlo_stream = 0;    // RS_QLO_STREAM   two-term searches: 1/2 = stream the lo query term
   int graph = 1;         // RS_GRAPH        0: host-buffer searches enqueue eagerly instead of replaying a CUDA graph
   int no_events = 0;     // RS_NO_EVENTS    1: no CUDA events around the fused launch
+  int dmpair = 1;        // RS_DMPAIR       1: two-accumulator doc-major searches of large corpora run on CTA pairs (cta_group::2); 0: never
   int wide = 2;          // RS_WIDE         batches above 128: 2 = one pass, CTA-pair kernel (cta_group::2); 1 = one pass, one CTA
                          //                 per SM; 0 = split into passes of 128
   int overlap = 0;       // RS_OVERLAP      1: consecutive device-buffer searches on one stream may overlap (PDL)
@@ -91,7 +92,7 @@ const OptDef kOptDefs[] = {
     {"RS_DOCM", &Options::docm}, {"RS_INLINE_PREP", &Options::inline_prep}, {"RS_FUSED_TAIL", &Options::fused_tail},
     {"RS_DYN_SCHED", &Options::dyn_sched}, {"RS_SHARED_BOUND", &Options::shared_bound},
     {"RS_LISTS_GLOBAL", &Options::lists_global}, {"RS_QLO_STREAM", &Options::qlo_stream}, {"RS_GRAPH", &Options::graph},
-    {"RS_NO_EVENTS", &Options::no_events}, {"RS_WIDE", &Options::wide}, {"RS_OVERLAP", &Options::overlap}, {"RS_DEBUG_FLAGS", &Options::debug_flags},
+    {"RS_NO_EVENTS", &Options::no_events}, {"RS_WIDE", &Options::wide}, {"RS_DMPAIR", &Options::dmpair}, {"RS_OVERLAP", &Options::overlap}, {"RS_DEBUG_FLAGS", &Options::debug_flags},
     {"RS_DEBUG_TS", &Options::debug_ts}, {"RS_QRESIDENT", &Options::qresident}, {"RS_CPS", &Options::cps},
     {"RS_SUB", &Options::sub}, {"RS_BUFC", &Options::bufc}, {"RS_LEAN", &Options::lean}, {"RS_MMA_M", &Options::mma_m},
     {"RS_NBUF", &Options::nbuf}, {"RS_QSTAGES", &Options::qstages},
@@ -131,6 +132,7 @@ struct rs_index {
   unsigned int launch_parity = 0;
   float* g_best = nullptr;           // shared bound table [sm_count][256] (k > 16 and wide searches)
   void* cbuf = nullptr;              // wide searches: candidate buffers [256][grid][32] x 8 B
+  int dm_pair_clusters = 0;          // same for the doc-major pair kernel (two-accumulator searches, B <= 32, k <= 16)
   int pair_clusters = -1;            // CTA pairs of the pair kernel this device keeps resident at once (-1: not queried)
   unsigned long long* debug_ts = nullptr;  // RS_DEBUG_TS=1: [grid][8] phase stamps of the last fused launch
   unsigned int* err_flag = nullptr;  // mapped pinned word a kernel raises when a wait times out (1: own CTAs, 2: a peer GPU)
@@ -406,18 +408,36 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
                     k <= rs::fused_reg_k() && pl.bpad <= 32 && pl.sub == 1 && o.docm != 0 &&
                     rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, 1, pl.qstages, pl.bufc, pl.lg, 1) <= kMaxSmem;
   if (docm) pl.nbuf = 8;
+  // Two accumulators (fp32 storage / two query terms) on a large corpus: the CTA-pair form of the doc-major kernel,
+  // where each CTA keeps only HALF of the Q image and the document ring doubles (fused_search_dmpair_kernel).
+  const int nacc = (terms == 2 || ix->planes == 2) ? 2 : 1;
+  // (B <= 16: the whole image is 64 KiB anyway, and the one-CTA kernel keeps its in-kernel query prep)
+  bool dmpair = docm && nacc == 2 && pl.bpad > 16 && o.dmpair != 0 && ix->dm_pair_clusters > 0 && ix->n_tiles >= 8 * ix->sm_count;
+  if (dmpair) {
+    pl.bpad = 32;
+    pl.cps = o.cps > 0 ? o.cps : (ix->planes == 2 ? 2 : 4);  // 64 KiB ring stages
+    if (ix->kc % pl.cps != 0) pl.cps = 1;
+    const int fixed = rs::fused_dmpair_smem_bytes(ix->kc, terms, ix->planes, 0, pl.cps);
+    const int stage_bytes = ix->planes * pl.cps * RS_BLOCK_BYTES;
+    pl.stages = std::min(8, (kMaxSmem - fixed) / stage_bytes);
+    if (pl.stages < 2) dmpair = false;
+  }
   // CTAs that own tiles.  Pair kernel: both CTAs of every pair that owns a supertile (two tiles)
-  const int n_work = pl.wide == 2 ? 2 * std::min(ix->pair_clusters, (ix->n_tiles + 1) / 2) : std::min(ix->sm_count, ix->n_tiles);
+  const int n_work = pl.wide == 2 ? 2 * std::min(ix->pair_clusters, (ix->n_tiles + 1) / 2)
+                     : dmpair     ? 2 * std::min(ix->dm_pair_clusters, (ix->n_tiles + 1) / 2)
+                                  : std::min(ix->sm_count, ix->n_tiles);
   const int n_lists = pl.wide == 2 ? n_work / 2 : n_work;  // candidate lists per query
   // single-launch search (default): query prep in the fused kernel's prologue (resident-Q plans) and the
   // candidate merge (+ exchange) in its tail.  RS_INLINE_PREP=0 / RS_FUSED_TAIL=0 fall back to the
   // separate query_prep_kernel / merge kernels.
-  const bool inline_prep = !pl.wide && pl.q_resident == 1 && ix->cfg.dim <= 1024 && pl.bpad <= 32 && o.inline_prep != 0;
-  const int tail_cap = pl.wide == 2 ? rs::fused_pair_tail_capacity(k) : pl.wide ? rs::fused_wide_tail_capacity(k)
+  const bool inline_prep = !pl.wide && !dmpair && pl.q_resident == 1 && ix->cfg.dim <= 1024 && pl.bpad <= 32 && o.inline_prep != 0;
+  const int tail_cap = dmpair ? rs::fused_dmpair_tail_capacity(ix->kc, terms, ix->planes, pl.stages, pl.cps)
+                       : pl.wide == 2 ? rs::fused_pair_tail_capacity(k) : pl.wide ? rs::fused_wide_tail_capacity(k)
                                : rs::fused_tail_smem_capacity(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, pl.qstages);
   const bool fused_tail = o.fused_tail != 0 && rs::fused_tail_smem_bytes(n_lists, k, xg ? xg->world : 1) <= (size_t)tail_cap;
   // pair kernel: whole pairs; every resident pair when the tail needs merging CTAs for up to 256 queries
   const int grid = pl.wide == 2 ? (fused_tail ? 2 * ix->pair_clusters : n_work)
+                   : dmpair     ? n_work  // >= 8 tiles per SM: far more worker CTAs than queries
                                 : fused_tail ? std::max(n_work, std::min(pl.per_pass, ix->sm_count)) : n_work;
   // overlapped launches (RS_OVERLAP=1): the scan of this search may run while the previous search's tail drains.
   // Only for plans that touch no shared workspace before the tail (register lists, Q image built in shared memory).
@@ -428,12 +448,13 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   const bool shared_bound = (k > rs::fused_reg_k() || pl.wide) && n_lists * bound_rank >= k && o.shared_bound != 0;
   ix->stats.grid = grid;
   ix->stats.stages = pl.stages;
-  ix->stats.smem_bytes = pl.wide == 2 ? rs::fused_pair_smem_bytes(k) : pl.wide ? rs::fused_wide_smem_bytes(k)
+  ix->stats.smem_bytes = dmpair ? rs::fused_dmpair_smem_bytes(ix->kc, terms, ix->planes, pl.stages, pl.cps)
+                         : pl.wide == 2 ? rs::fused_pair_smem_bytes(k) : pl.wide ? rs::fused_wide_smem_bytes(k)
                                  : rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, pl.qstages, pl.bufc, pl.lg, docm);
   ix->stats.q_resident = pl.q_resident;
   ix->stats.sub = pl.sub;
   ix->stats.nbuf = pl.nbuf;
-  ix->stats.mma_m = pl.mma_m;
+  ix->stats.mma_m = dmpair ? 256 : pl.mma_m;
   ix->stats.overlapped = pdl ? 1 : 0;
   ix->stats.doc_major = docm ? 1 : 0;
   ix->stats.passes = pl.passes;
@@ -503,6 +524,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.bufc = pl.bufc;
     p.lists_global = pl.lg;
     p.docm = docm ? 1 : 0;
+    p.dmpair = dmpair ? 1 : 0;
     p.wide = pl.wide;
     p.cbuf = reinterpret_cast<uint2*>(ix->cbuf);
     p.qstages = pl.qstages;
@@ -699,6 +721,8 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   RS_ALLOC(cudaMalloc(&ix->ingest_dev, kIngestChunkBytes));
   RS_ALLOC(cudaHostAlloc(&ix->pinned, ix->pinned_bytes, cudaHostAllocPortable));
   RS_ALLOC(cudaMalloc(&ix->g_best, (size_t)prop.multiProcessorCount * pass_rows * sizeof(float)));
+  // doc-major pair kernel: pairs the device keeps resident (largest shared-memory configuration)
+  ix->dm_pair_clusters = std::min(rs::fused_dmpair_max_clusters(kMaxSmem), prop.multiProcessorCount / 2);
   if (cfg->max_batch > 128) {
     RS_ALLOC(cudaMalloc(&ix->cbuf, (size_t)grid * pass_rows * rs::fused_wide_bufc() * sizeof(uint2)));
     ix->pair_clusters = ix->planes == 1 ? std::min(rs::fused_pair_max_clusters(cfg->max_k), prop.multiProcessorCount / 2) : 0;
@@ -1224,6 +1248,80 @@ RS_API int rs_debug_timestamps(rs_index* ix, uint64_t* out, int32_t n_ctas) {
   if (!ix->debug_ts) return fail(RS_E_STATE, "no stamps recorded: run a search with RS_DEBUG_TS=1 first");
   RS_CUDA(cudaDeviceSynchronize());
   RS_CUDA(cudaMemcpy(out, ix->debug_ts, (size_t)n_ctas * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return RS_OK;
+}
+
+// ---------------------------------------------------------------- document arena (host side: SURVEY §8f.3)
+struct rs_docs {
+  std::vector<char> arena;
+  std::vector<int64_t> off;  // n + 1
+};
+
+RS_API int rs_docs_create(const char* arena, const int64_t* offsets, int64_t n_docs, rs_docs** out) {
+  if (!offsets || !out || n_docs < 0 || (n_docs > 0 && offsets[n_docs] > 0 && !arena)) return fail(RS_E_INVALID, "null argument");
+  *out = nullptr;
+  if (offsets[0] != 0) return fail(RS_E_INVALID, "offsets[0] must be 0");
+  for (int64_t i = 0; i < n_docs; ++i)
+    if (offsets[i + 1] < offsets[i]) return fail(RS_E_INVALID, "offsets must not decrease (document %lld)", (long long)i);
+  rs_docs* d = new (std::nothrow) rs_docs;
+  if (!d) return fail(RS_E_INVALID, "out of memory");
+  try {
+    d->off.assign(offsets, offsets + n_docs + 1);
+    d->arena.assign(arena, arena + offsets[n_docs]);
+  } catch (...) {
+    delete d;
+    return fail(RS_E_INVALID, "out of memory");
+  }
+  *out = d;
+  return RS_OK;
+}
+
+RS_API int rs_docs_destroy(rs_docs* d) {
+  delete d;
+  return RS_OK;
+}
+
+RS_API int rs_docs_join(const rs_docs* d, const int64_t* idx, int32_t B, int32_t stride, const int32_t* ks, const char* sep,
+                        int32_t sep_len, char* out, int64_t out_cap, int64_t* out_offsets, int64_t* need) {
+  if (!d || !idx || !ks || !out_offsets || !need || B < 0 || stride < 0 || sep_len < 0 || (sep_len > 0 && !sep))
+    return fail(RS_E_INVALID, "bad argument");
+  const int64_t n = (int64_t)d->off.size() - 1;
+  // pass 1: sizes (and validation); pass 2: copy, only if the caller's buffer is large enough
+  int64_t total = 0;
+  out_offsets[0] = 0;
+  for (int32_t i = 0; i < B; ++i) {
+    const int32_t ki = std::min(ks[i], stride);
+    int64_t bytes = 0;
+    int32_t hits = 0;
+    for (int32_t j = 0; j < stride && hits < ki; ++j) {
+      const int64_t r = idx[(size_t)i * stride + j];
+      if (r < 0) continue;  // padding (-1) of rows with fewer than k valid documents
+      if (r >= n) return fail(RS_E_INVALID, "index %lld of query %d outside the %lld documents", (long long)r, i, (long long)n);
+      bytes += (hits ? sep_len : 0) + (d->off[r + 1] - d->off[r]);
+      ++hits;
+    }
+    total += bytes;
+    out_offsets[i + 1] = total;
+  }
+  *need = total;
+  if (!out || out_cap < total) return RS_OK;  // sizes only: call again with a buffer of *need bytes
+  for (int32_t i = 0; i < B; ++i) {
+    const int32_t ki = std::min(ks[i], stride);
+    char* w = out + out_offsets[i];
+    int32_t hits = 0;
+    for (int32_t j = 0; j < stride && hits < ki; ++j) {
+      const int64_t r = idx[(size_t)i * stride + j];
+      if (r < 0) continue;
+      if (hits) {
+        memcpy(w, sep, (size_t)sep_len);
+        w += sep_len;
+      }
+      const int64_t len = d->off[r + 1] - d->off[r];
+      memcpy(w, d->arena.data() + d->off[r], (size_t)len);
+      w += len;
+      ++hits;
+    }
+  }
   return RS_OK;
 }
 

@@ -877,8 +877,11 @@ __device__ __forceinline__ void fused_tail(const SearchParams& p, uint8_t* smem,
 struct DmBars {
   uint32_t tfull0, tempty0, sched_full0, sched_empty0, qfull;
   volatile int* tile_u;
+  // CTA-pair variant (fused_search_dmpair_kernel): static schedule, accumulators handed back to the LEADER's issuer
+  int pair, n_pairs, rank;
+  uint32_t tempty_leader0;  // shared::cluster address of the leader's tempty[0]
 };
-template <int KS, int NACC>
+template <int KS, int NACC, bool PAIR = false>
 __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars& b, uint32_t tmem_base, int w, int lane,
                                             float* dump /* this warp's [32][32] */, float* s_qnorm, float* s_qscale,
                                             bool inline_prep, bool worker, float* out_s /* [4][32][k] */, int* out_i) {
@@ -908,18 +911,26 @@ __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars&
   }
   int acc = 0, sslot = 0;
   uint32_t acc_ph = 0, sph = 0;
+  int pu = b.pair;  // PAIR: tile pair of this iteration
   while (true) {
-    mbar_wait(b.sched_full0 + 8u * sslot, sph);
-    const int t = b.tile_u[sslot];
-    __syncwarp();
-    if (lane == 0) mbar_arrive(b.sched_empty0 + 8u * sslot);
-    if (++sslot == kSched) {
-      sslot = 0;
-      sph ^= 1u;
+    int t;
+    if constexpr (PAIR) {
+      if (!worker || pu >= (p.n_tiles + 1) / 2) break;
+      t = 2 * pu + b.rank;  // an odd tile count leaves the peer's last tile empty: t == n_tiles, every document masked
+      pu += b.n_pairs;
+    } else {
+      mbar_wait(b.sched_full0 + 8u * sslot, sph);
+      t = b.tile_u[sslot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b.sched_empty0 + 8u * sslot);
+      if (++sslot == kSched) {
+        sslot = 0;
+        sph ^= 1u;
+      }
+      if (t < 0) break;
     }
-    if (t < 0) break;
     const int doc0 = t * RS_TILE_ROWS + w * 32;
-    const float nd = cosine ? __ldg(p.dnorm + doc0 + lane) : 1.f;  // dnorm is padded to whole tiles
+    const float nd = (cosine && t < p.n_tiles) ? __ldg(p.dnorm + doc0 + lane) : 1.f;  // dnorm is padded to whole tiles
     mbar_wait(b.tfull0 + 8u * acc, acc_ph);
     tc_fence_after();
     float v[32];
@@ -941,7 +952,10 @@ __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars&
     // the scores are in registers: hand the accumulator back before looking at them
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(b.tempty0 + 8u * acc);
+    if (lane == 0) {
+      if constexpr (PAIR) mbar_arrive_remote(b.tempty_leader0 + 8u * acc);
+      else mbar_arrive(b.tempty0 + 8u * acc);
+    }
     if (++acc == p.nbuf) {
       acc = 0;
       acc_ph ^= 1u;
@@ -1008,6 +1022,43 @@ __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars&
       }
     }
   }
+}
+
+// Doc-major kernels: the four warps' lists of query q (best first, shared memory at offset 0: [4][32][k] scores, then
+// ids) -> the CTA's one list in cand_* (list index = blockIdx.x).  Whole CTA; ends with a barrier.
+__device__ __forceinline__ void dm_publish_cta_lists(const SearchParams& p, const uint8_t* smem, const bool worker) {
+  // the four warps' lists of query q (best first, shared memory) -> the CTA's one list in cand_*
+  if (worker && (int)threadIdx.x < p.n_queries) {
+    const int q = threadIdx.x, k = p.k;
+    const float* ss = reinterpret_cast<const float*>(smem);
+    const int* si = reinterpret_cast<const int*>(smem + 4 * 32 * kRegK * sizeof(float));
+    float* cs = p.cand_score + ((size_t)q * p.n_work + blockIdx.x) * k;
+    int* ci = p.cand_idx + ((size_t)q * p.n_work + blockIdx.x) * k;
+    int h[4] = {0, 0, 0, 0};
+    for (int r = 0; r < k; ++r) {
+      int bw = -1, bi = 0;
+      float bs = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        if (h[w] < k) {
+          const int id = si[(size_t)(w * 32 + q) * k + h[w]];
+          const float sc = ss[(size_t)(w * 32 + q) * k + h[w]];
+          if (id >= 0 && (bw < 0 || sc > bs || (sc == bs && id < bi))) {
+            bw = w;
+            bs = sc;
+            bi = id;
+          }
+        }
+      }
+      cs[r] = bw < 0 ? -CUDART_INF_F : bs;
+      ci[r] = bw < 0 ? -1 : bi;
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (w == bw) ++h[w];
+    }
+    if (p.tail_mode != 0) __threadfence();
+  }
+  __syncthreads();
 }
 
 // One CTA walks "supertiles" of p.sub consecutive 128-document tiles.  Per supertile the K loop
@@ -1318,7 +1369,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const __grid_
       if (threadIdx.x == kFirstEpiWarp * 32) stamp(p.debug_ts, 1);  // query prep done
     }
     if constexpr (DOCM) {
-      const DmBars bars{tfull_bar(0), tempty_bar(0), sched_full(0), sched_empty(0), qfull_bar, tile_u};
+      const DmBars bars{tfull_bar(0), tempty_bar(0), sched_full(0), sched_empty(0), qfull_bar, tile_u, 0, 0, 0, 0u};
       // lists of the four warps go to shared memory at offset 0: by then the last accumulator is complete, so
       // the Q image and the ring are dead
       dm_epilogue<kSched, NACC>(p, bars, tmem_base, quarter, lane, reinterpret_cast<float*>(smem + map.dump_off) + quarter * 1024,
@@ -1612,40 +1663,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const __grid_
   griddep_wait();
   if (p.pdl != 2) griddep_launch_dependents();
 
-  if constexpr (DOCM) {
-    // the four warps' lists of query q (best first, shared memory) -> the CTA's one list in cand_*
-    if (worker && (int)threadIdx.x < p.n_queries) {
-      const int q = threadIdx.x, k = p.k;
-      const float* ss = reinterpret_cast<const float*>(smem);
-      const int* si = reinterpret_cast<const int*>(smem + 4 * 32 * kRegK * sizeof(float));
-      float* cs = p.cand_score + ((size_t)q * p.n_work + blockIdx.x) * k;
-      int* ci = p.cand_idx + ((size_t)q * p.n_work + blockIdx.x) * k;
-      int h[4] = {0, 0, 0, 0};
-      for (int r = 0; r < k; ++r) {
-        int bw = -1, bi = 0;
-        float bs = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          if (h[w] < k) {
-            const int id = si[(size_t)(w * 32 + q) * k + h[w]];
-            const float sc = ss[(size_t)(w * 32 + q) * k + h[w]];
-            if (id >= 0 && (bw < 0 || sc > bs || (sc == bs && id < bi))) {
-              bw = w;
-              bs = sc;
-              bi = id;
-            }
-          }
-        }
-        cs[r] = bw < 0 ? -CUDART_INF_F : bs;
-        ci[r] = bw < 0 ? -1 : bi;
-#pragma unroll
-        for (int w = 0; w < 4; ++w)
-          if (w == bw) ++h[w];
-      }
-      if (p.tail_mode != 0) __threadfence();
-    }
-    __syncthreads();
-  }
+  if constexpr (DOCM) dm_publish_cta_lists(p, smem, worker);
   fused_tail(p, smem, worker);
 }
 
@@ -2588,6 +2606,215 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
   fused_tail(p, smem, worker);
 }
 
+// ==========================================================================================
+// CTA-pair variant of the DOC-MAJOR kernel (two accumulators: fp32 storage and/or two query terms; B <= 32, k <= 16,
+// large corpora).  The doc-major kernel keeps the whole Q image resident; with two terms that is 128 KiB at B = 32
+// and leaves the document ring 64 KiB, which is what holds fp32 corpora at 0.86 of the HBM roofline (B = 16, with a
+// 64 KiB image, streams at 1.0).  Here two SMs run one tcgen05.mma.cta_group::2 chain: M = 256 = the two CTAs'
+// document tiles (each CTA streams its OWN tile, both planes), N = 32 = the queries, of which each CTA holds HALF
+// (16 rows of the N operand: the tensor cores fetch the other half through the pair link).  The resident image
+// shrinks to 64 KiB per CTA and the ring doubles.  Each CTA's TMEM receives its 128 documents x 32 queries
+// (x 2 accumulators, 8 buffers), so the epilogue, the per-CTA candidate lists and the tail are the doc-major
+// kernel's (dm_epilogue<.., PAIR>).  Barriers and the relay are the wide pair kernel's.  Query prep is the
+// stand-alone kernel (each CTA bulk-copies its 16 rows of every k-chunk block).
+// ==========================================================================================
+struct DmPairSmem {
+  uint32_t q_bytes, stage_off, stage_bytes, bar_off, dump_off, total;
+};
+__host__ __device__ inline DmPairSmem make_dmpair_smem(int kc, int terms, int planes, int stages, int cps) {
+  DmPairSmem m;
+  m.q_bytes = (uint32_t)(terms * kc) * 2048u;  // per (term, k-chunk): 16 query rows x 128 B
+  m.stage_off = m.q_bytes;
+  m.stage_bytes = (uint32_t)(planes * cps) * RS_BLOCK_BYTES;
+  m.bar_off = m.stage_off + (uint32_t)stages * m.stage_bytes;
+  m.dump_off = m.bar_off + 2048u;  // [bar_off, +1 KiB) barriers + TMEM address, then qnorm[128], qscale[128]
+  m.total = m.dump_off + 4u * 32u * 32u * 4u;
+  return m;
+}
+
+template <int NACC>
+__global__ void __launch_bounds__(kThreads, 1) fused_search_dmpair_kernel(const __grid_constant__ SearchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = (int)blockIdx.x >> 1;
+  const int n_pairs = (int)gridDim.x >> 1;
+  const int cps = p.cps, NB = p.nbuf;
+  const DmPairSmem map = make_dmpair_smem(p.kc, p.terms, p.planes, p.stages, cps);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t q_smem = smem_base, stage_smem = smem_base + map.stage_off, bar_base = smem_base + map.bar_off;
+  auto full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty = [&](int s) { return bar_base + 8u * (uint32_t)(8 + s); };
+  auto tfull = [&](int a) { return bar_base + 8u * (uint32_t)(16 + a); };
+  auto tempty = [&](int a) { return bar_base + 8u * (uint32_t)(24 + a); };
+  const uint32_t qfull = bar_base + 8u * 32u;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + map.bar_off + 1016);
+  float* s_qnorm = reinterpret_cast<float*>(smem + map.bar_off + 1024);
+  float* s_qscale = s_qnorm + 128;
+  const int n_super = (p.n_tiles + 1) / 2;
+  const bool worker = pair < n_super && (int)blockIdx.x < p.n_work;
+  const size_t tile_bytes = (size_t)p.planes * p.kc * RS_BLOCK_BYTES;
+  const uint32_t tmem_cols = (uint32_t)(NB * NACC) * 32u;
+
+  if (threadIdx.x == 0) {
+    stamp(p.debug_ts, 0);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full(s), rank == 0 ? 2u : 1u);  // leader: its own copies + the peer's relay
+      mbar_init(empty(s), 1);
+    }
+    for (int a = 0; a < 8; ++a) {
+      mbar_init(tfull(a), 1);
+      mbar_init(tempty(a), 2 * kNumEpiWarps);  // leader only: the epilogue warps of both CTAs
+    }
+    mbar_init(qfull, rank == 0 ? 2u : 1u);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc_pair(smem_u32((const void*)tmem_slot), tmem_cols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    if (worker) {
+      const uint64_t pol_stream = l2_policy_evict_first();
+      const uint64_t pol_keep = l2_policy_evict_last();
+      if (lane == 0) {  // this CTA's 16 rows of every (term, k-chunk) block of the Q image
+        mbar_arrive_expect_tx(qfull, map.q_bytes);
+        for (int blk = 0; blk < p.terms * p.kc; ++blk)
+          bulk_g2s(q_smem + (uint32_t)blk * 2048u, p.qimg + (size_t)blk * 4096u + (size_t)rank * 2048u, 2048u, qfull, pol_keep);
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t plane_bytes = (uint32_t)cps * RS_BLOCK_BYTES;
+      for (int u = pair; u < n_super; u += n_pairs) {
+        const int tile = (2 * u + (int)rank < p.n_tiles) ? 2 * u + (int)rank : 2 * u;  // odd tail: masked duplicate
+        const uint8_t* src = p.corpus + (size_t)tile * tile_bytes;
+        for (int kc = 0; kc < p.kc; kc += cps) {
+          mbar_wait_guarded<false>(empty(s), ph ^ 1u, p.err_flag);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(full(s), map.stage_bytes);
+            for (int pl = 0; pl < p.planes; ++pl)
+              bulk_g2s(stage_smem + (uint32_t)s * map.stage_bytes + (uint32_t)pl * plane_bytes,
+                       src + (size_t)(pl * p.kc + kc) * RS_BLOCK_BYTES, plane_bytes, full(s), pol_stream);
+          }
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+      for (int i = 0; i < p.stages; ++i) {  // drain the last multicast commits
+        mbar_wait_guarded<false>(empty(s), ph ^ 1u, p.err_flag);
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (worker && rank == 0) {
+      // ===================== MMA issuer (leader): M = 256 (two document tiles) x N = 32 (queries) x K = 16 =====================
+      const uint32_t idesc = umma_idesc_f16(p.dtype == RS_DTYPE_BF16, 256, 32);
+      const bool skip_mma = (p.debug_flags & 1) != 0;
+      mbar_wait_guarded<true>(qfull, 0, p.err_flag);
+      tc_fence_after();
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_ph = 0;
+      const uint32_t plane_bytes = (uint32_t)cps * RS_BLOCK_BYTES;
+      for (int u = pair; u < n_super; u += n_pairs) {
+        mbar_wait_guarded<true>(tempty(acc), acc_ph ^ 1u, p.err_flag);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * NACC) * 32u, d1 = d0 + 32u;
+        for (int kc = 0; kc < p.kc; kc += cps) {
+          mbar_wait_guarded<true>(full(s), ph, p.err_flag);
+          tc_fence_after();
+          if (lane == 0) {
+            if (!skip_mma) {
+              const uint32_t st = stage_smem + (uint32_t)s * map.stage_bytes;
+              for (int c = 0; c < cps; ++c) {
+                const bool fresh = (kc + c) == 0;
+                const uint64_t a_hi = umma_smem_desc(st + (uint32_t)c * RS_BLOCK_BYTES);
+                const uint64_t b_hi = umma_smem_desc(q_smem + (uint32_t)(kc + c) * 2048u);
+#pragma unroll
+                for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
+                  umma_f16_pair(d0, a_hi + 2u * ks, b_hi + 2u * ks, idesc, (fresh && ks == 0) ? 0u : 1u);
+                if (NACC == 2) {
+                  const uint64_t b_lo = umma_smem_desc(q_smem + (uint32_t)(p.kc + kc + c) * 2048u);
+#pragma unroll
+                  for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
+                    umma_f16_pair(d1, a_hi + 2u * ks, b_lo + 2u * ks, idesc, (fresh && ks == 0) ? 0u : 1u);
+                  if (p.planes == 2) {  // lo plane of an fp32 corpus: q_hi . d_lo joins the low-order accumulator
+                    const uint64_t a_lo = umma_smem_desc(st + plane_bytes + (uint32_t)c * RS_BLOCK_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
+                      umma_f16_pair(d1, a_lo + 2u * ks, b_hi + 2u * ks, idesc, 1u);
+                  }
+                }
+              }
+            }
+            umma_commit_pair(empty(s));
+          }
+          __syncwarp();
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        if (lane == 0) umma_commit_pair(tfull(acc));
+        __syncwarp();
+        if (++acc == NB) {
+          acc = 0;
+          acc_ph ^= 1u;
+        }
+      }
+    } else if (worker) {
+      // ===================== relay (peer) =====================
+      const uint32_t full_leader = mapa_u32(full(0), 0);
+      mbar_wait_guarded<false>(qfull, 0, p.err_flag);
+      if (lane == 0) mbar_arrive_remote(mapa_u32(qfull, 0));
+      __syncwarp();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int u = pair; u < n_super; u += n_pairs) {
+        for (int kc = 0; kc < p.kc; kc += cps) {
+          mbar_wait_guarded<false>(full(s), ph, p.err_flag);
+          if (lane == 0) mbar_arrive_remote(full_leader + 8u * (uint32_t)s);
+          __syncwarp();
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const DmBars bars{tfull(0), tempty(0), 0u, 0u, qfull, nullptr, pair, n_pairs, (int)rank, mapa_u32(tempty(0), 0)};
+    dm_epilogue<8, NACC, true>(p, bars, tmem_base, quarter, lane, reinterpret_cast<float*>(smem + map.dump_off) + quarter * 1024,
+                               s_qnorm, s_qscale, false, worker, reinterpret_cast<float*>(smem),
+                               reinterpret_cast<int*>(smem + 4 * 32 * kRegK * sizeof(float)));
+  }
+
+  if (p.tail_mode != 0) __threadfence();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, tmem_cols);
+  }
+  dm_publish_cta_lists(p, smem, worker);
+  fused_tail(p, smem, worker);
+}
+
 // smem bytes the tail needs at offset 0 (result row + staged lists of one query)
 size_t fused_tail_smem_bytes(int n_lists, int k, int world) {
   return merge_res_bytes(k) + std::max((size_t)n_lists * k * 8, (size_t)world * k * 12);
@@ -2793,7 +3020,46 @@ static cudaError_t launch_fused_pair(const SearchParams& p, int grid, cudaStream
   return cudaLaunchKernelEx(&cfg, fused_search_pair_kernel, p);
 }
 
+int fused_dmpair_smem_bytes(int kc, int terms, int planes, int stages, int cps) {
+  return (int)make_dmpair_smem(kc, terms, planes, stages, cps).total + 1024;
+}
+int fused_dmpair_tail_capacity(int kc, int terms, int planes, int stages, int cps) {
+  return (int)make_dmpair_smem(kc, terms, planes, stages, cps).bar_off;
+}
+int fused_dmpair_max_clusters(int smem_bytes) {
+  if (cudaFuncSetAttribute(fused_search_dmpair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  pair_launch_config(&cfg, attr, sms & ~1, smem_bytes, nullptr);
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, fused_search_dmpair_kernel<2>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+static cudaError_t launch_fused_dmpair(const SearchParams& p, int grid, cudaStream_t stream) {
+  const int nacc = (p.terms == 2 || p.planes == 2) ? 2 : 1;
+  if (p.bpad != 32 || p.n_queries > 32 || p.k > kRegK || (grid & 1) || (p.n_work & 1) || p.nbuf * nacc * 32 > 512 ||
+      p.nbuf < 1 || p.nbuf > 8 || p.stages < 2 || p.stages > 8 || p.kc % p.cps != 0 || nacc != 2 || p.inline_prep)
+    return cudaErrorInvalidValue;
+  const int bytes = fused_dmpair_smem_bytes(p.kc, p.terms, p.planes, p.stages, p.cps);
+  cudaError_t e = cudaFuncSetAttribute(fused_search_dmpair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  pair_launch_config(&cfg, attr, grid, bytes, stream);
+  return cudaLaunchKernelEx(&cfg, fused_search_dmpair_kernel<2>, p);
+}
+
 cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t stream) {
+  if (p.dmpair) return launch_fused_dmpair(p, grid, stream);
   if (p.wide == 2) return launch_fused_pair(p, grid, stream);
   if (p.wide) return launch_fused_wide(p, grid, stream);
   const bool reglist = p.k <= kRegK;

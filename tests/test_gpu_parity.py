@@ -196,6 +196,8 @@ def test_cosine_equals_reference_cupy_class_golden(golden):
     for row, exp in zip(got, golden.cos_idx_var):
         assert row == [golden.contexts[i] for i in exp if i >= 0]
     assert c.retrieve(Q[3], k) == golden.cos_texts[3]
+    # contexts gathered and joined from the byte arena (rs_docs_join): what batch_processor.py:100 builds per request
+    assert c.batch_retrieve_contexts(Q, [k] * len(Q)) == ["\n---\n".join(t) for t in golden.cos_texts]
     c.close()
 
 
@@ -661,6 +663,39 @@ def test_wide_batch_kernel_sweep(dtype, metric, B, k, N):
         i3, s3 = ix.search(Q, k, metric, 1)
         assert ix.stats()["passes"] == -(-B // 128)
         assert np.array_equal(idx, i3) and np.array_equal(sc, s3)
+    finally:
+        ix.close()
+
+
+@pytest.mark.parametrize("dtype,terms,metric,B,k,N", [
+    ("fp32", 2, "cosine", 32, 10, 128 * 1184 + 77), ("fp32", 2, "dot", 17, 16, 128 * 1185), ("bf16", 2, "dot", 32, 1, 128 * 1186 + 1),
+    ("fp16", 2, "cosine", 19, 5, 128 * 1300 + 127)])
+def test_doc_major_pair_kernel(dtype, terms, metric, B, k, N):
+    """fused_search_dmpair_kernel (two accumulators, B <= 32, k <= 16, >= 8 tiles per SM: each CTA of a pair keeps half
+    of the Q image, M = 256 MMAs over the two CTAs' document tiles): odd and even tile counts, ragged last tile, both
+    metrics, fp32 storage and two-term 16-bit queries - against the oracle, and equal to the one-CTA kernel."""
+    sx = 4 if dtype == "fp32" else 0
+    E = o.synth_rows(29, np.arange(N))
+    rng = np.random.default_rng(7)
+    src = rng.integers(0, N, B)
+    src[:2] = [N - 1, 0]
+    Q = (E[src] + 0.03 * rng.standard_normal((B, 1024))).astype(np.float32)
+    ix = make_index(E, dtype, sx, max_batch=32, max_k=16)
+    try:
+        idx, sc = ix.search(Q, k, metric, terms)
+        st = ix.stats()
+        assert st["doc_major"] == 1 and st["mma_m"] == 256 and st["grid"] % 2 == 0 and st["launches"] == 2, st
+        S = exact_scores(Q, E, dtype, metric, terms, sx)
+        o.check_topk(idx, sc, S, k, rtol=RTOL[dtype], atol=1e-6)
+        assert (idx[:, 0] == src).all()
+        for _ in range(3):
+            i2, s2 = ix.search(Q, k, metric, terms)
+            assert np.array_equal(idx, i2) and np.array_equal(sc, s2)
+        ix.set_option("RS_DMPAIR", 0)                       # the one-CTA doc-major kernel: same values up to the order in
+        i3, s3 = ix.search(Q, k, metric, terms)             # which the three MMA chains reach the low-order accumulator
+        assert ix.stats()["mma_m"] != 256
+        o.check_topk(i3, s3, S, k, rtol=RTOL[dtype], atol=1e-6)
+        assert np.allclose(sc, s3, rtol=2e-6, atol=1e-7) and (idx == i3).mean() > 0.99
     finally:
         ix.close()
 

@@ -257,3 +257,42 @@ def test_rows_to_docs_matches_reference_slicing():
     got = _rows_to_docs(docs, np.array([[3, 4]], dtype=np.int64), [2])
     got[0].append("x")                                  # fresh lists: mutating the result never touches documents
     assert docs[3] == "d3" and len(docs) == 50
+
+
+def test_document_arena_join_matches_reference_joins(squad):
+    """rs_docs_* (host code of the C ABI, no GPU): per query the first k_i valid hits joined with the separator of
+    batch_processor.py:100 == "\\n---\\n".join(documents[i] ...) of the reference's slicing (retriever.py:776-790);
+    padding (-1), k_i <= 0, k_i > stride, non-ASCII and empty documents."""
+    docs = list(squad.contexts[:200]) + ["", "éü中文 \U0001f600", "tail"]
+    arena = _cabi.DocArena(docs)
+    rng = np.random.default_rng(1)
+    idx = rng.integers(0, len(docs), (16, 7))
+    idx[2, 4:] = -1
+    idx[3, :] = -1
+    idx[4, :3] = [200, 201, 202]
+    ks = [7, 2, 7, 5, 3, 0, -4, 100, 1, 7, 7, 6, 5, 4, 3, 2]
+    want = ["\n---\n".join(docs[j] for j in [x for x in row if x >= 0][:max(0, k)]) for row, k in zip(idx.tolist(), ks)]
+    assert arena.join(idx, ks) == want
+    assert arena.join(idx, ks, sep=" | ") == [w.replace("\n---\n", " | ") for w in want]
+    assert arena.join(np.zeros((0, 3), np.int64), []) == []
+    with pytest.raises(_cabi.RsError):
+        arena.join(np.array([[len(docs)]]), [1])            # an index outside the corpus is an error, not a crash
+    arena.close()
+
+
+def test_batch_retrieve_contexts_equals_joined_batch_retrieve(fake_backend, squad):
+    """batch_retrieve_contexts == [sep.join(d) for d in batch_retrieve(...)] (batch_processor.py:95-100), including
+    the reference's error conventions, and assemble_prompts == the template of batch_processor.py:103."""
+    r = retriever.CupyRetriever(squad.E, squad.contexts)
+    ks = list(squad.ks_var)
+    want = ["\n---\n".join(d) for d in r.batch_retrieve(squad.cos_Q, ks)]
+    assert r.batch_retrieve_contexts(squad.cos_Q, ks) == want
+    fixed = r.batch_retrieve_contexts(squad.cos_Q, [squad.k] * len(squad.cos_Q))
+    assert fixed == ["\n---\n".join(t) for t in squad.cos_texts]      # strings of the unmodified reference class, joined
+    assert r.batch_retrieve_contexts(squad.cos_Q, [0] * len(ks)) == [""] * len(ks)
+    assert r.batch_retrieve_contexts(squad.cos_Q[:, :5], ks) == [""] * len(ks)          # wrong dimension: [] rows
+    assert r.batch_retrieve_contexts("nope", ks) == [""] * len(ks)
+    qs = [f"q{i}" for i in range(len(ks))]
+    prompts = r.assemble_prompts(qs, want)
+    assert prompts[3] == f"Context:\n{want[3]}\n\nQuestion: q3\n\nThe Answer to this question is: "
+    r.close()
