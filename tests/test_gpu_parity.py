@@ -6,6 +6,7 @@ only inside the rounding band around the k-th score and is reported), scores wit
 relative for fp32 storage, 2e-3 for bf16/fp16."""
 import numpy as np
 import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
 
 from oracle import retrieval_oracle as o
 from rag_serving_system_b200 import CupyRetriever, SimpleRetriever, B200Retriever, _cabi
@@ -696,6 +697,42 @@ def test_doc_major_pair_kernel(dtype, terms, metric, B, k, N):
         assert ix.stats()["mma_m"] != 256
         o.check_topk(i3, s3, S, k, rtol=RTOL[dtype], atol=1e-6)
         assert np.allclose(sc, s3, rtol=2e-6, atol=1e-7) and (idx == i3).mean() > 0.99
+    finally:
+        ix.close()
+
+
+# ---------------------------------------------------------------- property test over the whole shape space
+_PROP_ROWS = o.synth_rows(77, np.arange(128 * 310 + 57))      # generated once; a prefix of it is the corpus
+
+
+@settings(max_examples=100, deadline=None, derandomize=True,
+          suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture, HealthCheck.data_too_large])
+@given(n=st.one_of(st.integers(1, 600), st.integers(601, len(_PROP_ROWS))), B=st.integers(1, 256), k=st.integers(1, 100),
+       dtype=st.sampled_from(["bf16", "fp16", "fp32"]), metric=st.sampled_from(["dot", "cosine"]),
+       two_terms=st.booleans(), seed=st.integers(0, 2 ** 16))
+def test_property_any_shape_matches_oracle(n, B, k, dtype, metric, two_terms, seed):
+    """for ANY corpus size (not a multiple of the tile, fewer rows than k, one row), batch 1..256, k 1..100,
+    storage type, metric and query-term count, the kernel the planner picks (doc-major, query-major resident or
+    streamed, wide pair, k <= 16 register lists or k > 16 buffered lists) returns the oracle's top-k: index sets
+    identical up to provable near-ties, scores inside the tolerance, (-1, -inf) padding past the corpus size, and
+    the same answer when the call is repeated."""
+    E = _PROP_ROWS[:n]
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, n, B)
+    Q = (E[src] * (1.0 + rng.random((B, 1)).astype(np.float32)) + 0.05 * rng.standard_normal((B, 1024)).astype(np.float32))
+    terms = 2 if (two_terms or dtype == "fp32") else 1
+    if terms == 1:
+        Q = o.round_to_dtype(Q, DT[dtype])
+    sx = 4 if dtype == "fp32" else 0
+    ix = make_index(E, dtype, sx, max_batch=256, max_k=128)
+    try:
+        idx, sc = ix.search(Q, k, metric, terms)
+        S = exact_scores(Q, E, dtype, metric, terms, sx)
+        o.check_topk(idx, sc, S, k, rtol=RTOL[dtype], atol=1e-6)
+        if k > n:
+            assert (idx[:, n:] == -1).all() and np.isneginf(sc[:, n:]).all()
+        i2, s2 = ix.search(Q, k, metric, terms)
+        assert np.array_equal(idx, i2) and np.array_equal(sc, s2)
     finally:
         ix.close()
 
