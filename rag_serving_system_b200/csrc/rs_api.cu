@@ -79,7 +79,8 @@ struct Options {
   int wide = 2;          // RS_WIDE         batches above 128: 2 = one pass, CTA-pair kernel (cta_group::2); 1 = one pass, one CTA
                          //                 per SM; 0 = split into passes of 128
   int overlap = 0;       // RS_OVERLAP      1: consecutive device-buffer searches on one stream may overlap (PDL)
-  int debug_flags = 0;   // RS_DEBUG_FLAGS  timing experiments: skip MMAs (1) / the epilogue (2) / the tail merge (4)
+  int debug_flags = 0;   // RS_DEBUG_FLAGS  timing experiments: skip MMAs (1) / the epilogue (2) / the tail merge (4); pair kernel:
+                         //                 thresholds at +inf so nothing is ever appended (32), documents without the L2 evict_first hint (64)
   int debug_ts = 0;      // RS_DEBUG_TS     per-CTA %globaltimer phase stamps
   // planner overrides (tests and A/B runs): -1 / 0 = let the planner decide
   int qresident = -1, cps = 0, sub = 0, bufc = 0, lean = -1, mma_m = 0, nbuf = 0, qstages = 0;
@@ -228,7 +229,8 @@ int make_plan(const rs_index* ix, const Options& o, int B, int k, int terms, Pla
       // CTA pairs (fused_search_pair_kernel): M=256 x N=256 MMAs across two SMs, two TMEM accumulators
       pl->wide = 2;
       pl->qstages = 0;
-      pl->stages = 6;
+      pl->cps = (o.cps == 2 && ix->kc % 2 == 0) ? 2 : 1;  // k-chunks per ring slot (32 KiB each)
+      pl->stages = 6 / pl->cps;
       pl->nbuf = 2;
       pl->mma_m = 256;
       return RS_OK;

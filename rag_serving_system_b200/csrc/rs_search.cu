@@ -2177,9 +2177,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
   const PairSmem map = make_pair_smem(p.k);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_base + map.bar_off;
-  auto slot_addr = [&](int s) { return smem_base + (uint32_t)s * kPairSlotBytes; };
+  // a ring slot holds cps (1 or 2) consecutive k-chunks, each [16 KiB query rows][16 KiB documents]; n_slots x cps = 6
+  const int cps = p.cps, n_slots = kPairSlots / cps;
+  const uint32_t slot_bytes = (uint32_t)cps * kPairSlotBytes;
+  auto slot_addr = [&](int s) { return smem_base + (uint32_t)s * slot_bytes; };
   auto full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
-  auto empty = [&](int s) { return bar_base + 8u * (uint32_t)(kPairSlots + s); };
+  auto empty = [&](int s) { return bar_base + 8u * (uint32_t)(kPairSlots + s); };  // (indices sized for cps == 1)
   auto tfull = [&](int b) { return bar_base + 8u * (uint32_t)(2 * kPairSlots + b); };
   auto tempty = [&](int b) { return bar_base + 8u * (uint32_t)(2 * kPairSlots + 2 + b); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + map.bar_off + 512);
@@ -2190,7 +2193,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
 
   if (threadIdx.x == 0) {
     stamp(p.debug_ts, 0);
-    for (int s = 0; s < kPairSlots; ++s) {
+    for (int s = 0; s < n_slots; ++s) {
       mbar_init(full(s), rank == 0 ? 2u : 1u);  // leader: its own copies + the peer's relay
       mbar_init(empty(s), 1);
     }
@@ -2216,6 +2219,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
     if (worker) {
       const uint64_t pol_stream = l2_policy_evict_first();
       const uint64_t pol_keep = l2_policy_evict_last();
+      uint64_t pol_normal;
+      asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_normal));
+      const bool no_hint = (p.debug_flags & 64) != 0;  // (experiment) documents without the evict_first hint
       int s = 0;
       uint32_t ph = 0;
       for (int u = pair; u < n_super; u += n_pairs) {
@@ -2223,23 +2229,26 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
         const int tile = 2 * u + ((int)rank < nsub ? (int)rank : 0);
         const uint8_t* dsrc = p.corpus + (size_t)tile * tile_bytes;
         const uint8_t* qsrc = p.qimg + (size_t)rank * RS_BLOCK_BYTES;
-        for (int kc = 0; kc < p.kc; ++kc) {
+        for (int kc = 0; kc < p.kc; kc += cps) {
           mbar_wait_guarded<false>(empty(s), ph ^ 1u, p.err_flag);
           if (lane == 0) {
-            mbar_arrive_expect_tx(full(s), kPairSlotBytes);
-            bulk_g2s(slot_addr(s), qsrc + (size_t)kc * kPairSlotBytes, RS_BLOCK_BYTES, full(s), pol_keep);
-            bulk_g2s(slot_addr(s) + RS_BLOCK_BYTES, dsrc + (size_t)kc * RS_BLOCK_BYTES, RS_BLOCK_BYTES, full(s), pol_stream);
+            mbar_arrive_expect_tx(full(s), slot_bytes);
+            for (int c = 0; c < cps; ++c) {
+              bulk_g2s(slot_addr(s) + (uint32_t)c * kPairSlotBytes, qsrc + (size_t)(kc + c) * kPairSlotBytes, RS_BLOCK_BYTES, full(s), pol_keep);
+              bulk_g2s(slot_addr(s) + (uint32_t)c * kPairSlotBytes + RS_BLOCK_BYTES, dsrc + (size_t)(kc + c) * RS_BLOCK_BYTES, RS_BLOCK_BYTES,
+                       full(s), no_hint ? pol_normal : pol_stream);
+            }
           }
-          if (++s == kPairSlots) {
+          if (++s == n_slots) {
             s = 0;
             ph ^= 1u;
           }
         }
       }
       // drain: the last multicast commits must have landed in this CTA's empty barriers before the pair may part
-      for (int i = 0; i < kPairSlots; ++i) {
+      for (int i = 0; i < n_slots; ++i) {
         mbar_wait_guarded<false>(empty(s), ph ^ 1u, p.err_flag);
-        if (++s == kPairSlots) {
+        if (++s == n_slots) {
           s = 0;
           ph ^= 1u;
         }
@@ -2255,20 +2264,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
       for (int u = pair; u < n_super; u += n_pairs) {
         mbar_wait_guarded<true>(tempty(b), ((acc_ph >> b) & 1u) ^ 1u, p.err_flag);
         tc_fence_after();
-        for (int kc = 0; kc < p.kc; ++kc) {
+        for (int kc = 0; kc < p.kc; kc += cps) {
           mbar_wait_guarded<true>(full(s), ph, p.err_flag);
           tc_fence_after();
           if (lane == 0) {
             if (!skip_mma) {
-              const uint64_t a = umma_smem_desc(slot_addr(s)), bd = umma_smem_desc(slot_addr(s) + RS_BLOCK_BYTES);
+              for (int c = 0; c < cps; ++c) {
+                const uint32_t base = slot_addr(s) + (uint32_t)c * kPairSlotBytes;
+                const uint64_t a = umma_smem_desc(base), bd = umma_smem_desc(base + RS_BLOCK_BYTES);
 #pragma unroll
-              for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
-                umma_f16_pair(tmem_base + (uint32_t)b * 256u, a + 2u * ks, bd + 2u * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+                for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
+                  umma_f16_pair(tmem_base + (uint32_t)b * 256u, a + 2u * ks, bd + 2u * ks, idesc, (kc + c == 0 && ks == 0) ? 0u : 1u);
+              }
             }
             umma_commit_pair(empty(s));
           }
           __syncwarp();
-          if (++s == kPairSlots) {
+          if (++s == n_slots) {
             s = 0;
             ph ^= 1u;
           }
@@ -2284,13 +2296,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
       uint32_t ph = 0;
       const uint32_t full_leader = mapa_u32(full(0), 0);
       for (int u = pair; u < n_super; u += n_pairs) {
-        for (int kc = 0; kc < p.kc; ++kc) {
+        for (int kc = 0; kc < p.kc; kc += cps) {
           mbar_wait_guarded<false>(full(s), ph, p.err_flag);
           // (a .release.cluster arrive here costs ~1 us each and serialises the relay: 3.2 ms instead of 1.2 ms for
           // the bare stream of 4M rows; the bulk copies' completion on full(s) already orders the data)
           if (lane == 0) mbar_arrive_remote(full_leader + 8u * (uint32_t)s);
           __syncwarp();
-          if (++s == kPairSlots) {
+          if (++s == n_slots) {
             s = 0;
             ph ^= 1u;
           }
@@ -2331,7 +2343,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
     __syncwarp();
     const bool shared_bound = p.g_best != nullptr && worker;
     const int bound_rank = p.bound_rank;
-    const int flush_at = (p.debug_flags >> 8) ? (p.debug_flags >> 8) : kWideFlushAt;  // (experiments)
+    constexpr int flush_at = kWideFlushAt;  // (28 or 32 instead of 20 measured equal: 6.54 / 6.56 vs 6.61 ms)
     int supers_done = 0, next_refresh = 1;
     bool count_bound = true;  // false while the first supertile is filtered: the sample pass has counted its documents
     // merge query ql of this warp: its n buffered candidates -> its sorted list; returns the new k-th best in FILTER
@@ -3009,7 +3021,7 @@ int fused_pair_max_clusters(int k) {
 
 static cudaError_t launch_fused_pair(const SearchParams& p, int grid, cudaStream_t stream) {
   if (p.bpad != 256 || p.terms != 1 || p.planes != 1 || p.n_queries > 256 || p.k > kMaxListK || p.cbuf == nullptr ||
-      (grid & 1) || (p.n_work & 1) || p.n_lists * 2 != p.n_work || (p.g_best && p.bound_rank != 1 && p.bound_rank != 2))
+      (grid & 1) || (p.n_work & 1) || p.n_lists * 2 != p.n_work || (p.cps != 1 && p.cps != 2) || p.kc % p.cps != 0 || (p.g_best && p.bound_rank != 1 && p.bound_rank != 2))
     return cudaErrorInvalidValue;
   const int bytes = fused_pair_smem_bytes(p.k);
   cudaError_t e = cudaFuncSetAttribute(fused_search_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
