@@ -1025,6 +1025,7 @@ struct rs_group {
   rs_index* ix[rs::kMaxPeers] = {};
   rs_xchg* xg[rs::kMaxPeers] = {};
   cudaEvent_t fork = nullptr, join[rs::kMaxPeers] = {};
+  cudaEvent_t done = nullptr;  // recorded right behind the D2H of the result on shard 0's stream: what the host waits for
   struct GraphEntry {
     int B, k, metric, terms, uses;
     cudaGraphExec_t exec;
@@ -1061,7 +1062,9 @@ RS_API int rs_group_create(rs_index** shards, int32_t n, rs_group** out) {
     for (int h = 0; h < n && rc == RS_OK; ++h) rc = rs_xchg_attach(gr->xg[g], gr->xg[h]);
   if (rc == RS_OK) {
     cudaSetDevice(shards[0]->cfg.device);
-    if (cudaEventCreateWithFlags(&gr->fork, cudaEventDisableTiming) != cudaSuccess) rc = fail(RS_E_CUDA, "event creation failed");
+    if (cudaEventCreateWithFlags(&gr->fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&gr->done, cudaEventDisableTiming) != cudaSuccess)
+      rc = fail(RS_E_CUDA, "event creation failed");
   }
   if (rc != RS_OK) {
     rs_group_destroy(gr);
@@ -1086,6 +1089,7 @@ RS_API int rs_group_destroy(rs_group* gr) {
     rs_xchg_destroy(gr->xg[g]);
   }
   if (gr->fork) cudaEventDestroy(gr->fork);
+  if (gr->done) cudaEventDestroy(gr->done);
   delete gr;
   return RS_OK;
 }
@@ -1120,11 +1124,18 @@ RS_API int rs_group_search(rs_group* gr, const float* q_host, int32_t B, int32_t
       int rc = search_device_locked(ix, ix->q_dev, B, k, metric, query_terms, ix->out_idx_dev, score_dev, ix->stream,
                                     gr->n > 1 ? gr->xg[g] : nullptr);
       if (rc != RS_OK) return rc;
-      if (g > 0) RS_CUDA(cudaEventRecord(gr->join[g], ix->stream));
+      if (g > 0) {
+        RS_CUDA(cudaEventRecord(gr->join[g], ix->stream));
+      } else {
+        // The result leaves shard 0 as soon as ITS kernel is done (it has every peer's candidates by then, so every
+        // peer has long read its queries): the host waits for `done`, not for the other GPUs' kernels to retire.
+        RS_CUDA(cudaMemcpyAsync(pin_idx, ix0->out_idx_dev, n_out * (sizeof(long long) + sizeof(float)), cudaMemcpyDeviceToHost, s0));
+        if (ix0->capturing) RS_CUDA(cudaEventRecordWithFlags(gr->done, s0, cudaEventRecordExternal));
+        else RS_CUDA(cudaEventRecord(gr->done, s0));
+      }
     }
     RS_CUDA(cudaSetDevice(ix0->cfg.device));
-    for (int g = 1; g < gr->n; ++g) RS_CUDA(cudaStreamWaitEvent(s0, gr->join[g], 0));
-    RS_CUDA(cudaMemcpyAsync(pin_idx, ix0->out_idx_dev, n_out * (sizeof(long long) + sizeof(float)), cudaMemcpyDeviceToHost, s0));
+    for (int g = 1; g < gr->n; ++g) RS_CUDA(cudaStreamWaitEvent(s0, gr->join[g], 0));  // the next search starts after all of them
     return RS_OK;
   };
   for (int g = 0; g < gr->n; ++g) {
@@ -1166,10 +1177,10 @@ RS_API int rs_group_search(rs_group* gr, const float* q_host, int32_t B, int32_t
     if (rc != RS_OK) return rc;
     if (ge) ++ge->uses;
   }
-  RS_CUDA(cudaStreamSynchronize(s0));
-  for (int g = 0; g < gr->n; ++g) {
-    RS_CUDA(cudaSetDevice(gr->ix[g]->cfg.device));
-    int rc = take_device_error(gr->ix[g], gr->ix[g]->stream);
+  RS_CUDA(cudaEventSynchronize(gr->done));
+  {  // shard 0 waited for every peer inside its kernel: a peer that never showed up raised shard 0's error word.  The
+     // peers' own error words are read at the start of the next call (their kernels may still be retiring).
+    int rc = take_device_error(ix0, s0);
     if (rc != RS_OK) return rc;
   }
   memcpy(out_idx, pin_idx, n_out * sizeof(long long));
