@@ -415,14 +415,27 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   const int nacc = (terms == 2 || ix->planes == 2) ? 2 : 1;
   // (B <= 16: the whole image is 64 KiB anyway, and the one-CTA kernel keeps its in-kernel query prep)
   bool dmpair = docm && nacc == 2 && pl.bpad > 16 && o.dmpair != 0 && ix->dm_pair_clusters > 0 && ix->n_tiles >= 8 * ix->sm_count;
-  if (dmpair) {
-    pl.bpad = 32;
-    pl.cps = o.cps > 0 ? o.cps : (ix->planes == 2 ? 2 : 4);  // 64 KiB ring stages
-    if (ix->kc % pl.cps != 0) pl.cps = 1;
-    const int fixed = rs::fused_dmpair_smem_bytes(ix->kc, terms, ix->planes, 0, pl.cps);
-    const int stage_bytes = ix->planes * pl.cps * RS_BLOCK_BYTES;
-    pl.stages = std::min(8, (kMaxSmem - fixed) / stage_bytes);
-    if (pl.stages < 2) dmpair = false;
+  // One accumulator (16-bit storage, one query term), 32 < B <= 64: the same kernel with N = 64 - each CTA holds 32
+  // queries' image (64 KiB at D = 1024), where the one-CTA kernels would need 128 KiB resident or stream Q.
+  const bool dmpair64 = !pl.wide && !docm && nacc == 1 && B > 32 && B <= 64 && k <= rs::fused_reg_k() && o.docm != 0 &&
+                        o.dmpair != 0 && ix->dm_pair_clusters > 0 && ix->n_tiles >= 8 * ix->sm_count;
+  if (dmpair || dmpair64) {
+    const int bpad = dmpair64 ? 64 : 32;
+    int cps = o.cps > 0 ? o.cps : (ix->planes == 2 ? 2 : 4);  // 64 KiB ring stages
+    if (ix->kc % cps != 0) cps = 1;
+    const int fixed = rs::fused_dmpair_smem_bytes(ix->kc, terms, ix->planes, 0, cps, bpad);
+    const int stages = std::min(8, (kMaxSmem - fixed) / (ix->planes * cps * RS_BLOCK_BYTES));
+    dmpair = stages >= 2;  // (larger dimensions: the plan made above stays)
+    if (dmpair) {
+      pl.bpad = bpad;
+      pl.q_resident = 1;
+      pl.sub = 1;
+      pl.nbuf = 8;
+      pl.passes = 1;
+      pl.per_pass = B;
+      pl.cps = cps;
+      pl.stages = stages;
+    }
   }
   // CTAs that own tiles.  Pair kernel: both CTAs of every pair that owns a supertile (two tiles)
   const int n_work = pl.wide == 2 ? 2 * std::min(ix->pair_clusters, (ix->n_tiles + 1) / 2)
@@ -433,7 +446,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   // candidate merge (+ exchange) in its tail.  RS_INLINE_PREP=0 / RS_FUSED_TAIL=0 fall back to the
   // separate query_prep_kernel / merge kernels.
   const bool inline_prep = !pl.wide && !dmpair && pl.q_resident == 1 && ix->cfg.dim <= 1024 && pl.bpad <= 32 && o.inline_prep != 0;
-  const int tail_cap = dmpair ? rs::fused_dmpair_tail_capacity(ix->kc, terms, ix->planes, pl.stages, pl.cps)
+  const int tail_cap = dmpair ? rs::fused_dmpair_tail_capacity(ix->kc, terms, ix->planes, pl.stages, pl.cps, pl.bpad)
                        : pl.wide == 2 ? rs::fused_pair_tail_capacity(k) : pl.wide ? rs::fused_wide_tail_capacity(k)
                                : rs::fused_tail_smem_capacity(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, pl.qstages);
   const bool fused_tail = o.fused_tail != 0 && rs::fused_tail_smem_bytes(n_lists, k, xg ? xg->world : 1) <= (size_t)tail_cap;
@@ -450,7 +463,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   const bool shared_bound = (k > rs::fused_reg_k() || pl.wide) && n_lists * bound_rank >= k && o.shared_bound != 0;
   ix->stats.grid = grid;
   ix->stats.stages = pl.stages;
-  ix->stats.smem_bytes = dmpair ? rs::fused_dmpair_smem_bytes(ix->kc, terms, ix->planes, pl.stages, pl.cps)
+  ix->stats.smem_bytes = dmpair ? rs::fused_dmpair_smem_bytes(ix->kc, terms, ix->planes, pl.stages, pl.cps, pl.bpad)
                          : pl.wide == 2 ? rs::fused_pair_smem_bytes(k) : pl.wide ? rs::fused_wide_smem_bytes(k)
                                  : rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, pl.qstages, pl.bufc, pl.lg, docm);
   ix->stats.q_resident = pl.q_resident;
@@ -458,7 +471,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   ix->stats.nbuf = pl.nbuf;
   ix->stats.mma_m = dmpair ? 256 : pl.mma_m;
   ix->stats.overlapped = pdl ? 1 : 0;
-  ix->stats.doc_major = docm ? 1 : 0;
+  ix->stats.doc_major = (docm || dmpair) ? 1 : 0;
   ix->stats.passes = pl.passes;
   ix->stats.query_terms = terms;
   ix->stats.launches = 0;
@@ -525,7 +538,7 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     p.cps = pl.cps;
     p.bufc = pl.bufc;
     p.lists_global = pl.lg;
-    p.docm = docm ? 1 : 0;
+    p.docm = (docm || dmpair) ? 1 : 0;
     p.dmpair = dmpair ? 1 : 0;
     p.wide = pl.wide;
     p.cbuf = reinterpret_cast<uint2*>(ix->cbuf);

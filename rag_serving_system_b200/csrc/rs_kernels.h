@@ -75,7 +75,8 @@ struct SearchParams {
   ExchangeArgs x;                    // tail_mode == 2
   int wide;                          // wide-batch kernels (128 < B <= 256 in one pass): 1 = fused_search_wide_kernel (one CTA per
                                      // SM), 2 = fused_search_pair_kernel (CTA pairs, tcgen05 cta_group::2)
-  int dmpair;                        // doc-major CTA-pair kernel (fused_search_dmpair_kernel): B <= 32, k <= 16, two accumulators
+  int dmpair;                        // doc-major CTA-pair kernel (fused_search_dmpair_kernel), k <= 16: two accumulators and B <= 32,
+                                     // or one accumulator and 32 < B <= 64
   int n_lists;                       // candidate lists per query the tail merges: n_work, or the worker PAIRS of the pair kernel
   int bound_rank;                    // pair kernel, shared bound: a CTA publishes its 1st or 2nd best score per query
   uint2* cbuf;                       // wide: [n_queries][n_work][32] candidate buffers {score bits, local row id}
@@ -96,8 +97,8 @@ int fused_wide_slots();
 int fused_pair_smem_bytes(int k);
 int fused_pair_tail_capacity(int k);
 int fused_pair_max_clusters(int k);
-int fused_dmpair_smem_bytes(int kc, int terms, int planes, int stages, int cps);
-int fused_dmpair_tail_capacity(int kc, int terms, int planes, int stages, int cps);
+int fused_dmpair_smem_bytes(int kc, int terms, int planes, int stages, int cps, int bpad);
+int fused_dmpair_tail_capacity(int kc, int terms, int planes, int stages, int cps, int bpad);
 int fused_dmpair_max_clusters(int smem_bytes);  // CTA pairs of the pair kernel the current device can keep resident at once (0: none)
 size_t fused_tail_smem_bytes(int n_lists, int k, int world);
 int fused_tail_smem_capacity(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages);

@@ -881,32 +881,41 @@ struct DmBars {
   int pair, n_pairs, rank;
   uint32_t tempty_leader0;  // shared::cluster address of the leader's tempty[0]
 };
-template <int KS, int NACC, bool PAIR = false>
+template <int KS, int NACC, bool PAIR = false, int NH = 1>
 __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars& b, uint32_t tmem_base, int w, int lane,
                                             float* dump /* this warp's [32][32] */, float* s_qnorm, float* s_qscale,
-                                            bool inline_prep, bool worker, float* out_s /* [4][32][k] */, int* out_i) {
+                                            bool inline_prep, bool worker, float* out_s /* [4][32 NH][k] */, int* out_i) {
+  // NH = halves of 32 queries (2: the pair kernel with N = 64).  A thread holds its document's scores of ONE half at a
+  // time; lane j keeps the running top-k of queries j and 32 + j (its warp's document slice) in registers.
   constexpr int kSched = KS;
   const int k = p.k, nq = p.n_queries;
   const uint32_t lane_base = tmem_base + ((uint32_t)(w * 32) << 16);
-  float thr[32];
+  float thr[NH][32];
+  float ls[NH][kRegK];
+  int li[NH][kRegK];
+  float mythr[NH];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) thr[j] = j < nq ? -CUDART_INF_F : CUDART_INF_F;
-  float ls[kRegK];
-  int li[kRegK];
+  for (int h = 0; h < NH; ++h) {
 #pragma unroll
-  for (int j = 0; j < kRegK; ++j) {
-    ls[j] = j < k ? -CUDART_INF_F : CUDART_INF_F;  // ascending, slot 0 = current k-th best
-    li[j] = -1;
+    for (int j = 0; j < 32; ++j) thr[h][j] = 32 * h + j < nq ? -CUDART_INF_F : CUDART_INF_F;
+#pragma unroll
+    for (int j = 0; j < kRegK; ++j) {
+      ls[h][j] = j < k ? -CUDART_INF_F : CUDART_INF_F;  // ascending, slot 0 = current k-th best
+      li[h][j] = -1;
+    }
+    mythr[h] = 32 * h + lane < nq ? -CUDART_INF_F : CUDART_INF_F;
   }
-  float mythr = lane < nq ? -CUDART_INF_F : CUDART_INF_F;
   const bool cosine = p.metric == RS_METRIC_COSINE;
   if (inline_prep && worker) {
     mbar_wait(b.qfull, 0);
   } else if (worker) {
     // separate prep kernel: bring the per-query constants into shared memory (every warp writes the same
     // values, so no cross-warp synchronisation is needed before this warp reads them back)
-    s_qnorm[lane] = lane < nq ? p.qnorm[lane] : 0.f;
-    s_qscale[lane] = lane < nq ? p.qscale[lane] : 1.f;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      s_qnorm[32 * h + lane] = 32 * h + lane < nq ? p.qnorm[32 * h + lane] : 0.f;
+      s_qscale[32 * h + lane] = 32 * h + lane < nq ? p.qscale[32 * h + lane] : 1.f;
+    }
     __syncwarp();
   }
   int acc = 0, sslot = 0;
@@ -933,92 +942,102 @@ __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars&
     const float nd = (cosine && t < p.n_tiles) ? __ldg(p.dnorm + doc0 + lane) : 1.f;  // dnorm is padded to whole tiles
     mbar_wait(b.tfull0 + 8u * acc, acc_ph);
     tc_fence_after();
-    float v[32];
-    {
-      uint32_t r[32];
-      tmem_ld_x32(lane_base + (uint32_t)(acc * NACC) * 32u, r);
-      if (NACC == 2) {  // hi + lo accumulators (two query terms and/or an fp32 corpus stored as two planes)
-        uint32_t r1[32];
-        tmem_ld_x32(lane_base + (uint32_t)(acc * NACC) * 32u + 32u, r1);
-        tmem_wait_ld();
+    const uint32_t abase = lane_base + (uint32_t)(acc * NACC * NH) * 32u;  // buffer: [accumulator][half][32 columns]
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r1[j]), p.lo_coef, __uint_as_float(r[j]));
-      } else {
-        tmem_wait_ld();
+    for (int h = 0; h < NH; ++h) {
+      float v[32];
+      {
+        uint32_t r[32];
+        tmem_ld_x32(abase + (uint32_t)h * 32u, r);
+        if (NACC == 2) {  // hi + lo accumulators (two query terms and/or an fp32 corpus stored as two planes)
+          uint32_t r1[32];
+          tmem_ld_x32(abase + (uint32_t)(NH + h) * 32u, r1);
+          tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      }
-    }
-    // the scores are in registers: hand the accumulator back before looking at them
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-      if constexpr (PAIR) mbar_arrive_remote(b.tempty_leader0 + 8u * acc);
-      else mbar_arrive(b.tempty0 + 8u * acc);
-    }
-    if (++acc == p.nbuf) {
-      acc = 0;
-      acc_ph ^= 1u;
-    }
-    if (p.debug_flags & 2) continue;
-    if (cosine) {
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r1[j]), p.lo_coef, __uint_as_float(r[j]));
+        } else {
+          tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float denom = __fadd_rn(__fmul_rn(s_qnorm[j], nd), 1e-8f);      // retriever.py:605,607
-        v[j] = fminf(fmaxf(__fdiv_rn(v[j] * s_qscale[j], denom), -1.0f), 1.0f);  // :607,:609
-      }
-    }
-    if (doc0 + 32 > p.n_rows && doc0 + lane >= p.n_rows) {  // ragged last tile: padded documents never pass
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = -CUDART_INF_F;
-    }
-    uint32_t pm = 0u;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) pm |= (v[j] > thr[j]) ? (1u << j) : 0u;
-    if (__any_sync(0xffffffffu, pm != 0u)) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) dump[j * 32 + lane] = v[j];  // [query][doc]: conflict-free
-      uint32_t mine = 0u;  // documents (lanes) of this warp that pass for query `lane`
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const uint32_t m = __ballot_sync(0xffffffffu, (pm >> j) & 1u);
-        if (lane == j) mine = m;
-      }
-      __syncwarp();
-      while (mine) {  // ascending document index: strict > keeps the lower index on ties
-        const int d = __ffs(mine) - 1;
-        mine &= mine - 1;
-        const float x = dump[lane * 32 + d];
-        if (x > mythr) {
-          const int idx = doc0 + d;
-          bool prev = true;
-#pragma unroll
-          for (int jj = 0; jj < kRegK; ++jj) {
-            const bool lt = (jj + 1 < kRegK) && (ls[jj + 1 < kRegK ? jj + 1 : jj] < x);
-            const float ns = lt ? ls[jj + 1 < kRegK ? jj + 1 : jj] : (prev ? x : ls[jj]);
-            const int ni = lt ? li[jj + 1 < kRegK ? jj + 1 : jj] : (prev ? idx : li[jj]);
-            ls[jj] = ns;
-            li[jj] = ni;
-            prev = lt;
-          }
-          mythr = ls[0];
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         }
       }
-      __syncwarp();
+      if (h == NH - 1) {
+        // the (last) scores are in registers: hand the accumulator back before looking at them
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_remote(b.tempty_leader0 + 8u * acc);
+          else mbar_arrive(b.tempty0 + 8u * acc);
+        }
+        if (++acc == p.nbuf) {
+          acc = 0;
+          acc_ph ^= 1u;
+        }
+      }
+      if (p.debug_flags & 2) continue;
+      if (cosine) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) thr[j] = __shfl_sync(0xffffffffu, mythr, j);
+        for (int j = 0; j < 32; ++j) {
+          const float denom = __fadd_rn(__fmul_rn(s_qnorm[32 * h + j], nd), 1e-8f);      // retriever.py:605,607
+          v[j] = fminf(fmaxf(__fdiv_rn(v[j] * s_qscale[32 * h + j], denom), -1.0f), 1.0f);  // :607,:609
+        }
+      }
+      if (doc0 + 32 > p.n_rows && doc0 + lane >= p.n_rows) {  // ragged last tile: padded documents never pass
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = -CUDART_INF_F;
+      }
+      uint32_t pm = 0u;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pm |= (v[j] > thr[h][j]) ? (1u << j) : 0u;
+      if (__any_sync(0xffffffffu, pm != 0u)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dump[j * 32 + lane] = v[j];  // [query][doc]: conflict-free
+        uint32_t mine = 0u;  // documents (lanes) of this warp that pass for query 32 h + lane
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t m = __ballot_sync(0xffffffffu, (pm >> j) & 1u);
+          if (lane == j) mine = m;
+        }
+        __syncwarp();
+        while (mine) {  // ascending document index: strict > keeps the lower index on ties
+          const int d = __ffs(mine) - 1;
+          mine &= mine - 1;
+          const float x = dump[lane * 32 + d];
+          if (x > mythr[h]) {
+            const int idx = doc0 + d;
+            bool prev = true;
+#pragma unroll
+            for (int jj = 0; jj < kRegK; ++jj) {
+              const bool lt = (jj + 1 < kRegK) && (ls[h][jj + 1 < kRegK ? jj + 1 : jj] < x);
+              const float ns = lt ? ls[h][jj + 1 < kRegK ? jj + 1 : jj] : (prev ? x : ls[h][jj]);
+              const int ni = lt ? li[h][jj + 1 < kRegK ? jj + 1 : jj] : (prev ? idx : li[h][jj]);
+              ls[h][jj] = ns;
+              li[h][jj] = ni;
+              prev = lt;
+            }
+            mythr[h] = ls[h][0];
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) thr[h][j] = __shfl_sync(0xffffffffu, mythr[h], j);
+      }
     }
   }
-  // this warp's list of query `lane`, best first, final units (exact power-of-two scale)
-  if (lane < nq && worker) {
-    const float qs = cosine ? 1.0f : s_qscale[lane];  // cosine lists are already in final units
-    float* os = out_s + (size_t)(w * 32 + lane) * k;
-    int* oi = out_i + (size_t)(w * 32 + lane) * k;
+  // this warp's lists of queries 32 h + lane, best first, final units (exact power-of-two scale)
 #pragma unroll
-    for (int j = 0; j < kRegK; ++j) {
-      if (j < k) {
-        os[k - 1 - j] = li[j] < 0 ? -CUDART_INF_F : ls[j] * qs;
-        oi[k - 1 - j] = li[j];
+  for (int h = 0; h < NH; ++h) {
+    const int q = 32 * h + lane;
+    if (q < nq && worker) {
+      const float qs = cosine ? 1.0f : s_qscale[q];  // cosine lists are already in final units
+      float* os = out_s + (size_t)(w * (32 * NH) + q) * k;
+      int* oi = out_i + (size_t)(w * (32 * NH) + q) * k;
+#pragma unroll
+      for (int j = 0; j < kRegK; ++j) {
+        if (j < k) {
+          os[k - 1 - j] = li[h][j] < 0 ? -CUDART_INF_F : ls[h][j] * qs;
+          oi[k - 1 - j] = li[h][j];
+        }
       }
     }
   }
@@ -1028,10 +1047,11 @@ __device__ __forceinline__ void dm_epilogue(const SearchParams& p, const DmBars&
 // ids) -> the CTA's one list in cand_* (list index = blockIdx.x).  Whole CTA; ends with a barrier.
 __device__ __forceinline__ void dm_publish_cta_lists(const SearchParams& p, const uint8_t* smem, const bool worker) {
   // the four warps' lists of query q (best first, shared memory) -> the CTA's one list in cand_*
+  const int NQ = p.bpad > 32 ? 64 : 32;  // query rows per warp block (dm_epilogue's NH * 32)
   if (worker && (int)threadIdx.x < p.n_queries) {
     const int q = threadIdx.x, k = p.k;
     const float* ss = reinterpret_cast<const float*>(smem);
-    const int* si = reinterpret_cast<const int*>(smem + 4 * 32 * kRegK * sizeof(float));
+    const int* si = reinterpret_cast<const int*>(smem + 4 * NQ * kRegK * sizeof(float));
     float* cs = p.cand_score + ((size_t)q * p.n_work + blockIdx.x) * k;
     int* ci = p.cand_idx + ((size_t)q * p.n_work + blockIdx.x) * k;
     int h[4] = {0, 0, 0, 0};
@@ -1041,8 +1061,8 @@ __device__ __forceinline__ void dm_publish_cta_lists(const SearchParams& p, cons
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         if (h[w] < k) {
-          const int id = si[(size_t)(w * 32 + q) * k + h[w]];
-          const float sc = ss[(size_t)(w * 32 + q) * k + h[w]];
+          const int id = si[(size_t)(w * NQ + q) * k + h[w]];
+          const float sc = ss[(size_t)(w * NQ + q) * k + h[w]];
           if (id >= 0 && (bw < 0 || sc > bs || (sc == bs && id < bi))) {
             bw = w;
             bs = sc;
@@ -2633,9 +2653,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_pair_kernel(const __
 struct DmPairSmem {
   uint32_t q_bytes, stage_off, stage_bytes, bar_off, dump_off, total;
 };
-__host__ __device__ inline DmPairSmem make_dmpair_smem(int kc, int terms, int planes, int stages, int cps) {
+__host__ __device__ inline DmPairSmem make_dmpair_smem(int kc, int terms, int planes, int stages, int cps, int bpad = 32) {
   DmPairSmem m;
-  m.q_bytes = (uint32_t)(terms * kc) * 2048u;  // per (term, k-chunk): 16 query rows x 128 B
+  m.q_bytes = (uint32_t)(terms * kc) * (uint32_t)(bpad / 2) * RS_KCHUNK_BYTES;  // per (term, k-chunk): this CTA's bpad/2 query rows x 128 B
   m.stage_off = m.q_bytes;
   m.stage_bytes = (uint32_t)(planes * cps) * RS_BLOCK_BYTES;
   m.bar_off = m.stage_off + (uint32_t)stages * m.stage_bytes;
@@ -2644,7 +2664,7 @@ __host__ __device__ inline DmPairSmem make_dmpair_smem(int kc, int terms, int pl
   return m;
 }
 
-template <int NACC>
+template <int NACC, int NH>
 __global__ void __launch_bounds__(kThreads, 1) fused_search_dmpair_kernel(const __grid_constant__ SearchParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -2654,7 +2674,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_dmpair_kernel(const 
   const int pair = (int)blockIdx.x >> 1;
   const int n_pairs = (int)gridDim.x >> 1;
   const int cps = p.cps, NB = p.nbuf;
-  const DmPairSmem map = make_dmpair_smem(p.kc, p.terms, p.planes, p.stages, cps);
+  const DmPairSmem map = make_dmpair_smem(p.kc, p.terms, p.planes, p.stages, cps, 32 * NH);
+  constexpr uint32_t qblk = (uint32_t)(16 * NH) * RS_KCHUNK_BYTES;  // this CTA's rows of one (term, k-chunk) block of the Q image
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t q_smem = smem_base, stage_smem = smem_base + map.stage_off, bar_base = smem_base + map.bar_off;
   auto full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
@@ -2668,7 +2689,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_dmpair_kernel(const 
   const int n_super = (p.n_tiles + 1) / 2;
   const bool worker = pair < n_super && (int)blockIdx.x < p.n_work;
   const size_t tile_bytes = (size_t)p.planes * p.kc * RS_BLOCK_BYTES;
-  const uint32_t tmem_cols = (uint32_t)(NB * NACC) * 32u;
+  const uint32_t tmem_cols = (uint32_t)(NB * NACC * NH) * 32u;
 
   if (threadIdx.x == 0) {
     stamp(p.debug_ts, 0);
@@ -2698,10 +2719,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_dmpair_kernel(const 
     if (worker) {
       const uint64_t pol_stream = l2_policy_evict_first();
       const uint64_t pol_keep = l2_policy_evict_last();
-      if (lane == 0) {  // this CTA's 16 rows of every (term, k-chunk) block of the Q image
+      if (lane == 0) {  // this CTA's 16 (32) rows of every (term, k-chunk) block of the Q image
         mbar_arrive_expect_tx(qfull, map.q_bytes);
         for (int blk = 0; blk < p.terms * p.kc; ++blk)
-          bulk_g2s(q_smem + (uint32_t)blk * 2048u, p.qimg + (size_t)blk * 4096u + (size_t)rank * 2048u, 2048u, qfull, pol_keep);
+          bulk_g2s(q_smem + (uint32_t)blk * qblk, p.qimg + (size_t)blk * 2u * qblk + (size_t)rank * qblk, qblk, qfull, pol_keep);
       }
       int s = 0;
       uint32_t ph = 0;
@@ -2734,7 +2755,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_dmpair_kernel(const 
   } else if (warp == kMmaWarp) {
     if (worker && rank == 0) {
       // ===================== MMA issuer (leader): M = 256 (two document tiles) x N = 32 (queries) x K = 16 =====================
-      const uint32_t idesc = umma_idesc_f16(p.dtype == RS_DTYPE_BF16, 256, 32);
+      const uint32_t idesc = umma_idesc_f16(p.dtype == RS_DTYPE_BF16, 256, 32 * NH);
       const bool skip_mma = (p.debug_flags & 1) != 0;
       mbar_wait_guarded<true>(qfull, 0, p.err_flag);
       tc_fence_after();
@@ -2744,7 +2765,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_dmpair_kernel(const 
       for (int u = pair; u < n_super; u += n_pairs) {
         mbar_wait_guarded<true>(tempty(acc), acc_ph ^ 1u, p.err_flag);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * NACC) * 32u, d1 = d0 + 32u;
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * NACC * NH) * 32u, d1 = d0 + (uint32_t)NH * 32u;
         for (int kc = 0; kc < p.kc; kc += cps) {
           mbar_wait_guarded<true>(full(s), ph, p.err_flag);
           tc_fence_after();
@@ -2754,12 +2775,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_dmpair_kernel(const 
               for (int c = 0; c < cps; ++c) {
                 const bool fresh = (kc + c) == 0;
                 const uint64_t a_hi = umma_smem_desc(st + (uint32_t)c * RS_BLOCK_BYTES);
-                const uint64_t b_hi = umma_smem_desc(q_smem + (uint32_t)(kc + c) * 2048u);
+                const uint64_t b_hi = umma_smem_desc(q_smem + (uint32_t)(kc + c) * qblk);
 #pragma unroll
                 for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
                   umma_f16_pair(d0, a_hi + 2u * ks, b_hi + 2u * ks, idesc, (fresh && ks == 0) ? 0u : 1u);
                 if (NACC == 2) {
-                  const uint64_t b_lo = umma_smem_desc(q_smem + (uint32_t)(p.kc + kc + c) * 2048u);
+                  const uint64_t b_lo = umma_smem_desc(q_smem + (uint32_t)(p.kc + kc + c) * qblk);
 #pragma unroll
                   for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
                     umma_f16_pair(d1, a_hi + 2u * ks, b_lo + 2u * ks, idesc, (fresh && ks == 0) ? 0u : 1u);
@@ -2810,9 +2831,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_dmpair_kernel(const 
   } else {
     const int quarter = warp & 3;
     const DmBars bars{tfull(0), tempty(0), 0u, 0u, qfull, nullptr, pair, n_pairs, (int)rank, mapa_u32(tempty(0), 0)};
-    dm_epilogue<8, NACC, true>(p, bars, tmem_base, quarter, lane, reinterpret_cast<float*>(smem + map.dump_off) + quarter * 1024,
+    dm_epilogue<8, NACC, true, NH>(p, bars, tmem_base, quarter, lane, reinterpret_cast<float*>(smem + map.dump_off) + quarter * 1024,
                                s_qnorm, s_qscale, false, worker, reinterpret_cast<float*>(smem),
-                               reinterpret_cast<int*>(smem + 4 * 32 * kRegK * sizeof(float)));
+                               reinterpret_cast<int*>(smem + 4 * 32 * NH * kRegK * sizeof(float)));
   }
 
   if (p.tail_mode != 0) __threadfence();
@@ -3032,14 +3053,14 @@ static cudaError_t launch_fused_pair(const SearchParams& p, int grid, cudaStream
   return cudaLaunchKernelEx(&cfg, fused_search_pair_kernel, p);
 }
 
-int fused_dmpair_smem_bytes(int kc, int terms, int planes, int stages, int cps) {
-  return (int)make_dmpair_smem(kc, terms, planes, stages, cps).total + 1024;
+int fused_dmpair_smem_bytes(int kc, int terms, int planes, int stages, int cps, int bpad) {
+  return (int)make_dmpair_smem(kc, terms, planes, stages, cps, bpad).total + 1024;
 }
-int fused_dmpair_tail_capacity(int kc, int terms, int planes, int stages, int cps) {
-  return (int)make_dmpair_smem(kc, terms, planes, stages, cps).bar_off;
+int fused_dmpair_tail_capacity(int kc, int terms, int planes, int stages, int cps, int bpad) {
+  return (int)make_dmpair_smem(kc, terms, planes, stages, cps, bpad).bar_off;
 }
 int fused_dmpair_max_clusters(int smem_bytes) {
-  if (cudaFuncSetAttribute(fused_search_dmpair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+  if (cudaFuncSetAttribute(fused_search_dmpair_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -3050,24 +3071,30 @@ int fused_dmpair_max_clusters(int smem_bytes) {
   cudaLaunchAttribute attr[1];
   pair_launch_config(&cfg, attr, sms & ~1, smem_bytes, nullptr);
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, fused_search_dmpair_kernel<2>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, fused_search_dmpair_kernel<2, 1>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   return n;
 }
-static cudaError_t launch_fused_dmpair(const SearchParams& p, int grid, cudaStream_t stream) {
-  const int nacc = (p.terms == 2 || p.planes == 2) ? 2 : 1;
-  if (p.bpad != 32 || p.n_queries > 32 || p.k > kRegK || (grid & 1) || (p.n_work & 1) || p.nbuf * nacc * 32 > 512 ||
-      p.nbuf < 1 || p.nbuf > 8 || p.stages < 2 || p.stages > 8 || p.kc % p.cps != 0 || nacc != 2 || p.inline_prep)
-    return cudaErrorInvalidValue;
-  const int bytes = fused_dmpair_smem_bytes(p.kc, p.terms, p.planes, p.stages, p.cps);
-  cudaError_t e = cudaFuncSetAttribute(fused_search_dmpair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+template <int NACC, int NH>
+static cudaError_t launch_fused_dmpair_t(const SearchParams& p, int grid, cudaStream_t stream) {
+  const int bytes = fused_dmpair_smem_bytes(p.kc, p.terms, p.planes, p.stages, p.cps, p.bpad);
+  cudaError_t e = cudaFuncSetAttribute(fused_search_dmpair_kernel<NACC, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   pair_launch_config(&cfg, attr, grid, bytes, stream);
-  return cudaLaunchKernelEx(&cfg, fused_search_dmpair_kernel<2>, p);
+  return cudaLaunchKernelEx(&cfg, fused_search_dmpair_kernel<NACC, NH>, p);
+}
+static cudaError_t launch_fused_dmpair(const SearchParams& p, int grid, cudaStream_t stream) {
+  const int nacc = (p.terms == 2 || p.planes == 2) ? 2 : 1;
+  const int nh = p.bpad / 32;
+  if ((p.bpad != 32 && p.bpad != 64) || p.n_queries > p.bpad || p.k > kRegK || (grid & 1) || (p.n_work & 1) ||
+      p.nbuf * nacc * nh * 32 > 512 || p.nbuf < 1 || p.nbuf > 8 || p.stages < 2 || p.stages > 8 || p.kc % p.cps != 0 || p.inline_prep ||
+      !((nacc == 2 && nh == 1) || (nacc == 1 && nh == 2)))
+    return cudaErrorInvalidValue;
+  return nacc == 2 ? launch_fused_dmpair_t<2, 1>(p, grid, stream) : launch_fused_dmpair_t<1, 2>(p, grid, stream);
 }
 
 cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t stream) {

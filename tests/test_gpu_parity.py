@@ -670,18 +670,22 @@ def test_wide_batch_kernel_sweep(dtype, metric, B, k, N):
 
 @pytest.mark.parametrize("dtype,terms,metric,B,k,N", [
     ("fp32", 2, "cosine", 32, 10, 128 * 1184 + 77), ("fp32", 2, "dot", 17, 16, 128 * 1185), ("bf16", 2, "dot", 32, 1, 128 * 1186 + 1),
-    ("fp16", 2, "cosine", 19, 5, 128 * 1300 + 127)])
+    ("fp16", 2, "cosine", 19, 5, 128 * 1300 + 127),
+    ("bf16", 1, "dot", 64, 10, 128 * 1185 + 3), ("fp16", 1, "cosine", 33, 16, 128 * 1184), ("bf16", 1, "cosine", 50, 1, 128 * 1201 + 64)])
 def test_doc_major_pair_kernel(dtype, terms, metric, B, k, N):
-    """fused_search_dmpair_kernel (two accumulators, B <= 32, k <= 16, >= 8 tiles per SM: each CTA of a pair keeps half
-    of the Q image, M = 256 MMAs over the two CTAs' document tiles): odd and even tile counts, ragged last tile, both
-    metrics, fp32 storage and two-term 16-bit queries - against the oracle, and equal to the one-CTA kernel."""
+    """fused_search_dmpair_kernel (k <= 16, >= 8 tiles per SM; two accumulators and B <= 32, or one accumulator and
+    32 < B <= 64: each CTA of a pair keeps half of the Q image, M = 256 MMAs over the two CTAs' document tiles): odd
+    and even tile counts, ragged last tile, both metrics, fp32 storage, two-term and one-term 16-bit queries - against
+    the oracle, and equal to the one-CTA kernels."""
     sx = 4 if dtype == "fp32" else 0
     E = o.synth_rows(29, np.arange(N))
     rng = np.random.default_rng(7)
     src = rng.integers(0, N, B)
     src[:2] = [N - 1, 0]
     Q = (E[src] + 0.03 * rng.standard_normal((B, 1024))).astype(np.float32)
-    ix = make_index(E, dtype, sx, max_batch=32, max_k=16)
+    if terms == 1:
+        Q = o.round_to_dtype(Q, DT[dtype])
+    ix = make_index(E, dtype, sx, max_batch=64, max_k=16)
     try:
         idx, sc = ix.search(Q, k, metric, terms)
         st = ix.stats()
@@ -696,6 +700,8 @@ def test_doc_major_pair_kernel(dtype, terms, metric, B, k, N):
         i3, s3 = ix.search(Q, k, metric, terms)             # which the three MMA chains reach the low-order accumulator
         assert ix.stats()["mma_m"] != 256
         o.check_topk(i3, s3, S, k, rtol=RTOL[dtype], atol=1e-6)
+        if terms == 1:                                      # one accumulator: the same sums in the same order
+            assert np.array_equal(idx, i3) and np.array_equal(sc, s3)
         assert np.allclose(sc, s3, rtol=2e-6, atol=1e-7) and (idx == i3).mean() > 0.99
     finally:
         ix.close()
