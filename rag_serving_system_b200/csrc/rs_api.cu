@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -22,6 +23,14 @@
 namespace {
 
 thread_local char g_err[512] = "";
+
+// Live indexes per device in this process, and a counter that moves whenever that number changes.  The in-kernel tail lets
+// CTAs of a grid wait for each other, which is only safe while no OTHER grid of this kind can hold SMs of the device
+// (SimpleRetriever + CupyRetriever in one service process, two indexes searched from two threads): with a second live
+// index on the device every search falls back to the separate merge launch - a few microseconds, never a stall.
+constexpr int kMaxDevices = 64;
+std::atomic<int> g_live_indexes[kMaxDevices];
+std::atomic<unsigned> g_live_epoch[kMaxDevices];
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -133,6 +142,8 @@ struct rs_index {
   unsigned int launch_parity = 0;
   float* g_best = nullptr;           // shared bound table [sm_count][256] (k > 16 and wide searches)
   void* cbuf = nullptr;              // wide searches: candidate buffers [256][grid][32] x 8 B
+  bool registered = false;           // counted in g_live_indexes
+  unsigned live_epoch_seen = 0;      // g_live_epoch when the cached CUDA graphs were captured
   int dm_pair_clusters = 0;          // same for the doc-major pair kernel (two-accumulator searches, B <= 32, k <= 16)
   int pair_clusters = -1;            // CTA pairs of the pair kernel this device keeps resident at once (-1: not queried)
   unsigned long long* debug_ts = nullptr;  // RS_DEBUG_TS=1: [grid][8] phase stamps of the last fused launch
@@ -449,7 +460,8 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   const int tail_cap = dmpair ? rs::fused_dmpair_tail_capacity(ix->kc, terms, ix->planes, pl.stages, pl.cps, pl.bpad)
                        : pl.wide == 2 ? rs::fused_pair_tail_capacity(k) : pl.wide ? rs::fused_wide_tail_capacity(k)
                                : rs::fused_tail_smem_capacity(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, pl.qstages);
-  const bool fused_tail = o.fused_tail != 0 && rs::fused_tail_smem_bytes(n_lists, k, xg ? xg->world : 1) <= (size_t)tail_cap;
+  const bool alone = !ix->registered || g_live_indexes[ix->cfg.device].load() <= 1;  // no other live index on this device
+  const bool fused_tail = o.fused_tail != 0 && alone && rs::fused_tail_smem_bytes(n_lists, k, xg ? xg->world : 1) <= (size_t)tail_cap;
   // pair kernel: whole pairs; every resident pair when the tail needs merging CTAs for up to 256 queries
   const int grid = pl.wide == 2 ? (fused_tail ? 2 * ix->pair_clusters : n_work)
                    : dmpair     ? n_work  // >= 8 tiles per SM: far more worker CTAs than queries
@@ -610,6 +622,13 @@ int search_host_locked(rs_index* ix, rs_xchg* xg, const float* q_host, int B, in
   rc = order_after_previous(ix, ix->stream);
   if (rc != RS_OK) return rc;
   memcpy(pin, q_host, q_bytes);
+  if (ix->registered) {  // an index was created or destroyed on this device: the cached launch sequences may have the wrong tail
+    const unsigned ep = g_live_epoch[ix->cfg.device].load();
+    if (ep != ix->live_epoch_seen) {
+      drop_graphs(ix);
+      ix->live_epoch_seen = ep;
+    }
+  }
   rs_index::GraphEntry* ge = nullptr;
   if (ix->opt.graph) {
     for (auto& g : ix->graphs)
@@ -754,12 +773,21 @@ RS_API int rs_create(const rs_config* cfg, rs_index** out) {
   }
   RS_ALLOC(cudaStreamSynchronize(ix->stream));
 #undef RS_ALLOC
+  if (cfg->device < kMaxDevices) {
+    g_live_indexes[cfg->device].fetch_add(1);
+    g_live_epoch[cfg->device].fetch_add(1);
+    ix->registered = true;
+  }
   *out = ix;
   return RS_OK;
 }
 
 RS_API int rs_destroy(rs_index* ix) {
   if (!ix) return RS_OK;
+  if (ix->registered) {
+    g_live_indexes[ix->cfg.device].fetch_sub(1);
+    g_live_epoch[ix->cfg.device].fetch_add(1);
+  }
   free_all(ix);
   delete ix;
   return RS_OK;
@@ -1044,6 +1072,7 @@ struct rs_group {
     cudaGraphExec_t exec;
   };
   std::vector<GraphEntry> graphs;
+  unsigned live_epoch_sum = 0;  // sum of g_live_epoch over the shards' devices when the graphs were captured
   int use_graph = 1;
   std::mutex mu;
 };
@@ -1159,6 +1188,17 @@ RS_API int rs_group_search(rs_group* gr, const float* q_host, int32_t B, int32_t
     if (rc != RS_OK) return rc;
   }
   memcpy(pin, q_host, q_bytes);
+  {  // an index was created or destroyed on one of the devices: the captured tails may be the wrong kind
+    unsigned ep = 0;
+    for (int g = 0; g < gr->n; ++g)
+      if (gr->ix[g]->registered) ep += g_live_epoch[gr->ix[g]->cfg.device].load();
+    if (ep != gr->live_epoch_sum) {
+      for (auto& g : gr->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+      gr->graphs.clear();
+      gr->live_epoch_sum = ep;
+    }
+  }
   rs_group::GraphEntry* ge = nullptr;
   if (gr->use_graph) {
     for (auto& g : gr->graphs)

@@ -707,6 +707,50 @@ def test_doc_major_pair_kernel(dtype, terms, metric, B, k, N):
         ix.close()
 
 
+def test_two_indexes_on_one_device_searched_concurrently(squad):
+    """SimpleRetriever + CupyRetriever in one service process (or two indexes searched from two threads): while a second
+    index lives on the device every search uses the separate merge launch instead of the in-kernel tail (whose CTAs
+    wait for each other and could starve against another such grid), cached CUDA graphs are dropped when the number
+    of live indexes changes, and concurrent searches return exactly what serial ones do."""
+    import threading
+    N = 128 * 300 + 11
+    E = o.synth_rows(17, np.arange(N))
+    Q, src = o.synth_queries(2, N, 32, 1024, dtype=o.DTYPE_BF16)
+    a = make_index(E, "bf16", max_batch=64, max_k=16)
+    try:
+        for _ in range(3):                                   # alone: in-kernel tail, graph captured
+            ia, sa = a.search(Q, 10, "dot", 1)
+        assert a.stats()["launches"] == 1
+        b = make_index(E[::-1].copy(), "bf16", max_batch=64, max_k=16)
+        try:
+            ib, sb = b.search(Q, 10, "dot", 1)
+            assert a.search(Q, 10, "dot", 1)[0].tolist() == ia.tolist()
+            assert a.stats()["launches"] == 2 and b.stats()["launches"] == 2      # separate merge kernel
+            errs = []
+
+            def loop(ix, want):
+                try:
+                    for _ in range(200):
+                        got, _s = ix.search(Q, 10, "dot", 1)
+                        if not np.array_equal(got, want):
+                            errs.append("mismatch")
+                            return
+                except Exception as e:  # noqa
+                    errs.append(repr(e))
+
+            ts = [threading.Thread(target=loop, args=(a, ia)), threading.Thread(target=loop, args=(b, ib))]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+            assert not errs, errs
+        finally:
+            b.close()
+        for _ in range(3):                                   # alone again: back to one launch
+            i2, _ = a.search(Q, 10, "dot", 1)
+        assert a.stats()["launches"] == 1 and np.array_equal(i2, ia)
+    finally:
+        a.close()
+
+
 # ---------------------------------------------------------------- property test over the whole shape space
 _PROP_ROWS = o.synth_rows(77, np.arange(128 * 310 + 57))      # generated once; a prefix of it is the corpus
 
