@@ -84,7 +84,8 @@ struct Options {
   int qlo_stream = 0;    // RS_QLO_STREAM   two-term searches: 1/2 = stream the lo query term
   int graph = 1;         // RS_GRAPH        0: host-buffer searches enqueue eagerly instead of replaying a CUDA graph
   int no_events = 0;     // RS_NO_EVENTS    1: no CUDA events around the fused launch
-  int dmpair = 1;        // RS_DMPAIR       1: two-accumulator doc-major searches of large corpora run on CTA pairs (cta_group::2); 0: never
+  int dmpair = 1;        // RS_DMPAIR       1: doc-major searches with two accumulators, or 32 < B <= 64, run on CTA pairs (cta_group::2)
+                         //                 when the corpus has >= 8 tiles per SM; 2: for any corpus size (tests); 0: never
   int wide = 2;          // RS_WIDE         batches above 128: 2 = one pass, CTA-pair kernel (cta_group::2); 1 = one pass, one CTA
                          //                 per SM; 0 = split into passes of 128
   int overlap = 0;       // RS_OVERLAP      1: consecutive device-buffer searches on one stream may overlap (PDL)
@@ -425,11 +426,12 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   // where each CTA keeps only HALF of the Q image and the document ring doubles (fused_search_dmpair_kernel).
   const int nacc = (terms == 2 || ix->planes == 2) ? 2 : 1;
   // (B <= 16: the whole image is 64 KiB anyway, and the one-CTA kernel keeps its in-kernel query prep)
-  bool dmpair = docm && nacc == 2 && pl.bpad > 16 && o.dmpair != 0 && ix->dm_pair_clusters > 0 && ix->n_tiles >= 8 * ix->sm_count;
+  const int dm_min_tiles = o.dmpair == 2 ? 1 : 8 * ix->sm_count;
+  bool dmpair = docm && nacc == 2 && pl.bpad > 16 && o.dmpair != 0 && ix->dm_pair_clusters > 0 && ix->n_tiles >= dm_min_tiles;
   // One accumulator (16-bit storage, one query term), 32 < B <= 64: the same kernel with N = 64 - each CTA holds 32
   // queries' image (64 KiB at D = 1024), where the one-CTA kernels would need 128 KiB resident or stream Q.
   const bool dmpair64 = !pl.wide && !docm && nacc == 1 && B > 32 && B <= 64 && k <= rs::fused_reg_k() && o.docm != 0 &&
-                        o.dmpair != 0 && ix->dm_pair_clusters > 0 && ix->n_tiles >= 8 * ix->sm_count;
+                        o.dmpair != 0 && ix->dm_pair_clusters > 0 && ix->n_tiles >= dm_min_tiles;
   if (dmpair || dmpair64) {
     const int bpad = dmpair64 ? 64 : 32;
     int cps = o.cps > 0 ? o.cps : (ix->planes == 2 ? 2 : 4);  // 64 KiB ring stages

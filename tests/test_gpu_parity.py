@@ -755,15 +755,16 @@ def test_two_indexes_on_one_device_searched_concurrently(squad):
 _PROP_ROWS = o.synth_rows(77, np.arange(128 * 310 + 57))      # generated once; a prefix of it is the corpus
 
 
-@settings(max_examples=100, deadline=None, derandomize=True,
+@settings(max_examples=150, deadline=None, derandomize=True,
           suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture, HealthCheck.data_too_large])
 @given(n=st.one_of(st.integers(1, 600), st.integers(601, len(_PROP_ROWS))), B=st.integers(1, 256), k=st.integers(1, 100),
        dtype=st.sampled_from(["bf16", "fp16", "fp32"]), metric=st.sampled_from(["dot", "cosine"]),
-       two_terms=st.booleans(), seed=st.integers(0, 2 ** 16))
-def test_property_any_shape_matches_oracle(n, B, k, dtype, metric, two_terms, seed):
+       two_terms=st.booleans(), seed=st.integers(0, 2 ** 16), force_pair=st.booleans())
+def test_property_any_shape_matches_oracle(n, B, k, dtype, metric, two_terms, seed, force_pair):
     """for ANY corpus size (not a multiple of the tile, fewer rows than k, one row), batch 1..256, k 1..100,
     storage type, metric and query-term count, the kernel the planner picks (doc-major, query-major resident or
-    streamed, wide pair, k <= 16 register lists or k > 16 buffered lists) returns the oracle's top-k: index sets
+    streamed, wide pair, doc-major pair - forced onto small corpora by RS_DMPAIR=2 in half of the examples -, k <= 16
+    register lists or k > 16 buffered lists) returns the oracle's top-k: index sets
     identical up to provable near-ties, scores inside the tolerance, (-1, -inf) padding past the corpus size, and
     the same answer when the call is repeated."""
     E = _PROP_ROWS[:n]
@@ -776,6 +777,8 @@ def test_property_any_shape_matches_oracle(n, B, k, dtype, metric, two_terms, se
     sx = 4 if dtype == "fp32" else 0
     ix = make_index(E, dtype, sx, max_batch=256, max_k=128)
     try:
+        if force_pair:
+            ix.set_option("RS_DMPAIR", 2)                   # doc-major pair kernel for any corpus size (where its shapes apply)
         idx, sc = ix.search(Q, k, metric, terms)
         S = exact_scores(Q, E, dtype, metric, terms, sx)
         o.check_topk(idx, sc, S, k, rtol=RTOL[dtype], atol=1e-6)
