@@ -86,8 +86,7 @@ struct Options {
   int no_events = 0;     // RS_NO_EVENTS    1: no CUDA events around the fused launch
   int dmpair = 1;        // RS_DMPAIR       1: doc-major searches with two accumulators, or 32 < B <= 64, run on CTA pairs (cta_group::2)
                          //                 when the corpus has >= 8 tiles per SM; 2: for any corpus size (tests); 0: never
-  int wide = 2;          // RS_WIDE         batches above 128: 2 = one pass, CTA-pair kernel (cta_group::2); 1 = one pass, one CTA
-                         //                 per SM; 0 = split into passes of 128
+  int wide = 1;          // RS_WIDE         batches above 128: 1 = ONE pass on CTA pairs (fused_search_pair_kernel); 0 = passes of 128
   int overlap = 0;       // RS_OVERLAP      1: consecutive device-buffer searches on one stream may overlap (PDL)
   int debug_flags = 0;   // RS_DEBUG_FLAGS  timing experiments: skip MMAs (1) / the epilogue (2) / the tail merge (4); pair kernel:
                          //                 thresholds at +inf so nothing is ever appended (32), documents without the L2 evict_first hint (64)
@@ -226,32 +225,23 @@ int make_plan(const rs_index* ix, const Options& o, int B, int k, int terms, Pla
   const int qstages = o.qstages > 0 ? o.qstages : 2 * terms;
   pl->qstages = qstages;
   pl->wide = 0;
-  if (o.wide != 0 && B > 128 && terms == 1 && ix->planes == 1 && rs::fused_wide_smem_bytes(k) <= kMaxSmem) {
-    // Wide batches (BASELINE config 5: B=256): both 128-row halves of the batch share ONE pass over the shard;
-    // the general kernel would stream the shard once per 128 queries.
+  if (o.wide != 0 && B > 128 && terms == 1 && ix->planes == 1 && ix->pair_clusters != 0 && rs::fused_pair_smem_bytes(k) <= kMaxSmem) {
+    // Wide batches (BASELINE config 5: B=256): both 128-row halves of the batch share ONE pass over the shard on CTA pairs
+    // (fused_search_pair_kernel: M=256 x N=256 MMAs across two SMs, two TMEM accumulators); the general kernel would
+    // stream the shard once per 128 queries.
+    pl->wide = 1;
     pl->passes = (B + 255) / 256;
     pl->per_pass = (B + pl->passes - 1) / pl->passes;
     pl->bpad = 256;
     pl->q_resident = 0;
     pl->sub = 2;
-    pl->cps = 1;
     pl->bufc = rs::fused_wide_bufc();
     pl->lg = 1;
-    if (o.wide == 2 && ix->pair_clusters != 0 && rs::fused_pair_smem_bytes(k) <= kMaxSmem) {
-      // CTA pairs (fused_search_pair_kernel): M=256 x N=256 MMAs across two SMs, two TMEM accumulators
-      pl->wide = 2;
-      pl->qstages = 0;
-      pl->cps = (o.cps == 2 && ix->kc % 2 == 0) ? 2 : 1;  // k-chunks per ring slot (32 KiB each)
-      pl->stages = 6 / pl->cps;
-      pl->nbuf = 2;
-      pl->mma_m = 256;
-      return RS_OK;
-    }
-    pl->wide = 1;  // fused_search_wide_kernel: one CTA per SM, one accumulator
-    pl->qstages = (o.qstages >= 2 && o.qstages <= rs::fused_wide_slots() - 2) ? o.qstages : 2;  // Q k-chunks come from L2 (short
-    pl->stages = rs::fused_wide_slots() - pl->qstages;  // latency), document k-chunks from HBM: the ring's 6 slots go 2 : 4
-    pl->nbuf = 1;
-    pl->mma_m = 128;
+    pl->qstages = 0;
+    pl->cps = (o.cps == 2 && ix->kc % 2 == 0) ? 2 : 1;  // k-chunks per ring slot (32 KiB each)
+    pl->stages = 6 / pl->cps;
+    pl->nbuf = 2;
+    pl->mma_m = 256;
     return RS_OK;
   }
   long long best_cost = -1;
@@ -451,21 +441,21 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
     }
   }
   // CTAs that own tiles.  Pair kernel: both CTAs of every pair that owns a supertile (two tiles)
-  const int n_work = pl.wide == 2 ? 2 * std::min(ix->pair_clusters, (ix->n_tiles + 1) / 2)
+  const int n_work = pl.wide ? 2 * std::min(ix->pair_clusters, (ix->n_tiles + 1) / 2)
                      : dmpair     ? 2 * std::min(ix->dm_pair_clusters, (ix->n_tiles + 1) / 2)
                                   : std::min(ix->sm_count, ix->n_tiles);
-  const int n_lists = pl.wide == 2 ? n_work / 2 : n_work;  // candidate lists per query
+  const int n_lists = pl.wide ? n_work / 2 : n_work;  // candidate lists per query
   // single-launch search (default): query prep in the fused kernel's prologue (resident-Q plans) and the
   // candidate merge (+ exchange) in its tail.  RS_INLINE_PREP=0 / RS_FUSED_TAIL=0 fall back to the
   // separate query_prep_kernel / merge kernels.
   const bool inline_prep = !pl.wide && !dmpair && pl.q_resident == 1 && ix->cfg.dim <= 1024 && pl.bpad <= 32 && o.inline_prep != 0;
   const int tail_cap = dmpair ? rs::fused_dmpair_tail_capacity(ix->kc, terms, ix->planes, pl.stages, pl.cps, pl.bpad)
-                       : pl.wide == 2 ? rs::fused_pair_tail_capacity(k) : pl.wide ? rs::fused_wide_tail_capacity(k)
+                       : pl.wide ? rs::fused_pair_tail_capacity(k)
                                : rs::fused_tail_smem_capacity(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, pl.qstages);
   const bool alone = !ix->registered || g_live_indexes[ix->cfg.device].load() <= 1;  // no other live index on this device
   const bool fused_tail = o.fused_tail != 0 && alone && rs::fused_tail_smem_bytes(n_lists, k, xg ? xg->world : 1) <= (size_t)tail_cap;
   // pair kernel: whole pairs; every resident pair when the tail needs merging CTAs for up to 256 queries
-  const int grid = pl.wide == 2 ? (fused_tail ? 2 * ix->pair_clusters : n_work)
+  const int grid = pl.wide ? (fused_tail ? 2 * ix->pair_clusters : n_work)
                    : dmpair     ? n_work  // >= 8 tiles per SM: far more worker CTAs than queries
                                 : fused_tail ? std::max(n_work, std::min(pl.per_pass, ix->sm_count)) : n_work;
   // overlapped launches (RS_OVERLAP=1): the scan of this search may run while the previous search's tail drains.
@@ -473,12 +463,12 @@ int search_device_locked(rs_index* ix, const float* q_dev, int B, int k, int met
   const bool pdl = o.overlap != 0 && !ix->capturing && inline_prep && fused_tail && pl.passes == 1 &&
                    k <= rs::fused_reg_k() && !o.debug_ts;
   // bound shared between CTAs: needs (lists x published rank) >= k documents known to reach it
-  const int bound_rank = pl.wide == 2 && n_lists < k ? 2 : 1;
+  const int bound_rank = pl.wide && n_lists < k ? 2 : 1;
   const bool shared_bound = (k > rs::fused_reg_k() || pl.wide) && n_lists * bound_rank >= k && o.shared_bound != 0;
   ix->stats.grid = grid;
   ix->stats.stages = pl.stages;
   ix->stats.smem_bytes = dmpair ? rs::fused_dmpair_smem_bytes(ix->kc, terms, ix->planes, pl.stages, pl.cps, pl.bpad)
-                         : pl.wide == 2 ? rs::fused_pair_smem_bytes(k) : pl.wide ? rs::fused_wide_smem_bytes(k)
+                         : pl.wide ? rs::fused_pair_smem_bytes(k)
                                  : rs::fused_smem_bytes(pl.bpad, ix->kc, terms, pl.stages, pl.cps, k, pl.q_resident, pl.qstages, pl.bufc, pl.lg, docm);
   ix->stats.q_resident = pl.q_resident;
   ix->stats.sub = pl.sub;

@@ -73,13 +73,12 @@ struct SearchParams {
   long long* out_idx;
   long long idx_offset;              // global index of this shard's row 0
   ExchangeArgs x;                    // tail_mode == 2
-  int wide;                          // wide-batch kernels (128 < B <= 256 in one pass): 1 = fused_search_wide_kernel (one CTA per
-                                     // SM), 2 = fused_search_pair_kernel (CTA pairs, tcgen05 cta_group::2)
+  int wide;                          // 1: wide-batch kernel (128 < B <= 256 in one pass; fused_search_pair_kernel, CTA pairs)
   int dmpair;                        // doc-major CTA-pair kernel (fused_search_dmpair_kernel), k <= 16: two accumulators and B <= 32,
                                      // or one accumulator and 32 < B <= 64
   int n_lists;                       // candidate lists per query the tail merges: n_work, or the worker PAIRS of the pair kernel
   int bound_rank;                    // pair kernel, shared bound: a CTA publishes its 1st or 2nd best score per query
-  uint2* cbuf;                       // wide: [n_queries][n_work][32] candidate buffers {score bits, local row id}
+  uint2* cbuf;                       // wide: [n_queries][n_lists][32] candidate buffers {score bits, local row id}
   float* g_best;                     // k > 16: [n_work][bpad] best score seen per (CTA, query), NaN = none yet; null = off
   unsigned long long* debug_ts;      // null, or [grid][8] globaltimer stamps of the kernel's phases (RS_DEBUG_TS=1)
 };
@@ -90,10 +89,7 @@ cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t st
 int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages, int bufc,
                      int lists_global, int docm = 0);
 int fused_reg_k();
-int fused_wide_smem_bytes(int k);
-int fused_wide_tail_capacity(int k);
 int fused_wide_bufc();
-int fused_wide_slots();
 int fused_pair_smem_bytes(int k);
 int fused_pair_tail_capacity(int k);
 int fused_pair_max_clusters(int k);

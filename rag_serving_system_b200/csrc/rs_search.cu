@@ -1687,454 +1687,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const __grid_
   fused_tail(p, smem, worker);
 }
 
-// ==========================================================================================
-// Wide-batch variant: 128 < B <= 256 queries share ONE pass over the shard (one query term, 16-bit storage;
-// BASELINE config 5: B=256, k=100, the tensor-bound regime).  Query-major like the general kernel, but
-//   * the batch is two HALVES of 128 query rows.  Both halves multiply the same document blocks: a document
-//     block is read from HBM once and stays in shared memory for the two MMA chains (the two-pass plan read
-//     the shard twice);
-//   * documents travel as tile PAIRS: a ring stage holds the same k-chunk of two consecutive tiles back to back
-//     (256 rows, 32 KiB), which is exactly one N=256 K-major SWIZZLE_128B operand, so one M=128 x N=256 MMA per
-//     16 k-elements and half replaces four M=128 x N=128 ones (12 KiB of operand reads per 128 tensor cycles
-//     instead of 8 KiB per 64);
-//   * Q k-chunks (256 rows x 64 columns = 32 KiB) stream through a ring of 3 slots - one slot is reused by both
-//     tiles of the pair - so the L2->SM traffic of Q equals the document traffic instead of twice it;
-//   * TMEM: [half][tile of the pair][128 columns] = all 512 columns, single-buffered.  The epilogue therefore
-//     only FILTERS while it holds the accumulator (scores -> threshold compare -> passing candidates appended to
-//     a per-(query, CTA) buffer); the expensive part - merging a full buffer into the query's sorted list - is
-//     deferred until the accumulator is back with the MMA warp and overlaps the next supertile's MMAs;
-//   * selection state lives in global memory (L2): the sorted lists are the per-CTA candidate arrays the tail
-//     merges anyway (cand_*, final units), the 32-entry candidate buffers are cbuf.  Shared memory is all ring.
-// An epilogue thread owns query rows r and 128 + r.  Prologue (query_prep_kernel, bpad = 256) and tail (merge,
-// exchange) are the general kernel's.
-// ==========================================================================================
-constexpr int kWideSlots = 6;      // 32 KiB ring slots in all: p.qstages of them hold Q k-chunks, p.stages document k-chunks
-constexpr int kWideBufC = 32;     // candidate-buffer entries per (query, CTA)
+// Selection state of the wide-batch (CTA-pair) kernel: per (query, list) a 32-entry candidate buffer in global memory
+constexpr int kWideBufC = 32;     // candidate-buffer entries per (query, pair)
 constexpr int kWideFlushAt = 20;  // deferred flush once a buffer holds this many (a full one is flushed on the spot)
-constexpr uint32_t kWideSlotBytes = 2u * RS_BLOCK_BYTES;  // 32 KiB
-
-struct WideSmem {
-  uint32_t q_off, d_off, bar_off, dump_off, scratch_off, total;
-};
-__host__ __device__ inline WideSmem make_wide_smem(int k, int qslots = 2) {
-  WideSmem m;
-  m.q_off = 0;
-  m.d_off = (uint32_t)qslots * kWideSlotBytes;
-  m.bar_off = (uint32_t)kWideSlots * kWideSlotBytes;
-  m.dump_off = m.bar_off + 1024u;                                 // barriers, scheduler queue, TMEM address
-  m.scratch_off = m.dump_off + 4u * 32u * 32u * 4u;               // rare-path chunk per warp: [32 columns][32 lanes]
-  m.total = m.scratch_off + 4u * (2u * (uint32_t)k + 64u) * 4u;   // per warp: list scores k, list ids k, 32 sorted candidates
-  return m;
-}
-
-__global__ void __launch_bounds__(kThreads, 1) fused_search_wide_kernel(const __grid_constant__ SearchParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int kWideQSlots = p.qstages, kWideDStages = p.stages;  // kWideQSlots + kWideDStages == kWideSlots
-  const WideSmem map = make_wide_smem(p.k, kWideQSlots);
-  const uint32_t smem_base = smem_u32(smem);
-  const uint32_t q_smem = smem_base + map.q_off, d_smem = smem_base + map.d_off, bar_base = smem_base + map.bar_off;
-  auto dfull = [&](int s) { return bar_base + 8u * (uint32_t)s; };
-  auto dempty = [&](int s) { return bar_base + 8u * (uint32_t)(kWideDStages + s); };
-  auto qfull = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kWideDStages + s); };
-  auto qempty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kWideDStages + kWideQSlots + s); };
-  const uint32_t tfull = bar_base + 8u * (uint32_t)(2 * kWideSlots);
-  const uint32_t tempty = tfull + 8u;
-  constexpr int kSched = 8;
-  auto sched_full = [&](int s) { return tempty + 8u + 8u * (uint32_t)s; };
-  auto sched_empty = [&](int s) { return tempty + 8u + 8u * (uint32_t)(kSched + s); };
-  volatile int* tile_u = reinterpret_cast<volatile int*>(smem + map.bar_off + 512);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + map.bar_off + 512 + 4 * kSched);
-  const bool worker = (int)blockIdx.x < p.n_work;
-  const int n_super = (p.n_tiles + 1) / 2;
-  const size_t tile_bytes = (size_t)p.kc * RS_BLOCK_BYTES;
-  constexpr uint32_t kTmemCols = 512;
-
-  if (threadIdx.x == 0) {
-    stamp(p.debug_ts, 0);
-    for (int s = 0; s < kWideDStages; ++s) {
-      mbar_init(dfull(s), 1);
-      mbar_init(dempty(s), 1);
-    }
-    for (int s = 0; s < kWideQSlots; ++s) {
-      mbar_init(qfull(s), 1);
-      mbar_init(qempty(s), 1);
-    }
-    mbar_init(tfull, 1);
-    mbar_init(tempty, kNumEpiWarps);
-    for (int s = 0; s < kSched; ++s) {
-      mbar_init(sched_full(s), 1);
-      mbar_init(sched_empty(s), 1 + kNumEpiWarps);
-    }
-    fence_mbar_init();
-    fence_proxy_async();
-  }
-  if (warp == kMmaWarp) {
-    tmem_alloc(smem_u32((const void*)tmem_slot), kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == kProducerWarp) {
-    // ===================== bulk-copy producer + dynamic scheduler =====================
-    const uint64_t pol_stream = l2_policy_evict_first();
-    const uint64_t pol_keep = l2_policy_evict_last();
-    int ds = 0, qs = 0, sslot = 0;
-    uint32_t dph = 0, qph = 0, sph = 0;
-    int u = (worker && (int)blockIdx.x < n_super) ? (int)blockIdx.x : -1;
-    while (true) {
-      mbar_wait(sched_empty(sslot), sph ^ 1u);
-      if (lane == 0) {
-        tile_u[sslot] = u;
-        mbar_arrive(sched_full(sslot));
-      }
-      if (++sslot == kSched) {
-        sslot = 0;
-        sph ^= 1u;
-      }
-      if (u < 0) break;
-      int nxt = u + (int)gridDim.x;
-      if (p.dyn_sched && lane == 0) nxt = (int)atomicAdd(p.sync + 4, 1u) + (int)gridDim.x;
-      const int nsub = min(2, p.n_tiles - 2 * u);
-      const uint8_t* src = p.corpus + (size_t)u * 2 * tile_bytes;
-      for (int kc = 0; kc < p.kc; ++kc) {
-        mbar_wait(qempty(qs), qph ^ 1u);
-        if (lane == 0) {
-          mbar_arrive_expect_tx(qfull(qs), kWideSlotBytes);
-          bulk_g2s(q_smem + (uint32_t)qs * kWideSlotBytes, p.qimg + (size_t)kc * kWideSlotBytes, kWideSlotBytes, qfull(qs), pol_keep);
-        }
-        if (++qs == kWideQSlots) {
-          qs = 0;
-          qph ^= 1u;
-        }
-        mbar_wait(dempty(ds), dph ^ 1u);
-        if (lane == 0) {
-          const uint32_t dst = d_smem + (uint32_t)ds * kWideSlotBytes;
-          mbar_arrive_expect_tx(dfull(ds), (uint32_t)nsub * RS_BLOCK_BYTES);
-          bulk_g2s(dst, src + (size_t)kc * RS_BLOCK_BYTES, RS_BLOCK_BYTES, dfull(ds), pol_stream);
-          if (nsub == 2) bulk_g2s(dst + RS_BLOCK_BYTES, src + tile_bytes + (size_t)kc * RS_BLOCK_BYTES, RS_BLOCK_BYTES, dfull(ds), pol_stream);
-        }
-        if (++ds == kWideDStages) {
-          ds = 0;
-          dph ^= 1u;
-        }
-      }
-      nxt = __shfl_sync(0xffffffffu, nxt, 0);
-      u = nxt < n_super ? nxt : -1;
-    }
-  } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer: per k-chunk 2 halves x 4 MMAs of M=128 x N=256 x K=16 =====================
-    const uint32_t idesc = umma_idesc_f16(p.dtype == RS_DTYPE_BF16, 128, 256);
-    const bool skip_mma = (p.debug_flags & 1) != 0;
-    int ds = 0, qs = 0, sslot = 0;
-    uint32_t dph = 0, qph = 0, sph = 0, acc_ph = 0;
-    while (true) {
-      mbar_wait(sched_full(sslot), sph);
-      const int u = tile_u[sslot];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sched_empty(sslot));
-      if (++sslot == kSched) {
-        sslot = 0;
-        sph ^= 1u;
-      }
-      if (u < 0) break;
-      mbar_wait(tempty, acc_ph ^ 1u);
-      tc_fence_after();
-      for (int kc = 0; kc < p.kc; ++kc) {
-        mbar_wait(qfull(qs), qph);
-        mbar_wait(dfull(ds), dph);
-        tc_fence_after();
-        if (lane == 0 && !skip_mma) {
-          const uint32_t qa = q_smem + (uint32_t)qs * kWideSlotBytes;
-          const uint64_t a0 = umma_smem_desc(qa), a1 = umma_smem_desc(qa + RS_BLOCK_BYTES);
-          const uint64_t b = umma_smem_desc(d_smem + (uint32_t)ds * kWideSlotBytes);
-#pragma unroll
-          for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
-            umma_f16(tmem_base, a0 + 2u * ks, b + 2u * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
-#pragma unroll
-          for (int ks = 0; ks < RS_KCHUNK_ELEMS / RS_UMMA_K; ++ks)
-            umma_f16(tmem_base + 256u, a1 + 2u * ks, b + 2u * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
-        }
-        __syncwarp();
-        if (lane == 0) {
-          umma_commit(dempty(ds));
-          umma_commit(qempty(qs));
-        }
-        if (++ds == kWideDStages) {
-          ds = 0;
-          dph ^= 1u;
-        }
-        if (++qs == kWideQSlots) {
-          qs = 0;
-          qph ^= 1u;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) umma_commit(tfull);
-      acc_ph ^= 1u;
-    }
-  } else {
-    // ===================== epilogue: a thread owns query rows r and 128 + r =====================
-    const int quarter = warp & 3;
-    const int k = p.k;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const bool cosine = p.metric == RS_METRIC_COSINE;
-    int row[2];
-    bool live[2];
-    float qs[2], inv_qs[2], nq[2], thr[2], thr_raw[2], best_seen[2], gbound[2];
-    int cnt[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      row[h] = h * 128 + quarter * 32 + lane;
-      live[h] = row[h] < p.n_queries;
-      qs[h] = live[h] ? p.qscale[row[h]] : 1.f;
-      inv_qs[h] = 1.0f / qs[h];
-      nq[h] = live[h] ? p.qnorm[row[h]] : 0.f;
-      thr[h] = live[h] ? -CUDART_INF_F : CUDART_INF_F;
-      thr_raw[h] = thr[h];
-      best_seen[h] = -CUDART_INF_F;
-      gbound[h] = -CUDART_INF_F;
-      cnt[h] = 0;
-    }
-    float* dump = reinterpret_cast<float*>(smem + map.dump_off) + (size_t)quarter * 32 * 32;
-    float* Ws = reinterpret_cast<float*>(smem + map.scratch_off) + (size_t)quarter * (2 * k + 64);
-    int* Wi = reinterpret_cast<int*>(Ws + k);
-    float* Bs = Ws + 2 * k;
-    auto glist_s = [&](int qrow) { return p.cand_score + ((size_t)qrow * p.n_work + blockIdx.x) * k; };
-    auto glist_i = [&](int qrow) { return p.cand_idx + ((size_t)qrow * p.n_work + blockIdx.x) * k; };
-    auto gbuf = [&](int qrow) { return p.cbuf + ((size_t)qrow * p.n_work + blockIdx.x) * kWideBufC; };
-    if (worker) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-        if (live[h]) {
-          float* l0 = glist_s(row[h]);
-          int* i0 = glist_i(row[h]);
-          for (int j = 0; j < k; ++j) {
-            l0[j] = -CUDART_INF_F;
-            i0[j] = -1;
-          }
-        }
-    }
-    __syncwarp();
-    const bool shared_bound = p.g_best != nullptr && worker;
-    int tiles_done = 0, next_refresh = 1;
-    // merge query ql (of half h) of this warp: its n buffered candidates -> its sorted list; returns the new k-th
-    // best in FILTER units (raw accumulator units for dot).  Whole warp, converged.
-    auto flush_query = [&](const float qs_h, const float inv_qs_h, int h, int ql, int n) -> float {
-      const int qrow = h * 128 + quarter * 32 + ql;
-      const float unit = cosine ? 1.0f : __shfl_sync(0xffffffffu, qs_h, ql);  // list units = final units
-      float* gs = glist_s(qrow);
-      int* gi = glist_i(qrow);
-      float cs = -CUDART_INF_F;
-      int ci = 0x7fffffff;
-      if (lane < n) {
-        const uint2 c = __ldcg(gbuf(qrow) + lane);
-        cs = __uint_as_float(c.x) * unit;
-        ci = (int)c.y;
-      }
-      for (int j = lane; j < k; j += 32) {
-        Ws[j] = __ldcg(gs + j);
-        Wi[j] = __ldcg(gi + j);
-      }
-      __syncwarp();
-      const float nt = merge_sorted_candidates(Ws, Wi, Bs, cs, ci, n, k, lane);
-      for (int j = lane; j < k; j += 32) {
-        __stcg(gs + j, Ws[j]);
-        __stcg(gi + j, Wi[j]);
-      }
-      __syncwarp();
-      if (p.debug_ts && lane == 0) atomicAdd(p.debug_ts + (size_t)blockIdx.x * 8 + 7, 1ull << 32);  // flushes
-      return cosine ? nt : nt * __shfl_sync(0xffffffffu, inv_qs_h, ql);  // exact: qs is a power of two
-    };
-
-    int sslot = 0;
-    uint32_t sph = 0, acc_ph = 0;
-    // RS_DEBUG_TS: cycles this warp spent waiting for an accumulator / holding it / merging afterwards (slots 1-3)
-    const bool prof = p.debug_ts != nullptr && threadIdx.x == kFirstEpiWarp * 32;
-    long long t_wait = 0, t_hold = 0, t_merge = 0, tc0 = 0, tc1 = 0, tc2 = 0;
-    while (true) {
-      mbar_wait(sched_full(sslot), sph);
-      const int u = tile_u[sslot];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sched_empty(sslot));
-      if (++sslot == kSched) {
-        sslot = 0;
-        sph ^= 1u;
-      }
-      if (u < 0) break;
-      const int nsub = min(2, p.n_tiles - 2 * u);
-      if (prof) tc0 = clock64();
-      mbar_wait(tfull, acc_ph);
-      tc_fence_after();
-      if (prof) tc1 = clock64();
-      if (shared_bound && tiles_done >= next_refresh) {  // after 1, 2, 4, ... tiles, then every 64 (see the general kernel)
-        next_refresh = tiles_done < 64 ? 2 * tiles_done : tiles_done + 64;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (live[h]) {
-            float mn = CUDART_INF_F;
-#pragma unroll 8
-            for (int c = 0; c < p.n_work; ++c) {
-              const float v = __ldcg(p.g_best + (size_t)c * p.bpad + row[h]);
-              mn = fminf(mn, v == v ? v : -CUDART_INF_F);  // NaN = that CTA has not published yet
-            }
-            if (mn > -CUDART_INF_F && mn < CUDART_INF_F) {
-              gbound[h] = __uint_as_float(__float_as_uint(mn) + (mn > 0.f ? -1 : (mn < 0.f ? 1 : 0)));  // next float below
-              if (mn == 0.f) gbound[h] = -1.401298464e-45f;
-              if (gbound[h] > thr[h]) {
-                thr[h] = gbound[h];
-                thr_raw[h] = cosine ? CUDART_INF_F : thr[h];  // cosine: recomputed per tile just below
-              }
-            }
-          }
-        }
-      }
-      tiles_done += nsub;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (h * 128 + quarter * 32 >= p.n_queries || (p.debug_flags & 2)) continue;  // no live row of this warp in the half
-        for (int sub = 0; sub < nsub; ++sub) {
-          const int t = 2 * u + sub;
-          float ndmin = 1.f, ndmax = 1.f;
-          if (cosine) {
-            const float2 mm = p.tile_norm_minmax[t];
-            ndmin = mm.x;
-            ndmax = mm.y;
-            thr_raw[h] = live[h] ? cosine_raw_bound(thr[h], nq[h], inv_qs[h], ndmin, ndmax) : CUDART_INF_F;
-          }
-          const uint32_t tacc = lane_base + (uint32_t)(h * 256 + sub * 128);
-          const int tile_row0 = t * RS_TILE_ROWS;
-#pragma unroll 1
-          for (int c0 = 0; c0 < RS_TILE_ROWS; c0 += 32) {
-            float v[32];
-            {
-              uint32_t r0[32];
-              tmem_ld_x32(tacc + c0, r0);
-              tmem_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
-            }
-            const float m = max32(v);
-            if (__any_sync(0xffffffffu, m > thr_raw[h])) {
-              uint32_t pm = 0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                pm |= (v[j] > thr_raw[h]) ? (1u << j) : 0u;
-                dump[j * 32 + lane] = v[j];
-              }
-              if (tile_row0 + c0 + 32 > p.n_rows) {  // ragged last tile: mask padded rows
-                const int valid = p.n_rows - (tile_row0 + c0);
-                pm = valid <= 0 ? 0u : (pm & (0xffffffffu >> (32 - valid)));
-              }
-              __syncwarp();
-              while (__any_sync(0xffffffffu, pm != 0u)) {
-                if (pm != 0u) {
-                  const int j = __ffs(pm) - 1;
-                  pm &= pm - 1;
-                  const float s = dump[j * 32 + lane];
-                  const int idx = tile_row0 + c0 + j;
-                  float x = s;  // dot: compare and buffer raw units (exact power-of-two scale)
-                  if (cosine) {
-                    const float nd = p.dnorm[idx];
-                    const float denom = __fadd_rn(__fmul_rn(nq[h], nd), 1e-8f);  // retriever.py:605,607
-                    x = __fdiv_rn(s * qs[h], denom);
-                    x = fminf(fmaxf(x, -1.0f), 1.0f);                            // retriever.py:609
-                  }
-                  if (x > thr[h]) {
-                    __stcg(gbuf(row[h]) + cnt[h], make_uint2(__float_as_uint(x), (unsigned int)idx));
-                    ++cnt[h];
-                    if (p.debug_ts) atomicAdd(p.debug_ts + (size_t)blockIdx.x * 8 + 7, 1ull);  // appends (low word)
-                    if (shared_bound && x > best_seen[h]) {
-                      best_seen[h] = x;
-                      __stcg(p.g_best + (size_t)blockIdx.x * p.bpad + row[h], x);
-                    }
-                  }
-                }
-                uint32_t full = __ballot_sync(0xffffffffu, cnt[h] == kWideBufC);  // (rare: flushes normally happen below)
-                while (full) {
-                  const int ql = __ffs(full) - 1;
-                  full &= full - 1;
-                  const float nt = flush_query(qs[h], inv_qs[h], h, ql, kWideBufC);
-                  if (lane == ql) {
-                    thr[h] = fmaxf(nt, gbound[h]);
-                    cnt[h] = 0;
-                    thr_raw[h] = cosine ? cosine_raw_bound(thr[h], nq[h], inv_qs[h], ndmin, ndmax) : thr[h];
-                  }
-                }
-              }
-              __syncwarp();
-            }
-          }
-        }
-      }
-      // every TMEM read of this supertile is complete (wait::ld above): hand the accumulator back, THEN merge
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);
-      acc_ph ^= 1u;
-      if (prof) tc2 = clock64();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t due = __ballot_sync(0xffffffffu, cnt[h] >= kWideFlushAt);
-        while (due) {
-          const int ql = __ffs(due) - 1;
-          due &= due - 1;
-          const int n = __shfl_sync(0xffffffffu, cnt[h], ql);
-          const float nt = flush_query(qs[h], inv_qs[h], h, ql, n);
-          if (lane == ql) {
-            thr[h] = fmaxf(nt, gbound[h]);
-            cnt[h] = 0;
-            thr_raw[h] = cosine ? CUDART_INF_F : thr[h];  // cosine: recomputed per tile
-          }
-        }
-      }
-      if (prof) {
-        t_wait += tc1 - tc0;
-        t_hold += tc2 - tc1;
-        t_merge += clock64() - tc2;
-      }
-    }
-    if (prof) {
-      p.debug_ts[(size_t)blockIdx.x * 8 + 1] = (unsigned long long)t_wait;
-      p.debug_ts[(size_t)blockIdx.x * 8 + 2] = (unsigned long long)t_hold;
-      p.debug_ts[(size_t)blockIdx.x * 8 + 3] = (unsigned long long)t_merge;
-    }
-    // drain the partially filled buffers; the lists already sit in cand_* in final units
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint32_t rem = __ballot_sync(0xffffffffu, cnt[h] > 0);
-      while (rem) {
-        const int ql = __ffs(rem) - 1;
-        rem &= rem - 1;
-        const int n = __shfl_sync(0xffffffffu, cnt[h], ql);
-        flush_query(qs[h], inv_qs[h], h, ql, n);
-      }
-    }
-  }
-
-  if (p.tail_mode != 0) __threadfence();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kMmaWarp) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-  fused_tail(p, smem, worker);
-}
 
 // ==========================================================================================
-// CTA-pair variant of the wide-batch kernel (the default for 128 < B <= 256 per pass): the two SMs of a TPC run
-// as a thread-block cluster of 2 and share ONE document stream through tcgen05.mma.cta_group::2.
+// Wide-batch kernel (128 < B <= 256 queries per pass share ONE pass over the shard; one query term, 16-bit storage;
+// BASELINE config 5: B=256, k=100, the tensor-bound regime): the two SMs of a TPC run as a thread-block cluster of 2 and
+// share ONE document stream through tcgen05.mma.cta_group::2.  (The general kernel holds one query per TMEM lane and
+// would stream the shard once per 128 queries; a one-CTA form of this kernel - both 128-row halves against N=256 tile
+// pairs - needs all 512 TMEM columns for one supertile, so its MMAs and its epilogue alternate: 8.0 ms per 12.5M-row
+// slice where this kernel takes 5.9-6.2.  It was removed.)
 //   * CTA rank r of a pair owns query rows 128r .. 128r+127 (its half of the MMA's M = 256) and loads ONE tile
 //     of the pair's supertile (tiles 2u and 2u+1 = the two halves of the MMA's N = 256): per k-chunk a CTA
 //     brings 16 KiB of documents from HBM and 16 KiB of its own query rows from L2 into one 32 KiB ring slot;
 //     the tensor cores read the other CTA's document half through the pair link.  L2->SM traffic of Q equals the
-//     document traffic, as in the single-CTA wide kernel.
+//     document traffic.
 //   * One thread of the leader (rank 0) issues M=256 x N=256 x K=16 MMAs (128 tensor cycles each, the full rate
 //     of both SMs; 8 KiB of shared-memory operand reads per CTA per MMA = half the limit).  Each CTA's TMEM
 //     receives ITS 128 query rows x 256 documents = 256 columns, so the 512 columns hold TWO accumulators and
@@ -2146,9 +1714,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_wide_kernel(const __
 //   * Static schedule: pair P takes supertiles P, P + n_pairs, ... (ascending document order per CTA, which the
 //     tie rule needs).  An odd tile count leaves the last supertile with one tile: rank 1 re-reads tile 2u and
 //     nobody looks at columns 128-255.
-//   * Epilogue: a thread owns ONE query; selection state as in the wide kernel (sorted list in cand_*, 32-entry
-//     candidate buffer in cbuf, both L2-resident; filter while holding the accumulator, merge after releasing
-//     it); TMEM loads are software-pipelined (the next 32 columns are in flight while these are compared).
+//   * Epilogue: a thread owns ONE query; selection state in global memory (L2): the sorted list is the per-pair candidate
+//     array the tail merges anyway (cand_*, final units), the 32-entry candidate buffer is cbuf; shared memory is all
+//     ring.  The thread filters while it holds the accumulator and merges full buffers after releasing it; TMEM loads are software-pipelined (the next 32 columns are in flight while these are compared).
 //     Candidate lists per query = number of worker pairs (p.n_lists).  Shared bound: a CTA publishes its
 //     bound_rank-th best score (1 or 2), so that bound_rank * n_lists >= k documents are known to reach the bound.
 // Every wait has a watchdog (a few seconds of wall clock, then the error word is raised and the kernel traps):
@@ -2986,21 +2554,7 @@ static cudaError_t launch_fused_q(const SearchParams& p, int grid, cudaStream_t 
                       : launch_fused_t<NACC, REGLIST, false>(p, grid, stream);
 }
 
-int fused_wide_smem_bytes(int k) { return (int)make_wide_smem(k).total + 1024; }
-int fused_wide_tail_capacity(int k) { return (int)make_wide_smem(k).bar_off; }
-int fused_wide_slots() { return kWideSlots; }
 int fused_wide_bufc() { return kWideBufC; }
-
-static cudaError_t launch_fused_wide(const SearchParams& p, int grid, cudaStream_t stream) {
-  if (p.bpad != 256 || p.terms != 1 || p.planes != 1 || p.n_queries > 256 || p.k > kMaxListK || p.cbuf == nullptr ||
-      p.qstages < 2 || p.stages < 2 || p.qstages + p.stages != kWideSlots)
-    return cudaErrorInvalidValue;
-  const int bytes = fused_wide_smem_bytes(p.k);
-  cudaError_t e = cudaFuncSetAttribute(fused_search_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e != cudaSuccess) return e;
-  fused_search_wide_kernel<<<grid, kThreads, bytes, stream>>>(p);
-  return cudaGetLastError();
-}
 
 int fused_pair_smem_bytes(int k) { return (int)make_pair_smem(k).total + 1024; }
 int fused_pair_tail_capacity(int k) { return (int)make_pair_smem(k).bar_off; }
@@ -3098,8 +2652,7 @@ static cudaError_t launch_fused_dmpair(const SearchParams& p, int grid, cudaStre
 
 cudaError_t launch_fused_search(const SearchParams& p, int grid, cudaStream_t stream) {
   if (p.dmpair) return launch_fused_dmpair(p, grid, stream);
-  if (p.wide == 2) return launch_fused_pair(p, grid, stream);
-  if (p.wide) return launch_fused_wide(p, grid, stream);
+  if (p.wide) return launch_fused_pair(p, grid, stream);
   const bool reglist = p.k <= kRegK;
   const int nacc = (p.terms == 2 || p.planes == 2) ? 2 : 1;
   if (p.docm) {
