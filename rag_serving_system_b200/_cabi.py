@@ -29,7 +29,7 @@ ABI_VERSION = 2          # include/rs_retriever.h: RS_ABI_VERSION
 # switches of an index and their defaults (csrc/rs_api.cu: Options); rs_create reads the environment once
 OPTION_DEFAULTS = {
     "RS_DOCM": 1, "RS_INLINE_PREP": 1, "RS_FUSED_TAIL": 1, "RS_DYN_SCHED": 1, "RS_SHARED_BOUND": 1,
-    "RS_LISTS_GLOBAL": 1, "RS_QLO_STREAM": 0, "RS_GRAPH": 1, "RS_NO_EVENTS": 0, "RS_WIDE": 1, "RS_DMPAIR": 1, "RS_OVERLAP": 0,
+    "RS_LISTS_GLOBAL": 1, "RS_GRAPH": 1, "RS_NO_EVENTS": 0, "RS_WIDE": 1, "RS_DMPAIR": 1, "RS_OVERLAP": 0,
     "RS_DEBUG_FLAGS": 0, "RS_DEBUG_TS": 0, "RS_QRESIDENT": -1, "RS_CPS": 0, "RS_SUB": 0, "RS_BUFC": 0,
     "RS_LEAN": -1, "RS_MMA_M": 0, "RS_NBUF": 0, "RS_QSTAGES": 0,
 }

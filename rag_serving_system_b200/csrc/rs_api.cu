@@ -81,7 +81,6 @@ struct Options {
   int dyn_sched = 1;     // RS_DYN_SCHED    0: static round-robin tiles
   int shared_bound = 1;  // RS_SHARED_BOUND k > 16: 0 = no bound shared between CTAs
   int lists_global = 1;  // RS_LISTS_GLOBAL k > 16: 0 = sorted lists in shared memory
-  int qlo_stream = 0;    // RS_QLO_STREAM   two-term searches: 1/2 = stream the lo query term
   int graph = 1;         // RS_GRAPH        0: host-buffer searches enqueue eagerly instead of replaying a CUDA graph
   int no_events = 0;     // RS_NO_EVENTS    1: no CUDA events around the fused launch
   int dmpair = 1;        // RS_DMPAIR       1: doc-major searches with two accumulators, or 32 < B <= 64, run on CTA pairs (cta_group::2)
@@ -101,7 +100,7 @@ struct OptDef {
 const OptDef kOptDefs[] = {
     {"RS_DOCM", &Options::docm}, {"RS_INLINE_PREP", &Options::inline_prep}, {"RS_FUSED_TAIL", &Options::fused_tail},
     {"RS_DYN_SCHED", &Options::dyn_sched}, {"RS_SHARED_BOUND", &Options::shared_bound},
-    {"RS_LISTS_GLOBAL", &Options::lists_global}, {"RS_QLO_STREAM", &Options::qlo_stream}, {"RS_GRAPH", &Options::graph},
+    {"RS_LISTS_GLOBAL", &Options::lists_global}, {"RS_GRAPH", &Options::graph},
     {"RS_NO_EVENTS", &Options::no_events}, {"RS_WIDE", &Options::wide}, {"RS_DMPAIR", &Options::dmpair}, {"RS_OVERLAP", &Options::overlap}, {"RS_DEBUG_FLAGS", &Options::debug_flags},
     {"RS_DEBUG_TS", &Options::debug_ts}, {"RS_QRESIDENT", &Options::qresident}, {"RS_CPS", &Options::cps},
     {"RS_SUB", &Options::sub}, {"RS_BUFC", &Options::bufc}, {"RS_LEAN", &Options::lean}, {"RS_MMA_M", &Options::mma_m},
@@ -286,33 +285,6 @@ int make_plan(const rs_index* ix, const Options& o, int B, int k, int terms, Pla
   if (best_cost < 0) return fail(RS_E_UNSUPPORTED, "B=%d k=%d dim=%d does not fit in shared memory", B, k, ix->cfg.dim);
   pl->per_pass = (B + pl->passes - 1) / pl->passes;
   pl->bpad = (pl->per_pass + 7) / 8 * 8;
-  // Optional (RS_QLO_STREAM=1, or 2 to force it for any corpus size; default off): with two query terms and a
-  // resident Q, keep only the hi term resident and stream the lo term (one MMA chain uses it) through a ring.
-  // That halves the resident image (128 -> 64 KiB at B=32, D=1024) in favour of the document ring.  Measured on
-  // 1M x 1024 fp32: 0.775 -> 0.738 ms at B=32, but 0.665 -> 0.736 ms at B=16 and 0.625 -> 0.709 ms at B=1 (smaller
-  // ring stages, one more launch), so it stays an opt-in.
-  if (pl->q_resident == 1 && terms == 2 && o.qlo_stream != 0 && o.qresident != 1 &&
-      ((size_t)ix->corpus_bytes >= ((size_t)256 << 20) || o.qlo_stream == 2)) {  // 2: force (tests)
-    auto ring_bytes = [&](int mode, int cps) {
-      int st = std::max(2, (4 + cps - 1) / cps);
-      if (rs::fused_smem_bytes(pl->bpad, ix->kc, terms, st, cps, k, mode, qstages, pl->bufc, pl->lg) > kMaxSmem) return 0;
-      while (st < kMaxStages &&
-             rs::fused_smem_bytes(pl->bpad, ix->kc, terms, st + 1, cps, k, mode, qstages, pl->bufc, pl->lg) <= kMaxSmem)
-        ++st;
-      return st * cps * RS_BLOCK_BYTES;
-    };
-    const int have = ring_bytes(1, pl->cps);
-    for (int cps = 4; cps >= 1; cps >>= 1) {
-      if (ix->kc % cps != 0 || (o.cps && cps != o.cps)) continue;
-      const int got = ring_bytes(2, cps);
-      if (got > have) {
-        pl->q_resident = 2;
-        pl->cps = cps;
-        pl->stages = std::max(2, (4 + cps - 1) / cps);
-        break;
-      }
-    }
-  }
   pl->mma_m = o.mma_m ? o.mma_m : (pl->bpad <= 64 ? 64 : 128);
   if (pl->mma_m != 128 && !(pl->mma_m == 64 && pl->bpad <= 64)) return fail(RS_E_INVALID, "RS_MMA_M=%d invalid for bpad=%d", pl->mma_m, pl->bpad);
   // as many accumulator buffers as the 512 TMEM columns hold: the epilogue's start-up burst (every

@@ -311,13 +311,11 @@ struct SmemMap {
 // otherwise Q k-chunks travel through the ring next to the document blocks (large batches).
 __host__ __device__ inline SmemMap make_smem_map(int bpad, int kc, int terms, int stages, int cps, int k,
                                                  bool reglist, bool q_resident, int qstages, int bufc = kBufC,
-                                                 bool lists_global = false, bool lo_stream = false, bool docm = false) {
+                                                 bool lists_global = false, bool docm = false) {
   SmemMap m;
   // resident: the whole Q image; streamed: a private ring of qstages slots of cps k-chunks each
-  // lo_stream (resident mode, two query terms): only the hi term is resident, the lo term - used by one MMA
-  // chain instead of two - streams through a small ring, which halves the resident Q image
-  m.q_res_bytes = q_resident ? (uint32_t)(lo_stream ? 1 : terms) * kc * bpad * RS_KCHUNK_BYTES : 0u;
-  m.q_bytes = m.q_res_bytes + ((!q_resident || lo_stream) ? (uint32_t)qstages * cps * bpad * RS_KCHUNK_BYTES : 0u);
+  m.q_res_bytes = q_resident ? (uint32_t)terms * kc * bpad * RS_KCHUNK_BYTES : 0u;
+  m.q_bytes = m.q_res_bytes + (!q_resident ? (uint32_t)qstages * cps * bpad * RS_KCHUNK_BYTES : 0u);
   m.stage_off = m.q_bytes;  // multiple of 1024 because bpad % 8 == 0
   m.bar_off = m.stage_off + (uint32_t)stages * (uint32_t)cps * RS_BLOCK_BYTES;
   m.dump_off = m.bar_off + 2048;                       // [bar_off, +1 KiB) barriers, then qnorm[128], qscale[128];
@@ -1092,9 +1090,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr bool q_resident = QRES;
-  const bool lo_stream = QRES && p.q_resident == 2;  // hi term resident, lo term streamed (needs terms == 2, prep kernel)
   const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, q_resident, p.qstages, p.bufc,
-                                    p.lists_global != 0, lo_stream, DOCM);
+                                    p.lists_global != 0, DOCM);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t q_smem = smem_base;
   const uint32_t stage_smem = smem_base + map.stage_off;
@@ -1147,7 +1144,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const __grid_
       mbar_init(tempty_bar(a), nact_warps);
     }
     mbar_init(qfull_bar, inline_prep ? kNumEpiWarps : 1);
-    if (!q_resident || lo_stream)
+    if (!q_resident)
       for (int s = 0; s < p.qstages; ++s) {
         mbar_init(qring_full(s), 1);
         mbar_init(qring_empty(s), 1);
@@ -1240,7 +1237,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const __grid_
       for (int kc = 0; kc < p.kc; kc += cps) {
         if (!q_resident)
           for (int j = 0; j < p.terms; ++j) push_q(p.qimg + (size_t)(j * p.kc + kc) * qblk, cps * qblk);
-        if (lo_stream) push_q(p.qimg + (size_t)(p.kc + kc) * qblk, cps * qblk);
         for (int pl = 0; pl < p.planes; ++pl)
           for (int sub = 0; sub < nsub; ++sub)
             push(src + (size_t)sub * tile_bytes + (size_t)(pl * p.kc + kc) * RS_BLOCK_BYTES, stage_bytes, pol_stream);
@@ -1301,15 +1297,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const __grid_
           }
           qa0 = q_smem + (uint32_t)kc * qblk;
           qa1 = q_smem + (uint32_t)(p.kc + kc) * qblk;
-          if (lo_stream) {  // the lo term of this k-chunk group arrives through the Q ring
-            mbar_wait(qring_full(qs), qph);
-            qa1 = q_smem + map.q_res_bytes + (uint32_t)qs * (uint32_t)cps * qblk;
-            qslot1 = qs;
-            if (++qs == p.qstages) {
-              qs = 0;
-              qph ^= 1u;
-            }
-          }
         } else {
           mbar_wait(qring_full(qs), qph);
           qa0 = q_smem + (uint32_t)qs * (uint32_t)cps * qblk;
@@ -1357,7 +1344,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const __grid_
           umma_commit(qring_empty(qslot0));
           if (p.terms == 2) umma_commit(qring_empty(qslot1));
         }
-        if (lo_stream && lane == 0) umma_commit(qring_empty(qslot1));
       }
       q_pending = false;
       __syncwarp();
@@ -2420,7 +2406,7 @@ size_t fused_tail_smem_bytes(int n_lists, int k, int world) {
   return merge_res_bytes(k) + std::max((size_t)n_lists * k * 8, (size_t)world * k * 12);
 }
 int fused_tail_smem_capacity(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages) {
-  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages, kBufC, false, q_resident == 2)
+  return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages, kBufC, false)
       .bar_off;
 }
 
@@ -2519,7 +2505,7 @@ cudaError_t launch_query_prep(const float* q_dev, int B, int D, int bpad, int dt
 template <int NACC, bool REGLIST, bool QRES, bool DOCM = false>
 static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t stream) {
   const SmemMap map = make_smem_map(p.bpad, p.kc, p.terms, p.stages, p.cps, p.k, REGLIST, QRES, p.qstages, p.bufc,
-                                    p.lists_global != 0, QRES && p.q_resident == 2, DOCM);
+                                    p.lists_global != 0, DOCM);
   auto kern = fused_search_kernel<NACC, REGLIST, QRES, DOCM>;
   const int bytes = (int)map.total + 1024;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -2543,7 +2529,7 @@ static cudaError_t launch_fused_t(const SearchParams& p, int grid, cudaStream_t 
 int fused_smem_bytes(int bpad, int kc, int terms, int stages, int cps, int k, int q_resident, int qstages, int bufc,
                      int lists_global, int docm) {
   return (int)make_smem_map(bpad, kc, terms, stages, cps, k, k <= kRegK, q_resident != 0, qstages, bufc, lists_global != 0,
-                            q_resident == 2, docm != 0)
+                            docm != 0)
              .total + 1024;
 }
 int fused_reg_k() { return kRegK; }

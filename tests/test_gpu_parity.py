@@ -275,8 +275,6 @@ MODES = [
     {"RS_QRESIDENT": "1", "RS_SUB": "2", "RS_NBUF": "2"},
     # the multi-launch fallbacks of the single-launch search: separate query_prep_kernel / merge kernel
     {"RS_INLINE_PREP": "0"}, {"RS_FUSED_TAIL": "0"}, {"RS_INLINE_PREP": "0", "RS_FUSED_TAIL": "0"},
-    # two-term queries: hi term resident, lo term streamed (forced here; by default only for corpora >= 256 MB)
-    {"RS_QLO_STREAM": "2"}, {"RS_QLO_STREAM": "2", "RS_CPS": "1"}, {"RS_QLO_STREAM": "0"},
     # k > 16 state: lists in shared memory instead of global memory, no bound shared between CTAs
     {"RS_LISTS_GLOBAL": "0"}, {"RS_SHARED_BOUND": "0"}, {"RS_DYN_SCHED": "0"},
     # query-major kernel everywhere / doc-major kernel only for one-term 16-bit searches

@@ -43,7 +43,7 @@ class Power:
 
 
 def run(ix, q_dev, B, k, metric, terms, steps, env, label, out):
-    for key in ("RS_MMA_M", "RS_QRESIDENT", "RS_SUB", "RS_NBUF", "RS_CPS", "RS_INLINE_PREP", "RS_FUSED_TAIL", "RS_DEBUG_FLAGS", "RS_SHARED_BOUND", "RS_DOCM", "RS_QLO_STREAM", "RS_LISTS_GLOBAL", "RS_DYN_SCHED", "RS_BUFC", "RS_LEAN"):
+    for key in ("RS_MMA_M", "RS_QRESIDENT", "RS_SUB", "RS_NBUF", "RS_CPS", "RS_INLINE_PREP", "RS_FUSED_TAIL", "RS_DEBUG_FLAGS", "RS_SHARED_BOUND", "RS_DOCM", "RS_LISTS_GLOBAL", "RS_DYN_SCHED", "RS_BUFC", "RS_LEAN"):
         os.environ.pop(key, None)
     os.environ.update({k_: str(v) for k_, v in env.items()})
     ix.reload_env_options()
