@@ -177,9 +177,10 @@ RS_API int rs_xchg_attach(rs_xchg* x, rs_xchg* peer);
  * constructed once in one process - main.py:52-55 - drives when it owns several devices).  `shards` are n
  * indices on n DISTINCT devices holding consecutive row ranges (row_offset) of one corpus, with the same dim,
  * dtype, max_batch and max_k; the group does not own them (destroy the group first).  rs_group_search is
- * rs_search for the whole corpus: one pinned copy of the queries, H2D + ONE fused kernel per GPU (candidate
- * exchange and final merge inside the kernels, over NVLink peer memory), ONE D2H from the first shard's GPU;
- * the whole multi-device sequence is replayed from one CUDA graph from the second call of a shape on. */
+ * rs_search for the whole corpus: one pinned copy of the queries, then per GPU an H2D + ONE fused kernel (candidate
+ * exchange and final merge inside the kernels, over NVLink peer memory) issued in parallel - the calling thread drives
+ * the first shard, one worker thread per further shard (they sleep between bursts of calls) - and ONE D2H from the
+ * first shard's GPU; every shard's sequence is replayed from its own CUDA graph from the second call of a shape on. */
 typedef struct rs_group rs_group;
 RS_API int rs_group_create(rs_index** shards, int32_t n, rs_group** out);
 RS_API int rs_group_search(rs_group* g, const float* q_host, int32_t B, int32_t k, int32_t metric, int32_t query_terms,

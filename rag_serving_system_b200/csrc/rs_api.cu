@@ -11,6 +11,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -1020,26 +1022,145 @@ RS_API int rs_search_exchange_host(rs_index* ix, rs_xchg* x, const float* q_host
 
 // ---------------------------------------------------------------------------------------------------------
 // Single-process multi-GPU: what a service that constructs ONE retriever in ONE process gets (main.py:52-55).
-// The group owns one exchange buffer per shard (peer access inside the process) and drives every search from
-// the calling host thread: one pinned copy of the queries, an H2D + one fused kernel per GPU (the candidate
-// exchange and the final merge run inside those kernels, over NVLink), ONE D2H from the first GPU.  From the
-// second call of a shape on, the whole multi-device sequence is one captured CUDA graph = one launch call.
+// The group owns one exchange buffer per shard (peer access inside the process).  Per search: one pinned copy of the
+// queries, then every shard's launch sequence - H2D of the queries + ONE fused kernel (candidate exchange and final
+// merge inside the kernels, over NVLink), + the D2H of the result on shard 0 - is issued by the host thread that drives
+// that shard: the caller for shard 0, one worker thread per further shard, so the n launches go out in parallel
+// (issued from one thread, as one multi-device CUDA graph, they cost ~60 us more per call at 8 GPUs).  Each sequence is
+// replayed from its own single-device CUDA graph from the second call of a shape on.  The host waits on an event
+// recorded behind shard 0's D2H: shard 0 has every peer's candidates by then, so every peer has long read its queries.
+// Workers spin for a short while after a search (back-to-back calls find them awake), then sleep on a condition variable.
 // ---------------------------------------------------------------------------------------------------------
 struct rs_group {
   int n = 0;
   rs_index* ix[rs::kMaxPeers] = {};
   rs_xchg* xg[rs::kMaxPeers] = {};
-  cudaEvent_t fork = nullptr, join[rs::kMaxPeers] = {};
   cudaEvent_t done = nullptr;  // recorded right behind the D2H of the result on shard 0's stream: what the host waits for
   struct GraphEntry {
     int B, k, metric, terms, uses;
     cudaGraphExec_t exec;
   };
-  std::vector<GraphEntry> graphs;
-  unsigned live_epoch_sum = 0;  // sum of g_live_epoch over the shards' devices when the graphs were captured
+  std::vector<GraphEntry> graphs[rs::kMaxPeers];  // per shard, touched only by the thread that drives the shard
+  unsigned live_epoch_seen[rs::kMaxPeers] = {};
   int use_graph = 1;
-  std::mutex mu;
+  std::mutex mu;  // one search at a time
+  // the job of the current search (written by the caller before `gen` moves) and the workers' state
+  struct Job {
+    size_t q_bytes, n_out;
+    int B, k, metric, terms;
+  } job = {};
+  std::thread workers[rs::kMaxPeers];
+  std::atomic<unsigned long long> gen{0};
+  std::atomic<int> pending{0};
+  std::atomic<int> sleepers{0};
+  std::atomic<bool> stop{false};
+  std::mutex wmu;
+  std::condition_variable wcv;
+  int rc[rs::kMaxPeers] = {};
+  char err[rs::kMaxPeers][256] = {};
+  int spin_us = 500;
 };
+
+namespace {
+
+// One shard's launch sequence of the current job, issued by the thread that drives the shard.
+int group_launch_shard(rs_group* gr, int g) {
+  rs_index* ix = gr->ix[g];
+  rs_index* ix0 = gr->ix[0];
+  const rs_group::Job& jb = gr->job;
+  std::lock_guard<std::mutex> lock(ix->mu);
+  RS_CUDA(cudaSetDevice(ix->cfg.device));
+  int rc = take_device_error(ix, ix->stream);
+  if (rc == RS_OK) rc = order_after_previous(ix, ix->stream);
+  if (rc != RS_OK) return rc;
+  char* pin = static_cast<char*>(ix0->pinned);  // portable pinned memory: every GPU copies the queries from it
+  long long* pin_idx = reinterpret_cast<long long*>(pin + ((jb.q_bytes + 255) & ~size_t(255)));
+  auto enqueue = [&]() -> int {
+    RS_CUDA(cudaMemcpyAsync(ix->q_dev, pin, jb.q_bytes, cudaMemcpyHostToDevice, ix->stream));
+    float* score_dev = reinterpret_cast<float*>(ix->out_idx_dev + jb.n_out);
+    int r = search_device_locked(ix, ix->q_dev, jb.B, jb.k, jb.metric, jb.terms, ix->out_idx_dev, score_dev, ix->stream,
+                                 gr->n > 1 ? gr->xg[g] : nullptr);
+    if (r != RS_OK) return r;
+    if (g == 0) {
+      RS_CUDA(cudaMemcpyAsync(pin_idx, ix->out_idx_dev, jb.n_out * (sizeof(long long) + sizeof(float)), cudaMemcpyDeviceToHost,
+                              ix->stream));
+      if (ix->capturing) RS_CUDA(cudaEventRecordWithFlags(gr->done, ix->stream, cudaEventRecordExternal));
+      else RS_CUDA(cudaEventRecord(gr->done, ix->stream));
+    }
+    return RS_OK;
+  };
+  auto& graphs = gr->graphs[g];
+  if (ix->registered) {  // an index was created or destroyed on this device: the captured tail may be the wrong kind
+    const unsigned ep = g_live_epoch[ix->cfg.device].load();
+    if (ep != gr->live_epoch_seen[g]) {
+      for (auto& e : graphs)
+        if (e.exec) cudaGraphExecDestroy(e.exec);
+      graphs.clear();
+      gr->live_epoch_seen[g] = ep;
+    }
+  }
+  rs_group::GraphEntry* ge = nullptr;
+  if (gr->use_graph) {
+    for (auto& e : graphs)
+      if (e.B == jb.B && e.k == jb.k && e.metric == jb.metric && e.terms == jb.terms) ge = &e;
+    if (!ge && graphs.size() < 64) {
+      graphs.push_back({jb.B, jb.k, jb.metric, jb.terms, 0, nullptr});
+      ge = &graphs.back();
+    }
+  }
+  if (ge && !ge->exec && ge->uses >= 1) {  // second call with this shape: capture (the first, eager call validated everything)
+    ix->capturing = true;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(ix->stream, cudaStreamCaptureModeThreadLocal);
+    int crc = ce == cudaSuccess ? enqueue() : RS_E_CUDA;
+    cudaError_t ee = cudaStreamEndCapture(ix->stream, &graph);
+    ix->capturing = false;
+    if (crc == RS_OK && ee == cudaSuccess && graph && cudaGraphInstantiate(&ge->exec, graph, 0) != cudaSuccess) ge->exec = nullptr;
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (!ge->exec) ge->uses = -1000000;
+  }
+  if (ge && ge->exec) {
+    RS_CUDA(cudaGraphLaunch(ge->exec, ix->stream));
+    ix->stats.total_launches += ix->stats.launches;
+  } else {
+    rc = enqueue();
+    if (rc != RS_OK) return rc;
+    if (ge) ++ge->uses;
+  }
+  return RS_OK;
+}
+
+void group_worker(rs_group* gr, int g) {
+  unsigned long long seen = 0;
+  while (true) {
+    // wait for the next job: spin briefly (back-to-back searches), then sleep
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (gr->gen.load(std::memory_order_acquire) == seen && !gr->stop.load(std::memory_order_acquire)) {
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+      if ((++spins & 63u) == 0u &&
+          std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(gr->spin_us)) {
+        std::unique_lock<std::mutex> lk(gr->wmu);
+        gr->sleepers.fetch_add(1);
+        gr->wcv.wait(lk, [&] { return gr->gen.load(std::memory_order_acquire) != seen || gr->stop.load(std::memory_order_acquire); });
+        gr->sleepers.fetch_sub(1);
+      }
+    }
+    if (gr->stop.load(std::memory_order_acquire)) return;
+    seen = gr->gen.load(std::memory_order_acquire);
+    const int rc = group_launch_shard(gr, g);
+    gr->rc[g] = rc;
+    if (rc != RS_OK) snprintf(gr->err[g], sizeof(gr->err[g]), "%s", g_err);
+    gr->pending.fetch_sub(1, std::memory_order_release);
+  }
+}
+
+}  // namespace
+
+RS_API int rs_group_destroy(rs_group* gr);
 
 RS_API int rs_group_create(rs_index** shards, int32_t n, rs_group** out) {
   if (!shards || !out) return fail(RS_E_INVALID, "null argument");
@@ -1057,24 +1178,27 @@ RS_API int rs_group_create(rs_index** shards, int32_t n, rs_group** out) {
   if (!gr) return fail(RS_E_INVALID, "out of host memory");
   gr->n = n;
   gr->use_graph = shards[0]->opt.graph;
+  gr->spin_us = env_int("RS_GROUP_SPIN_US", 500);  // workers stay awake across back-to-back searches of up to half a millisecond
   int rc = RS_OK;
   for (int g = 0; g < n && rc == RS_OK; ++g) {
     gr->ix[g] = shards[g];
     rc = rs_xchg_create(shards[g]->cfg.device, n, g, shards[g]->cfg.max_batch, shards[g]->cfg.max_k, &gr->xg[g]);
-    if (rc == RS_OK && cudaEventCreateWithFlags(&gr->join[g], cudaEventDisableTiming) != cudaSuccess)
-      rc = fail(RS_E_CUDA, "event creation failed on device %d", shards[g]->cfg.device);
   }
   for (int g = 0; g < n && rc == RS_OK; ++g)
     for (int h = 0; h < n && rc == RS_OK; ++h) rc = rs_xchg_attach(gr->xg[g], gr->xg[h]);
   if (rc == RS_OK) {
     cudaSetDevice(shards[0]->cfg.device);
-    if (cudaEventCreateWithFlags(&gr->fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&gr->done, cudaEventDisableTiming) != cudaSuccess)
-      rc = fail(RS_E_CUDA, "event creation failed");
+    if (cudaEventCreateWithFlags(&gr->done, cudaEventDisableTiming) != cudaSuccess) rc = fail(RS_E_CUDA, "event creation failed");
   }
   if (rc != RS_OK) {
     rs_group_destroy(gr);
     return rc;
+  }
+  try {
+    for (int g = 1; g < n; ++g) gr->workers[g] = std::thread(group_worker, gr, g);
+  } catch (...) {
+    rs_group_destroy(gr);
+    return fail(RS_E_INVALID, "could not start the group's worker threads");
   }
   *out = gr;
   return RS_OK;
@@ -1082,19 +1206,22 @@ RS_API int rs_group_create(rs_index** shards, int32_t n, rs_group** out) {
 
 RS_API int rs_group_destroy(rs_group* gr) {
   if (!gr) return RS_OK;
-  for (auto& g : gr->graphs)
-    if (g.exec) cudaGraphExecDestroy(g.exec);
+  {
+    std::lock_guard<std::mutex> lk(gr->wmu);
+    gr->stop.store(true, std::memory_order_release);
+  }
+  gr->wcv.notify_all();
+  for (int g = 1; g < gr->n; ++g)
+    if (gr->workers[g].joinable()) gr->workers[g].join();
   for (int g = 0; g < gr->n; ++g) {
     if (gr->ix[g]) {
       cudaSetDevice(gr->ix[g]->cfg.device);
       cudaDeviceSynchronize();
     }
+    for (auto& e : gr->graphs[g])
+      if (e.exec) cudaGraphExecDestroy(e.exec);
   }
-  for (int g = 0; g < gr->n; ++g) {
-    if (gr->join[g]) cudaEventDestroy(gr->join[g]);
-    rs_xchg_destroy(gr->xg[g]);
-  }
-  if (gr->fork) cudaEventDestroy(gr->fork);
+  for (int g = 0; g < gr->n; ++g) rs_xchg_destroy(gr->xg[g]);
   if (gr->done) cudaEventDestroy(gr->done);
   delete gr;
   return RS_OK;
@@ -1104,100 +1231,52 @@ RS_API int rs_group_search(rs_group* gr, const float* q_host, int32_t B, int32_t
                            int64_t* out_idx, float* out_score) {
   if (!gr || !q_host || !out_idx || !out_score) return fail(RS_E_INVALID, "null argument");
   std::lock_guard<std::mutex> glock(gr->mu);
-  std::unique_lock<std::mutex> locks[rs::kMaxPeers];
-  for (int g = 0; g < gr->n; ++g) locks[g] = std::unique_lock<std::mutex>(gr->ix[g]->mu);
   rs_index* ix0 = gr->ix[0];
   if (B <= 0 || B > ix0->cfg.max_batch) return fail(RS_E_INVALID, "B=%d outside [1,%d]", B, ix0->cfg.max_batch);
   if (k <= 0 || k > ix0->cfg.max_k) return fail(RS_E_INVALID, "k=%d outside [1,%d]", k, ix0->cfg.max_k);
+  if (metric != RS_METRIC_DOT && metric != RS_METRIC_COSINE) return fail(RS_E_INVALID, "bad metric %d", metric);
   for (int g = 0; g < gr->n; ++g)
     if (!gr->ix[g]->finalized) return fail(RS_E_STATE, "rs_finalize has not been called on shard %d", g);
   if (ix0->planes == 2) query_terms = 2;
+  if (query_terms != 1 && query_terms != 2) return fail(RS_E_INVALID, "query_terms must be 1 or 2");
   const size_t q_bytes = (size_t)B * ix0->cfg.dim * sizeof(float);
   const size_t n_out = (size_t)B * k;
-  char* pin = static_cast<char*>(ix0->pinned);  // portable pinned memory: every GPU copies the queries from it
+  char* pin = static_cast<char*>(ix0->pinned);
   long long* pin_idx = reinterpret_cast<long long*>(pin + ((q_bytes + 255) & ~size_t(255)));
   float* pin_score = reinterpret_cast<float*>(pin_idx + n_out);
-  cudaStream_t s0 = ix0->stream;
-  auto enqueue = [&]() -> int {
-    RS_CUDA(cudaSetDevice(ix0->cfg.device));
-    RS_CUDA(cudaEventRecord(gr->fork, s0));
-    for (int g = 0; g < gr->n; ++g) {
-      rs_index* ix = gr->ix[g];
-      RS_CUDA(cudaSetDevice(ix->cfg.device));
-      if (g > 0) RS_CUDA(cudaStreamWaitEvent(ix->stream, gr->fork, 0));
-      RS_CUDA(cudaMemcpyAsync(ix->q_dev, pin, q_bytes, cudaMemcpyHostToDevice, ix->stream));
-      float* score_dev = reinterpret_cast<float*>(ix->out_idx_dev + n_out);
-      int rc = search_device_locked(ix, ix->q_dev, B, k, metric, query_terms, ix->out_idx_dev, score_dev, ix->stream,
-                                    gr->n > 1 ? gr->xg[g] : nullptr);
-      if (rc != RS_OK) return rc;
-      if (g > 0) {
-        RS_CUDA(cudaEventRecord(gr->join[g], ix->stream));
-      } else {
-        // The result leaves shard 0 as soon as ITS kernel is done (it has every peer's candidates by then, so every
-        // peer has long read its queries): the host waits for `done`, not for the other GPUs' kernels to retire.
-        RS_CUDA(cudaMemcpyAsync(pin_idx, ix0->out_idx_dev, n_out * (sizeof(long long) + sizeof(float)), cudaMemcpyDeviceToHost, s0));
-        if (ix0->capturing) RS_CUDA(cudaEventRecordWithFlags(gr->done, s0, cudaEventRecordExternal));
-        else RS_CUDA(cudaEventRecord(gr->done, s0));
-      }
-    }
-    RS_CUDA(cudaSetDevice(ix0->cfg.device));
-    for (int g = 1; g < gr->n; ++g) RS_CUDA(cudaStreamWaitEvent(s0, gr->join[g], 0));  // the next search starts after all of them
-    return RS_OK;
-  };
-  for (int g = 0; g < gr->n; ++g) {
-    rs_index* ix = gr->ix[g];
-    RS_CUDA(cudaSetDevice(ix->cfg.device));
-    int rc = take_device_error(ix, ix->stream);
-    if (rc == RS_OK) rc = order_after_previous(ix, ix->stream);
-    if (rc != RS_OK) return rc;
-  }
   memcpy(pin, q_host, q_bytes);
-  {  // an index was created or destroyed on one of the devices: the captured tails may be the wrong kind
-    unsigned ep = 0;
-    for (int g = 0; g < gr->n; ++g)
-      if (gr->ix[g]->registered) ep += g_live_epoch[gr->ix[g]->cfg.device].load();
-    if (ep != gr->live_epoch_sum) {
-      for (auto& g : gr->graphs)
-        if (g.exec) cudaGraphExecDestroy(g.exec);
-      gr->graphs.clear();
-      gr->live_epoch_sum = ep;
+  gr->job = {q_bytes, n_out, B, k, metric, query_terms};
+  // publish the job: the workers issue their shards' launches while this thread issues shard 0's
+  gr->pending.store(gr->n - 1, std::memory_order_relaxed);
+  {
+    // (the lock orders the generation bump against a worker that is just going to sleep)
+    std::lock_guard<std::mutex> lk(gr->wmu);
+    gr->gen.fetch_add(1, std::memory_order_release);
+  }
+  if (gr->sleepers.load() > 0) gr->wcv.notify_all();
+  gr->rc[0] = group_launch_shard(gr, 0);
+  if (gr->rc[0] != RS_OK) snprintf(gr->err[0], sizeof(gr->err[0]), "%s", g_err);
+  while (gr->pending.load(std::memory_order_acquire) != 0) {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  for (int g = 0; g < gr->n; ++g)
+    if (gr->rc[g] != RS_OK) {
+      // some shard's launch failed: drain what was issued (the kernels that did start give up on their own after
+      // the peer time-out), then report
+      for (int h = 0; h < gr->n; ++h) {
+        cudaSetDevice(gr->ix[h]->cfg.device);
+        cudaStreamSynchronize(gr->ix[h]->stream);
+      }
+      return fail(gr->rc[g], "shard %d: %s", g, gr->err[g]);
     }
-  }
-  rs_group::GraphEntry* ge = nullptr;
-  if (gr->use_graph) {
-    for (auto& g : gr->graphs)
-      if (g.B == B && g.k == k && g.metric == metric && g.terms == query_terms) ge = &g;
-    if (!ge && gr->graphs.size() < 64) {
-      gr->graphs.push_back({B, k, metric, query_terms, 0, nullptr});
-      ge = &gr->graphs.back();
-    }
-  }
-  if (ge && !ge->exec && ge->uses >= 1) {
-    for (int g = 0; g < gr->n; ++g) gr->ix[g]->capturing = true;
-    cudaGraph_t graph = nullptr;
-    cudaSetDevice(ix0->cfg.device);
-    cudaError_t ce = cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal);
-    int crc = ce == cudaSuccess ? enqueue() : RS_E_CUDA;
-    cudaSetDevice(ix0->cfg.device);
-    cudaError_t ee = cudaStreamEndCapture(s0, &graph);
-    for (int g = 0; g < gr->n; ++g) gr->ix[g]->capturing = false;
-    if (crc == RS_OK && ee == cudaSuccess && graph && cudaGraphInstantiate(&ge->exec, graph, 0) != cudaSuccess) ge->exec = nullptr;
-    if (graph) cudaGraphDestroy(graph);
-    cudaGetLastError();
-    if (!ge->exec) ge->uses = -1000000;
-  }
   RS_CUDA(cudaSetDevice(ix0->cfg.device));
-  if (ge && ge->exec) {
-    RS_CUDA(cudaGraphLaunch(ge->exec, s0));
-  } else {
-    int rc = enqueue();
-    if (rc != RS_OK) return rc;
-    if (ge) ++ge->uses;
-  }
   RS_CUDA(cudaEventSynchronize(gr->done));
   {  // shard 0 waited for every peer inside its kernel: a peer that never showed up raised shard 0's error word.  The
-     // peers' own error words are read at the start of the next call (their kernels may still be retiring).
-    int rc = take_device_error(ix0, s0);
+     // peers' own error words are read when their next launch is issued (their kernels may still be retiring).
+    std::lock_guard<std::mutex> lock(ix0->mu);
+    int rc = take_device_error(ix0, ix0->stream);
     if (rc != RS_OK) return rc;
   }
   memcpy(out_idx, pin_idx, n_out * sizeof(long long));
