@@ -1153,7 +1153,7 @@ void group_worker(rs_group* gr, int g) {
     seen = gr->gen.load(std::memory_order_acquire);
     const int rc = group_launch_shard(gr, g);
     gr->rc[g] = rc;
-    if (rc != RS_OK) snprintf(gr->err[g], sizeof(gr->err[g]), "%s", g_err);
+    if (rc != RS_OK) snprintf(gr->err[g], sizeof(gr->err[g]), "%.250s", g_err);
     gr->pending.fetch_sub(1, std::memory_order_release);
   }
 }
@@ -1255,7 +1255,7 @@ RS_API int rs_group_search(rs_group* gr, const float* q_host, int32_t B, int32_t
   }
   if (gr->sleepers.load() > 0) gr->wcv.notify_all();
   gr->rc[0] = group_launch_shard(gr, 0);
-  if (gr->rc[0] != RS_OK) snprintf(gr->err[0], sizeof(gr->err[0]), "%s", g_err);
+  if (gr->rc[0] != RS_OK) snprintf(gr->err[0], sizeof(gr->err[0]), "%.250s", g_err);
   while (gr->pending.load(std::memory_order_acquire) != 0) {
 #if defined(__x86_64__) || defined(__i386__)
     __builtin_ia32_pause();

@@ -489,7 +489,7 @@ __device__ __forceinline__ void select_rounds(Load load, int n_lists, int kc, in
                                               float* res_s, long long* res_i, int lane) {
   unsigned int ks[kMergeMaxOwn];
   unsigned long long ki[kMergeMaxOwn];
-  int head[kMergeMaxOwn];
+  int head[kMergeMaxOwn] = {};
   auto read_head = [&](int i) {
     const int l = lane + 32 * i;
     ks[i] = 0u;
