@@ -125,6 +125,12 @@ RS_API int rs_search(rs_index* ix, const float* q_host, int32_t B, int32_t k, in
  * reported by this asynchronous call: it surfaces from rs_check, or from the next search call. */
 RS_API int rs_search_device(rs_index* ix, const float* q_dev, int32_t B, int32_t k, int32_t metric, int32_t query_terms,
                      int64_t* out_idx_dev, float* out_score_dev, void* stream);
+/* Query hand-off from the embedder.  Replaces `outputs.last_hidden_state.mean(dim=1)` followed by
+ * `.cpu().numpy()` (batch_processor.py:91-92) and the H2D copy that rs_search would do: mean over ALL T positions of
+ * hidden [B][T][D] (RS_DTYPE_FP32 / FP16 / BF16, contiguous, on `device`) into the fp32 query buffer out_q_dev [B][D],
+ * asynchronous on `stream`; rs_search_device on the same stream then consumes it with no host round trip. */
+RS_API int rs_pool_mean_device(int32_t device, const void* hidden_dev, int32_t src_dtype, int32_t B, int32_t T, int32_t D,
+                        float* out_q_dev, void* stream);
 /* RS_OK, or RS_E_CUDA if a kernel of an earlier asynchronous search raised the error word (and clears it).
  * Call after synchronising the stream.  rs_search and the other host-buffer calls check it themselves and
  * fail the call whose result is affected. */

@@ -23,7 +23,7 @@ EXPORTS = (
     "rs_debug_plan", "rs_debug_timestamps", "rs_xchg_create", "rs_xchg_export", "rs_xchg_import", "rs_xchg_attach",
     "rs_xchg_destroy", "rs_search_exchange", "rs_search_exchange_host", "rs_check", "rs_set_option",
     "rs_get_rows_device", "rs_group_create", "rs_group_search", "rs_group_destroy",
-    "rs_docs_create", "rs_docs_destroy", "rs_docs_join",
+    "rs_docs_create", "rs_docs_destroy", "rs_docs_join", "rs_pool_mean_device",
 )
 ABI_VERSION = 2          # include/rs_retriever.h: RS_ABI_VERSION
 # switches of an index and their defaults (csrc/rs_api.cu: Options); rs_create reads the environment once
@@ -112,6 +112,7 @@ def load() -> C.CDLL:
         "rs_docs_create": [vp, vp, i64, C.POINTER(vp)],
         "rs_docs_destroy": [vp],
         "rs_docs_join": [vp, vp, i32, i32, vp, C.c_char_p, i32, vp, i64, vp, vp],
+        "rs_pool_mean_device": [i32, vp, i32, i32, i32, i32, vp, vp],
         "rs_get_rows": [vp, i64, i64, vp],
         "rs_get_norms": [vp, i64, i64, vp],
         "rs_get_image": [vp, i64, i64, vp],
@@ -318,6 +319,11 @@ class Group:
             self.h = None
 
     __del__ = close
+
+
+def pool_mean_device(device: int, hidden_ptr: int, src_dtype: str, B: int, T: int, D: int, out_ptr: int, stream: int = 0):
+    """Mean over the T positions of hidden [B,T,D] on `device` into fp32 [B,D], asynchronous on `stream` (rs_pool_mean_device)."""
+    check(load().rs_pool_mean_device(device, hidden_ptr, DTYPES[src_dtype], B, T, D, out_ptr, stream), "rs_pool_mean_device")
 
 
 class DocArena:

@@ -882,6 +882,16 @@ RS_API int rs_search(rs_index* ix, const float* q_host, int32_t B, int32_t k, in
   return search_host_locked(ix, nullptr, q_host, B, k, metric, query_terms, reinterpret_cast<long long*>(out_idx), out_score);
 }
 
+RS_API int rs_pool_mean_device(int32_t device, const void* hidden_dev, int32_t src_dtype, int32_t B, int32_t T, int32_t D,
+                               float* out_q_dev, void* stream) {
+  if (!hidden_dev || !out_q_dev) return fail(RS_E_INVALID, "null argument");
+  if (B <= 0 || T <= 0 || D <= 0) return fail(RS_E_INVALID, "bad shape B=%d T=%d D=%d", B, T, D);
+  if (src_dtype < RS_DTYPE_BF16 || src_dtype > RS_DTYPE_FP32) return fail(RS_E_INVALID, "bad dtype %d", src_dtype);
+  RS_CUDA(cudaSetDevice(device));
+  RS_CUDA(rs::launch_mean_pool(hidden_dev, src_dtype, B, T, D, out_q_dev, static_cast<cudaStream_t>(stream)));
+  return RS_OK;
+}
+
 RS_API int rs_check(rs_index* ix) {
   if (!ix) return fail(RS_E_INVALID, "null argument");
   std::lock_guard<std::mutex> lock(ix->mu);

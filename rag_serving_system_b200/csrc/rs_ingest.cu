@@ -3,6 +3,8 @@
 // are computed once), the inverse transform (used by tests and the CPU-baseline sampler) and the
 // on-device synthetic corpus generator (bit-identical to oracle/retrieval_oracle.py:synth_rows).
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -227,6 +229,44 @@ cudaError_t launch_synth_fill(unsigned long long seed, long long global_row0, lo
 cudaError_t launch_tile_minmax(const float* dnorm, int n_rows, int n_tiles, float2* minmax, cudaStream_t stream) {
   if (n_tiles <= 0) return cudaSuccess;
   tile_minmax_kernel<<<(n_tiles + 3) / 4, 128, 0, stream>>>(dnorm, n_rows, n_tiles, minmax);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Query hand-off from the embedder: batch_processor.py:89-92 mean-pools the last hidden state on the GPU,
+// copies it to the host and hands NumPy to the retriever, which copies it back.  This kernel does the pooling
+// (`outputs.last_hidden_state.mean(dim=1)`: a plain mean over ALL T positions, padding included, as the reference
+// computes it) straight into the fp32 query buffer a device-buffer search reads, on the caller's stream.
+// One thread per (query, column): T coalesced reads, fp32 accumulation in position order.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float pool_load(const T* p);
+template <>
+__device__ __forceinline__ float pool_load<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float pool_load<__half>(const __half* p) { return __half2float(*p); }
+template <>
+__device__ __forceinline__ float pool_load<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) mean_pool_kernel(const T* __restrict__ hidden, int T_len, int D, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const T* src = hidden + (size_t)b * T_len * D + d;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int t = 0; t < T_len; ++t) acc += pool_load<T>(src + (size_t)t * D);
+  out[(size_t)b * D + d] = acc / (float)T_len;
+}
+
+cudaError_t launch_mean_pool(const void* hidden_dev, int src_dtype, int B, int T_len, int D, float* out_dev, cudaStream_t stream) {
+  if (B <= 0 || T_len <= 0 || D <= 0) return cudaErrorInvalidValue;
+  const dim3 grid((unsigned)((D + 255) / 256), (unsigned)B);
+  if (src_dtype == RS_DTYPE_FP32) mean_pool_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(hidden_dev), T_len, D, out_dev);
+  else if (src_dtype == RS_DTYPE_FP16) mean_pool_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(hidden_dev), T_len, D, out_dev);
+  else if (src_dtype == RS_DTYPE_BF16) mean_pool_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(hidden_dev), T_len, D, out_dev);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

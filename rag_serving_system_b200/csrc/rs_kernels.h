@@ -115,6 +115,8 @@ cudaError_t launch_untile_rows(const uint8_t* corpus, long long row0, int nrows,
                                float* out_rows_dev, cudaStream_t stream);
 cudaError_t launch_synth_fill(unsigned long long seed, long long global_row0, long long local_row0, int nrows, int D,
                               int dtype, int scale_exp, uint8_t* corpus, float* dnorm, cudaStream_t stream);
+// mean over the T positions of hidden [B][T][D] (fp32 / fp16 / bf16) -> out [B][D] fp32 (batch_processor.py:91)
+cudaError_t launch_mean_pool(const void* hidden_dev, int src_dtype, int B, int T_len, int D, float* out_dev, cudaStream_t stream);
 cudaError_t launch_tile_minmax(const float* dnorm, int n_rows, int n_tiles, float2* minmax, cudaStream_t stream);
 
 }  // namespace rs

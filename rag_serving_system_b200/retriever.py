@@ -233,6 +233,34 @@ class B200Retriever:
                              torch.cuda.current_stream(q.device).cuda_stream)
         return oi, os_
 
+    def search_hidden_states(self, last_hidden_state, k: int, metric: Optional[str] = None):
+        """batch_processor.py:89-97 without the host round trip: ``last_hidden_state`` is the embedder's output, a CUDA
+        tensor [B, T, D] (fp32 / fp16 / bf16) on the index's device.  The mean over the sequence
+        (``.mean(dim=1)``, batch_processor.py:91) is taken by ``rs_pool_mean_device`` straight into the query buffer and
+        the search follows on torch's current stream; returns CUDA tensors (indices int64[B,k], scores float32[B,k],
+        pooled queries float32[B,D])."""
+        import torch
+        if len(self._shards) != 1:
+            raise ValueError("search_hidden_states drives a single-device index")
+        ix = self._shards[0]
+        h = last_hidden_state
+        if not h.is_cuda or h.device.index != ix.device or h.dim() != 3 or h.shape[2] != self.D:
+            raise ValueError(f"last_hidden_state must be a CUDA tensor [B, T, {self.D}] on cuda:{ix.device}")
+        src = {torch.float32: "fp32", torch.float16: "fp16", torch.bfloat16: "bf16"}[h.dtype]
+        h = h.contiguous()
+        B, T = int(h.shape[0]), int(h.shape[1])
+        if B > self._max_batch or k > self._max_k or k <= 0 or B <= 0 or T <= 0:
+            raise ValueError("B / k outside the limits given at construction")
+        stream = torch.cuda.current_stream(h.device).cuda_stream
+        q = torch.empty((B, self.D), dtype=torch.float32, device=h.device)
+        _cabi.pool_mean_device(ix.device, h.data_ptr(), src, B, T, self.D, q.data_ptr(), stream)
+        terms = self._query_terms or 2       # pooled fp32 values are not representable in a 16-bit storage type
+        oi = torch.empty((B, k), dtype=torch.int64, device=h.device)
+        os_ = torch.empty((B, k), dtype=torch.float32, device=h.device)
+        with self._lock:
+            ix.search_device(q.data_ptr(), B, k, oi.data_ptr(), os_.data_ptr(), metric or self._metric, terms, stream)
+        return oi, os_, q
+
     def retrieve_with_scores(self, queries: np.ndarray, k: int):
         """north_star triple: (indices, scores, contexts)."""
         idx, sc = self.search(queries, k)

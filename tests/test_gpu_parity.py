@@ -701,6 +701,32 @@ def test_doc_major_pair_kernel(dtype, terms, metric, B, k, N):
         ix.close()
 
 
+@pytest.mark.parametrize("hdtype", ["float32", "bfloat16", "float16"])
+def test_hidden_state_handoff_mean_pool(squad, hdtype):
+    """search_hidden_states: the embedder's [B, T, D] CUDA tensor is mean-pooled over T by
+    rs_pool_mean_device (batch_processor.py:91: a plain mean over all positions) into the query buffer and searched on
+    the same stream; pooled queries == torch's fp32 mean, results == the oracle on those queries == what the host
+    path (batch_processor.py:92-97: .cpu().numpy() -> batch_retrieve) returns for them."""
+    import torch
+    r = CupyRetriever(squad.E, squad.contexts)
+    try:
+        g = torch.Generator().manual_seed(1)
+        B, T = 16, 37
+        base = torch.from_numpy(squad.Q[:B]).float()
+        h = (base[:, None, :] + 0.3 * torch.randn(B, T, 1024, generator=g)).to(getattr(torch, hdtype)).cuda()
+        idx, sc, q = r.search_hidden_states(h, squad.k)
+        torch.cuda.synchronize()
+        want = h.float().mean(dim=1)
+        assert torch.allclose(q, want, rtol=1e-5, atol=1e-6)
+        qn = q.cpu().numpy()
+        S = o.scores_cosine(qn.astype(np.float64), o.stored_values(squad.E, o.DTYPE_FP32), accum=np.float64)
+        o.check_topk(idx.cpu().numpy(), sc.cpu().numpy(), S, squad.k, rtol=1e-5, atol=1e-7)
+        hi, hs = r.search(qn, squad.k)
+        assert np.array_equal(hi, idx.cpu().numpy()) and np.allclose(hs, sc.cpu().numpy(), rtol=1e-6)
+    finally:
+        r.close()
+
+
 def test_two_indexes_on_one_device_searched_concurrently(squad):
     """SimpleRetriever + CupyRetriever in one service process (or two indexes searched from two threads): while a second
     index lives on the device every search uses the separate merge launch instead of the in-kernel tail (whose CTAs
