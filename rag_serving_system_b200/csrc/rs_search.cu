@@ -345,7 +345,10 @@ __device__ __forceinline__ float max32(const float (&v)[32]) {
 __device__ __forceinline__ float cosine_raw_bound(float thr_cos, float nq, float inv_qs, float ndmin, float ndmax) {
   if (thr_cos == -CUDART_INF_F) return -CUDART_INF_F;
   if (thr_cos >= 0.f) return thr_cos * nq * ndmin * inv_qs * (1.0f - 1e-6f);
-  return thr_cos * (nq * ndmax + 1e-8f) * inv_qs * (1.0f + 1e-6f);
+  // negative threshold: the product may underflow to -0 (zero query, a threshold just below 0 from the shared bound),
+  // which a raw score of 0 does not beat although its cosine (0) beats the threshold: stay strictly negative
+  const float r = thr_cos * (nq * ndmax + 1e-8f) * inv_qs * (1.0f + 1e-6f);
+  return r < 0.f ? r : -1.17549435e-38f;
 }
 
 // k > kRegK selection state (per query one shared-memory row of list_row_words() words, odd stride):
@@ -1466,6 +1469,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const __grid_
       const bool shared_bound = !REGLIST && p.g_best != nullptr && worker;
       float best_seen = -CUDART_INF_F, gbound = -CUDART_INF_F;
       int tiles_done = 0, next_refresh = 1;
+      bool sampled = false;  // the sample pass over this CTA's first accumulator has run
 
       int acc = 0;
       uint32_t acc_ph = 0;
@@ -1484,7 +1488,72 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const __grid_
         const int nsub = min(S, p.n_tiles - u * S);
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
-        if (shared_bound && tiles_done >= next_refresh) {  // after 1, 2, 4, ... tiles, then every 64
+        if (shared_bound && !sampled) {
+          // ---- sample pass over the CTA's FIRST accumulator (as in the pair kernel): before a query has k candidates its
+          // own k-th best filters nothing, so every document of the first tiles would be appended and merged - at a
+          // 1.25M-row shard (66 tiles per CTA) that start-up cost made k = 100 searches 1.9x (B = 32) to 2.7x (B = 128)
+          // slower than k = 10 ones.  Pass A only tracks the query's best score and publishes it; once every CTA has
+          // published, the filter below runs against a bound that already rejects almost everything.
+          sampled = true;
+          if (!(p.debug_flags & 2)) {
+            for (int sub = 0; sub < nsub; ++sub) {
+              const uint32_t tacc = lane_base + (uint32_t)((acc * S + sub) * NACC) * RS_TILE_ROWS;
+              const int tile_row0 = (u * S + sub) * RS_TILE_ROWS;
+#pragma unroll 1
+              for (int c0 = 0; c0 < RS_TILE_ROWS; c0 += 32) {
+                uint32_t r0[32];
+                tmem_ld_x32(tacc + c0, r0);
+                float v[32];
+                if (NACC == 2) {
+                  uint32_t r1[32];
+                  tmem_ld_x32(tacc + RS_TILE_ROWS + c0, r1);
+                  tmem_wait_ld();
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r1[j]), lo_coef, __uint_as_float(r0[j]));
+                } else {
+                  tmem_wait_ld();
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+                }
+                const int valid = p.n_rows - (tile_row0 + c0);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  float x = v[j];
+                  if (cosine) {
+                    const float nd = p.dnorm[min(tile_row0 + c0 + j, p.n_rows - 1)];
+                    const float denom = __fadd_rn(__fmul_rn(nq, nd), 1e-8f);  // retriever.py:605,607
+                    x = fminf(fmaxf(__fdiv_rn(x * qs, denom), -1.0f), 1.0f);   // retriever.py:609
+                  }
+                  if (j >= valid) x = -CUDART_INF_F;  // padded rows of a ragged last tile
+                  best_seen = fmaxf(best_seen, x);
+                }
+              }
+            }
+          }
+          if (live) {
+            __stcg(p.g_best + (size_t)blockIdx.x * p.bpad + row, best_seen);  // -inf: nothing to offer
+            unsigned int polls = 0;
+            unsigned long long t0 = 0;
+            while (true) {
+              bool all = true;
+#pragma unroll 8
+              for (int c = 0; c < p.n_work; ++c) {
+                const float v = __ldcg(p.g_best + (size_t)c * p.bpad + row);
+                all = all && (v == v);
+              }
+              if (all) break;
+              __nanosleep(100);
+              if ((++polls & 0xffu) == 0u) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                if (now - t0 > 2000000000ull) break;  // 2 s: a CTA of this grid is not running; go on without the bound
+              }
+            }
+          }
+          next_refresh = 0;  // read the bound right away
+        }
+        if (shared_bound && tiles_done >= next_refresh) {  // after the sample, then after 1, 2, 4, ... tiles, then every 64
           next_refresh = tiles_done < 64 ? 2 * tiles_done : tiles_done + 64;
           float mn = CUDART_INF_F;
           if (live) {
@@ -1618,6 +1687,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_search_kernel(const __grid_
         }
       }
 
+      // a worker CTA that got no tile at all still owes the other CTAs' sample pass its entry (-inf: nothing to offer)
+      if (shared_bound && !sampled && live) __stcg(p.g_best + (size_t)blockIdx.x * p.bpad + row, -CUDART_INF_F);
       if (!REGLIST) {  // drain the partially filled buffers
         uint32_t rem = __ballot_sync(0xffffffffu, cnt > 0);
         while (rem) {

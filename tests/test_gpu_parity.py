@@ -396,6 +396,12 @@ def test_shared_bound_keeps_ties_at_the_bound():
         for metric in ("dot", "cosine"):
             idx, sc, _ = run_case(E, Q, k, "bf16", metric, 1, exact_idx=True)
             assert (idx == np.arange(k)).all()
+    # the same through the wide-batch (CTA-pair) kernel, whose sample pass applies the bound before anything is appended:
+    # a zero query's cosine threshold sits just below 0 and its raw-score bound must not underflow to -0
+    Qw = np.concatenate([Q, np.tile(E[0], (150, 1)) * np.linspace(0.5, 2.0, 150, dtype=np.float32)[:, None]])
+    for metric in ("dot", "cosine"):
+        idx, sc, _ = run_case(E, Qw, 17, "bf16", metric, 1, exact_idx=True)
+        assert (idx == np.arange(17)).all()
     rng = np.random.default_rng(3)
     E2 = o.synth_rows(33, np.arange(N), 256)
     hot = 128 * 177                                            # one tile holds 120 near-copies of the query
