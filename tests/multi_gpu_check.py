@@ -24,10 +24,14 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     N, D = 100_003, 1024                       # uneven shards
     ok = True
-    for dtype, metric, k, B, exch in (("bf16", "dot", 10, 32, "p2p"), ("bf16", "dot", 10, 32, "nccl"),
-                                      ("fp32", "cosine", 5, 7, "p2p"), ("fp16", "dot", 100, 3, "nccl"),
-                                      ("bf16", "dot", 17, 100, "p2p"), ("fp16", "dot", 100, 256, "p2p"),
-                                      ("fp16", "cosine", 100, 256, "p2p")):
+    # (dtype, metric, k, B, exchange, RS_DMPAIR): the last two run the doc-major CTA-pair kernel (forced onto these small
+    # shards) with the exchange in its tail - fp32 storage (two accumulators) and 32 < B <= 64 (N = 64)
+    for dtype, metric, k, B, exch, dmpair in (("bf16", "dot", 10, 32, "p2p", 1), ("bf16", "dot", 10, 32, "nccl", 1),
+                                              ("fp32", "cosine", 5, 7, "p2p", 1), ("fp16", "dot", 100, 3, "nccl", 1),
+                                              ("bf16", "dot", 17, 100, "p2p", 1), ("fp16", "dot", 100, 256, "p2p", 1),
+                                              ("fp16", "cosine", 100, 256, "p2p", 1), ("fp32", "cosine", 10, 32, "p2p", 2),
+                                              ("bf16", "dot", 16, 64, "p2p", 2)):
+        os.environ["RS_DMPAIR"] = str(dmpair)       # read once, by rs_create
         s = ShardedSearcher(N, D, dtype, max_batch=256, max_k=128, scale_exp=4 if dtype == "fp32" else 0,
                             exchange=exch)
         s.fill_synthetic(1234)
@@ -38,6 +42,7 @@ def main():
             idx, sc = s.search(q_dev, k, metric, terms)
         torch.cuda.synchronize()
         s.index.check()
+        assert (s.index.stats()["mma_m"] == 256) == (dmpair == 2 or B > 128), s.index.stats()   # the CTA-pair kernels ran where meant
         idx, sc = idx.cpu().numpy(), sc.cpu().numpy()
         # host-buffer call (C ABI, CUDA-graph replay from the 2nd call on); only rank 0 asks for the result
         for _ in range(3):

@@ -24,8 +24,8 @@ def test_sharded_search_under_torchrun():
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert res.stdout.count("multi-gpu ok") == 7
-    assert res.stdout.count("overlapped launches ok") == 5        # every p2p case also runs with RS_OVERLAP=1
+    assert res.stdout.count("multi-gpu ok") == 9
+    assert res.stdout.count("overlapped launches ok") == 7        # every p2p case also runs with RS_OVERLAP=1
 
 
 def test_single_process_multi_device_class(squad):
